@@ -1,0 +1,128 @@
+// common.cuh -- shared plumbing for libdopt_b200.so (errors, registry, launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+
+#include "../../include/dopt_b200.h"
+
+namespace db {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+void set_last_error(const std::string& s);
+
+#define DB_REQUIRE(cond, msg)                                                                         \
+    do {                                                                                              \
+        if (!(cond)) throw db::Error(std::string(msg) + " [" #cond "] at " __FILE__ ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define DB_CUDA(expr)                                                                                 \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            throw db::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " in " #expr " at " __FILE__ ":" + \
+                            std::to_string(__LINE__));                                                \
+    } while (0)
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// Post-launch check (cheap: only reads the sticky launch error, no sync).
+#define DB_LAUNCH_CHECK()                                                                             \
+    do {                                                                                              \
+        db::count_launch();                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                          \
+        if (_e != cudaSuccess)                                                                        \
+            throw db::Error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " at " __FILE__ ":" + \
+                            std::to_string(__LINE__));                                                \
+    } while (0)
+
+int sm_count();                 // SMs of the current device (148 on B200)
+void require_device();          // throws unless an sm_100 device is current
+
+inline int64_t volume(const dopt_b200_tensor& t) {
+    int64_t v = 1;
+    for (int i = 0; i < t.rank; ++i) v *= t.shape[i];
+    return v;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid size for a grid-stride streaming kernel: enough CTAs to fill every SM `waves` times over, never more than needed.
+inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
+    int64_t need = ceil_div(work_items, threads);
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// A kernel object == dopt's CUDAKernel (cuda/source/dopt/cuda/package.d:68-79).
+struct Kernel {
+    virtual ~Kernel() {}
+    virtual void run(const void* const* in, int n_in, void* out, cudaStream_t s) = 0;
+};
+using Factory = Kernel* (*)(const dopt_b200_op&);
+void register_kernel(const char* op_type, Factory f);   // == registerCUDAKernel (package.d:479-485)
+Factory find_kernel(const char* op_type);
+int resolve_math(int math);
+
+// registration entry points, one per translation unit (== dopt.cuda.{math,basic,nnet,random}.initialize)
+void register_pointwise();
+void register_basic();
+void register_reduce();
+void register_matmul();
+void register_nnet();
+void register_batchnorm();
+void register_conv();
+void register_random();
+
+// small device scratch that lives for the process (workspaces, packed weights); grows on demand.
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    void* get(size_t need);
+    ~Scratch();
+};
+
+}  // namespace db
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+namespace dbk {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming (read-once) 128-bit load / store: keep them out of L1
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace dbk

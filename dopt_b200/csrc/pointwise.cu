@@ -1,0 +1,165 @@
+// pointwise.cu -- the 19 elementwise ops of dopt.cuda.math (cuda/source/dopt/cuda/math.d:79-207).
+//
+// Reference: one NVRTC template `out[i] = a[i] OP b[i]` / `out[i] = f(a[i])`, T in {float,int}, 512 threads, scalar 4-byte
+// accesses, cuCtxSynchronize after every launch (math.d:129-170,199-201; nvrtc.d:111).
+// Here: one grid-stride kernel per (op, T), 128-bit loads/stores, 4 independent vectors in flight per thread, no sync.
+// Semantics are those of the CUDA C expressions the reference compiles:
+//   comparisons yield T(0/1); sgn = (0<a)-(a<0); max/min/pow/abs/exp/log/sqrt resolve to the CUDA math overloads
+//   (float: fmaxf/fminf/powf/fabsf/expf/logf/sqrtf, full precision; int: integer max/min/abs, and pow/exp/log/sqrt
+//   through double with a truncating conversion back to int).
+// HBM-bound: 2V*4 B (unary) or 3V*4 B (binary) per launch.
+#include "common.cuh"
+#include "pointwise.cuh"
+
+namespace db {
+
+template <int OP, typename T, int BMODE>
+__global__ void __launch_bounds__(256) pw_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o,
+                                                 int64_t n) {
+    using V = typename dbk::Vec4<T>::type;
+    const int64_t nvec = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    T sa = T(0), sb = T(0);
+    if (BMODE == dbk::B_SCALAR_A) sa = a[0];
+    if (BMODE == dbk::B_SCALAR_B) sb = b[0];
+    const V* av = reinterpret_cast<const V*>(a);
+    const V* bv = reinterpret_cast<const V*>(b);
+    V* ov = reinterpret_cast<V*>(o);
+    constexpr int U = 4;
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        V x[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (BMODE != dbk::B_SCALAR_A) x[u] = dbk::ldv(av + i + u * stride);
+            if (BMODE == dbk::B_TENSOR) y[u] = dbk::ldv(bv + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            V r;
+            r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].x, BMODE == dbk::B_TENSOR ? y[u].x : sb);
+            r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].y, BMODE == dbk::B_TENSOR ? y[u].y : sb);
+            r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].z, BMODE == dbk::B_TENSOR ? y[u].z : sb);
+            r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].w, BMODE == dbk::B_TENSOR ? y[u].w : sb);
+            dbk::stv(ov + i + u * stride, r);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        V x, y, r;
+        if (BMODE != dbk::B_SCALAR_A) x = dbk::ldv(av + i);
+        if (BMODE == dbk::B_TENSOR) y = dbk::ldv(bv + i);
+        r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.x, BMODE == dbk::B_TENSOR ? y.x : sb);
+        r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.y, BMODE == dbk::B_TENSOR ? y.y : sb);
+        r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.z, BMODE == dbk::B_TENSOR ? y.z : sb);
+        r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.w, BMODE == dbk::B_TENSOR ? y.w : sb);
+        dbk::stv(ov + i, r);
+    }
+    // scalar tail (n % 4 elements)
+    int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        T x = BMODE == dbk::B_SCALAR_A ? sa : a[t];
+        T y = BMODE == dbk::B_TENSOR ? b[t] : sb;
+        o[t] = dbk::apply<OP, T>(x, y);
+    }
+}
+
+// unaligned fallback (sub-buffers at odd offsets): scalar accesses
+template <int OP, typename T, int BMODE>
+__global__ void __launch_bounds__(256) pw_kernel_scalar(const T* __restrict__ a, const T* __restrict__ b,
+                                                        T* __restrict__ o, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    T sa = T(0), sb = T(0);
+    if (BMODE == dbk::B_SCALAR_A) sa = a[0];
+    if (BMODE == dbk::B_SCALAR_B) sb = b[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T x = BMODE == dbk::B_SCALAR_A ? sa : a[i];
+        T y = BMODE == dbk::B_TENSOR ? b[i] : sb;
+        o[i] = dbk::apply<OP, T>(x, y);
+    }
+}
+
+template <int OP, typename T, int BMODE>
+static void launch_pw(const void* a, const void* b, void* o, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    bool aligned = ((uintptr_t)o % 16 == 0) && (BMODE == dbk::B_SCALAR_A || (uintptr_t)a % 16 == 0) &&
+                   (BMODE != dbk::B_TENSOR || (uintptr_t)b % 16 == 0);
+    if (aligned) {
+        int grid = stream_grid(ceil_div(n, 16), 256, 8);   // 4 vectors of 4 per thread per trip
+        pw_kernel<OP, T, BMODE><<<grid, 256, 0, s>>>((const T*)a, (const T*)b, (T*)o, n);
+    } else {
+        int grid = stream_grid(n, 256, 16);
+        pw_kernel_scalar<OP, T, BMODE><<<grid, 256, 0, s>>>((const T*)a, (const T*)b, (T*)o, n);
+    }
+    DB_LAUNCH_CHECK();
+}
+
+template <int OP, typename T>
+static void launch_pw_mode(int bmode, const void* a, const void* b, void* o, int64_t n, cudaStream_t s) {
+    switch (bmode) {
+        case dbk::B_TENSOR: launch_pw<OP, T, dbk::B_TENSOR>(a, b, o, n, s); break;
+        case dbk::B_SCALAR_B: launch_pw<OP, T, dbk::B_SCALAR_B>(a, b, o, n, s); break;
+        case dbk::B_SCALAR_A: launch_pw<OP, T, dbk::B_SCALAR_A>(a, b, o, n, s); break;
+        default: throw Error("pointwise: bad broadcast mode");
+    }
+}
+
+template <typename T>
+static void launch_pw_op(int op, int bmode, const void* a, const void* b, void* o, int64_t n, cudaStream_t s) {
+    switch (op) {
+#define C(OP) case dbk::OP: launch_pw_mode<dbk::OP, T>(bmode, a, b, o, n, s); break;
+        C(OP_ADD) C(OP_SUB) C(OP_MUL) C(OP_DIV) C(OP_LT) C(OP_LTE) C(OP_GT) C(OP_GTE) C(OP_EQ) C(OP_NEQ) C(OP_MAX)
+        C(OP_MIN) C(OP_POW)
+#undef C
+#define C(OP) case dbk::OP: launch_pw<dbk::OP, T, dbk::B_SCALAR_B>(a, a, o, n, s); break;   /* unary: b unused */
+        C(OP_NEG) C(OP_ABS) C(OP_SGN) C(OP_EXP) C(OP_LOG) C(OP_SQRT)
+#undef C
+        default: throw Error("pointwise: unknown op");
+    }
+}
+
+void pointwise_launch(int op, int dtype, int bmode, const void* a, const void* b, void* o, int64_t n, cudaStream_t s) {
+    if (dtype == DOPT_B200_FLOAT32) launch_pw_op<float>(op, bmode, a, b, o, n, s);
+    else if (dtype == DOPT_B200_INT32) launch_pw_op<int>(op, bmode, a, b, o, n, s);
+    else throw Error("pointwise: unsupported dtype");
+}
+
+static const char* kNames[] = {"add", "sub", "mul", "div", "lt",  "lte", "gt",  "gte", "eq",  "neq",
+                               "max", "min", "pow", "neg", "abs", "sgn", "exp", "log", "sqrt"};
+
+int pointwise_op_id(const char* name) {
+    for (int i = 0; i < dbk::OP_COUNT; ++i)
+        if (strcmp(name, kNames[i]) == 0) return i;
+    return -1;
+}
+bool pointwise_is_unary(int op) { return op >= dbk::OP_NEG; }
+
+namespace {
+struct PointwiseKernel : Kernel {
+    int op, dtype;
+    int64_t n;
+    bool unary;
+    PointwiseKernel(const dopt_b200_op& d) {
+        op = pointwise_op_id(d.op_type);
+        DB_REQUIRE(op >= 0, "unknown pointwise op");
+        unary = pointwise_is_unary(op);
+        DB_REQUIRE(d.n_inputs == (unary ? 1 : 2), "pointwise: wrong number of operands");
+        dtype = d.output.dtype;
+        n = volume(d.output);
+        // verifier of the reference: operand types must be identical (core/source/dopt/core/ops/math.d:22-25)
+        for (int i = 0; i < d.n_inputs; ++i) {
+            DB_REQUIRE(d.inputs[i].dtype == dtype && volume(d.inputs[i]) == n, "pointwise: operand type mismatch");
+        }
+    }
+    void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
+        DB_REQUIRE(n_in == (unary ? 1 : 2), "pointwise: wrong number of inputs");
+        pointwise_launch(op, dtype, dbk::B_TENSOR, in[0], unary ? in[0] : in[1], out, n, s);
+    }
+};
+Kernel* make_pointwise(const dopt_b200_op& d) { return new PointwiseKernel(d); }
+}  // namespace
+
+void register_pointwise() {
+    for (int i = 0; i < dbk::OP_COUNT; ++i) register_kernel(kNames[i], make_pointwise);
+}
+
+}  // namespace db

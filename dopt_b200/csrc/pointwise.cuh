@@ -1,0 +1,97 @@
+// pointwise.cuh -- op table and per-element semantics shared by pointwise.cu and the plan's fused-region kernel.
+#pragma once
+#include "common.cuh"
+
+namespace dbk {
+
+enum PwOp {
+    OP_ADD = 0, OP_SUB, OP_MUL, OP_DIV, OP_LT, OP_LTE, OP_GT, OP_GTE, OP_EQ, OP_NEQ, OP_MAX, OP_MIN, OP_POW,
+    OP_NEG, OP_ABS, OP_SGN, OP_EXP, OP_LOG, OP_SQRT, OP_COUNT
+};
+enum PwBroadcast { B_TENSOR = 0, B_SCALAR_B = 1, B_SCALAR_A = 2 };
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<int> { using type = int4; };
+
+__device__ __forceinline__ float4 ldv(const float4* p) { return ld_stream(p); }
+__device__ __forceinline__ void stv(float4* p, const float4& v) { st_stream(p, v); }
+__device__ __forceinline__ int4 ldv(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stv(int4* p, const int4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// float semantics: the CUDA C overloads the reference's NVRTC template resolves to (math.d:129-170).
+// Explicit _rn intrinsics keep the compiler from contracting neighbouring ops into FMAs when these are inlined
+// into fused kernels, so fused and unfused results are bit-identical.
+template <int OP, typename T> struct Apply;
+template <int OP> struct Apply<OP, float> {
+    static __device__ __forceinline__ float f(float a, float b) {
+        switch (OP) {
+            case OP_ADD: return __fadd_rn(a, b);
+            case OP_SUB: return __fsub_rn(a, b);
+            case OP_MUL: return __fmul_rn(a, b);
+            case OP_DIV: return __fdiv_rn(a, b);
+            case OP_LT: return a < b ? 1.0f : 0.0f;
+            case OP_LTE: return a <= b ? 1.0f : 0.0f;
+            case OP_GT: return a > b ? 1.0f : 0.0f;
+            case OP_GTE: return a >= b ? 1.0f : 0.0f;
+            case OP_EQ: return a == b ? 1.0f : 0.0f;
+            case OP_NEQ: return a != b ? 1.0f : 0.0f;
+            case OP_MAX: return fmaxf(a, b);
+            case OP_MIN: return fminf(a, b);
+            case OP_POW: return powf(a, b);
+            case OP_NEG: return -a;
+            case OP_ABS: return fabsf(a);
+            case OP_SGN: return (float)((0.0f < a) - (a < 0.0f));
+            case OP_EXP: return expf(a);
+            case OP_LOG: return logf(a);
+            case OP_SQRT: return __fsqrt_rn(a);
+        }
+        return 0.0f;
+    }
+};
+template <int OP> struct Apply<OP, int> {
+    static __device__ __forceinline__ int f(int a, int b) {
+        switch (OP) {
+            case OP_ADD: return a + b;
+            case OP_SUB: return a - b;
+            case OP_MUL: return a * b;
+            case OP_DIV: return b == 0 ? 0 : a / b;   // C leaves x/0 undefined; pick 0 rather than trapping
+            case OP_LT: return a < b;
+            case OP_LTE: return a <= b;
+            case OP_GT: return a > b;
+            case OP_GTE: return a >= b;
+            case OP_EQ: return a == b;
+            case OP_NEQ: return a != b;
+            case OP_MAX: return max(a, b);
+            case OP_MIN: return min(a, b);
+            case OP_POW: return (int)pow((double)a, (double)b);
+            case OP_NEG: return -a;
+            case OP_ABS: return abs(a);
+            case OP_SGN: return (0 < a) - (a < 0);
+            case OP_EXP: return (int)exp((double)a);
+            case OP_LOG: return (int)log((double)a);
+            case OP_SQRT: return (int)sqrt((double)a);
+        }
+        return 0;
+    }
+};
+template <int OP, typename T> __device__ __forceinline__ T apply(T a, T b) { return Apply<OP, T>::f(a, b); }
+
+}  // namespace dbk
+
+namespace db {
+// op: dbk::PwOp; bmode: dbk::PwBroadcast (scalar operands are DEVICE pointers to one element)
+void pointwise_launch(int op, int dtype, int bmode, const void* a, const void* b, void* o, int64_t n, cudaStream_t s);
+int pointwise_op_id(const char* name);
+bool pointwise_is_unary(int op);
+}  // namespace db

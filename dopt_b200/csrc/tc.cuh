@@ -1,0 +1,24 @@
+// tc.cuh -- host-side interface of the tcgen05 (5th-gen tensor core) kernels in tc_gemm.cu / conv_tc.cu.
+#pragma once
+#include "common.cuh"
+#include "conv.cuh"
+
+namespace db {
+
+// ---- plain GEMM: C[M,N] = A[M,K] * B[K,N], fp32 row-major in/out, bf16 operands, fp32 accumulate ---------------------
+struct TcGemm;
+bool tc_gemm_supported(int64_t M, int64_t N, int64_t K);
+TcGemm* tc_gemm_create(int64_t M, int64_t N, int64_t K);
+void tc_gemm_run(TcGemm* g, const float* A, const float* B, float* C, cudaStream_t s);
+void tc_gemm_destroy(TcGemm* g);
+
+// ---- convolution (NCHW fp32 at the boundary, NHWC bf16 inside) -------------------------------------------------------
+enum ConvKind { CONV_FWD = 0, CONV_DGRAD = 1, CONV_WGRAD = 2 };
+struct ConvTc;
+bool conv_tc_supported(const ConvGeom& g, int kind);
+ConvTc* conv_tc_create(const ConvGeom& g, int kind);
+// fwd: a = x, b = w, out = y;  dgrad: a = dy, b = w, out = dx;  wgrad: a = dy, b = x, out = dw  (all NCHW / KCRS fp32)
+void conv_tc_run(ConvTc* c, const float* a, const float* b, float* out, cudaStream_t s);
+void conv_tc_destroy(ConvTc* c);
+
+}  // namespace db

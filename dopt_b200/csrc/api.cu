@@ -36,6 +36,7 @@ static void ensure_registered() {
         register_batchnorm();
         register_conv();
         register_random();
+        register_comm();
         for (auto& kv : registry()) {
             g_op_list += kv.first;
             g_op_list.push_back('\0');

@@ -57,6 +57,31 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, int64
 }  // namespace
 
 int comm_world() { return g_world; }
+
+namespace {
+// `allreduce` graph node (registered through dopt's registerOperation / registerCUDAKernel like any other op): the mean
+// over ranks of its operand.  With one rank it is a copy.
+struct AllreduceKernel : Kernel {
+    int64_t n;
+    AllreduceKernel(const dopt_b200_op& d) {
+        DB_REQUIRE(d.n_inputs == 1 && d.output.dtype == DOPT_B200_FLOAT32, "allreduce: one float32 operand");
+        n = volume(d.output);
+    }
+    void run(const void* const* in, int n_in, void* out, cudaStream_t s) override;
+};
+}  // namespace
+void allreduce(float* buf, int64_t n, float scale, cudaStream_t s);
+void AllreduceKernel::run(const void* const* in, int n_in, void* out, cudaStream_t s) {
+    DB_REQUIRE(n_in == 1, "allreduce: one input");
+    if (n == 0) return;
+    if (in[0] != out) {
+        DB_CUDA(cudaMemcpyAsync(out, in[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        count_launch();
+    }
+    allreduce((float*)out, n, 1.0f / (float)g_world, s);
+}
+static Kernel* make_allreduce(const dopt_b200_op& d) { return new AllreduceKernel(d); }
+void register_comm() { register_kernel("allreduce", make_allreduce); }
 int comm_rank() { return g_rank; }
 
 void allreduce(float* buf, int64_t n, float scale, cudaStream_t s) {

@@ -84,6 +84,7 @@ void register_nnet();
 void register_batchnorm();
 void register_conv();
 void register_random();
+void register_comm();
 
 // small device scratch that lives for the process (workspaces, packed weights); grows on demand.
 struct Scratch {

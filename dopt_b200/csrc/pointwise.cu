@@ -32,33 +32,33 @@ __global__ void __launch_bounds__(256) pw_kernel(const T* __restrict__ a, const 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (BMODE != dbk::B_SCALAR_A) x[u] = dbk::ldv(av + i + u * stride);
-            if (BMODE == dbk::B_TENSOR) y[u] = dbk::ldv(bv + i + u * stride);
+            if (BMODE != dbk::B_SCALAR_B) y[u] = dbk::ldv(bv + i + u * stride);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             V r;
-            r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].x, BMODE == dbk::B_TENSOR ? y[u].x : sb);
-            r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].y, BMODE == dbk::B_TENSOR ? y[u].y : sb);
-            r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].z, BMODE == dbk::B_TENSOR ? y[u].z : sb);
-            r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].w, BMODE == dbk::B_TENSOR ? y[u].w : sb);
+            r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].x, BMODE != dbk::B_SCALAR_B ? y[u].x : sb);
+            r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].y, BMODE != dbk::B_SCALAR_B ? y[u].y : sb);
+            r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].z, BMODE != dbk::B_SCALAR_B ? y[u].z : sb);
+            r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x[u].w, BMODE != dbk::B_SCALAR_B ? y[u].w : sb);
             dbk::stv(ov + i + u * stride, r);
         }
     }
     for (; i < nvec; i += stride) {
         V x, y, r;
         if (BMODE != dbk::B_SCALAR_A) x = dbk::ldv(av + i);
-        if (BMODE == dbk::B_TENSOR) y = dbk::ldv(bv + i);
-        r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.x, BMODE == dbk::B_TENSOR ? y.x : sb);
-        r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.y, BMODE == dbk::B_TENSOR ? y.y : sb);
-        r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.z, BMODE == dbk::B_TENSOR ? y.z : sb);
-        r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.w, BMODE == dbk::B_TENSOR ? y.w : sb);
+        if (BMODE != dbk::B_SCALAR_B) y = dbk::ldv(bv + i);
+        r.x = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.x, BMODE != dbk::B_SCALAR_B ? y.x : sb);
+        r.y = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.y, BMODE != dbk::B_SCALAR_B ? y.y : sb);
+        r.z = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.z, BMODE != dbk::B_SCALAR_B ? y.z : sb);
+        r.w = dbk::apply<OP, T>(BMODE == dbk::B_SCALAR_A ? sa : x.w, BMODE != dbk::B_SCALAR_B ? y.w : sb);
         dbk::stv(ov + i, r);
     }
     // scalar tail (n % 4 elements)
     int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) {
         T x = BMODE == dbk::B_SCALAR_A ? sa : a[t];
-        T y = BMODE == dbk::B_TENSOR ? b[t] : sb;
+        T y = BMODE != dbk::B_SCALAR_B ? b[t] : sb;
         o[t] = dbk::apply<OP, T>(x, y);
     }
 }
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) pw_kernel_scalar(const T* __restrict__ a,
     if (BMODE == dbk::B_SCALAR_B) sb = b[0];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T x = BMODE == dbk::B_SCALAR_A ? sa : a[i];
-        T y = BMODE == dbk::B_TENSOR ? b[i] : sb;
+        T y = BMODE != dbk::B_SCALAR_B ? b[i] : sb;
         o[i] = dbk::apply<OP, T>(x, y);
     }
 }
@@ -82,7 +82,7 @@ template <int OP, typename T, int BMODE>
 static void launch_pw(const void* a, const void* b, void* o, int64_t n, cudaStream_t s) {
     if (n <= 0) return;
     bool aligned = ((uintptr_t)o % 16 == 0) && (BMODE == dbk::B_SCALAR_A || (uintptr_t)a % 16 == 0) &&
-                   (BMODE != dbk::B_TENSOR || (uintptr_t)b % 16 == 0);
+                   (BMODE == dbk::B_SCALAR_B || (uintptr_t)b % 16 == 0);
     if (aligned) {
         int grid = stream_grid(ceil_div(n, 16), 256, 8);   // 4 vectors of 4 per thread per trip
         pw_kernel<OP, T, BMODE><<<grid, 256, 0, s>>>((const T*)a, (const T*)b, (T*)o, n);

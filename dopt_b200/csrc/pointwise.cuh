@@ -59,6 +59,17 @@ template <int OP> struct Apply<OP, float> {
         return 0.0f;
     }
 };
+// integer power as D's std.math.pow(int, int) computes it (exact, by squaring); negative exponents give 1/x^n truncated
+__device__ __forceinline__ int ipow(int a, int b) {
+    if (b < 0) return a == 1 ? 1 : (a == -1 ? ((b & 1) ? -1 : 1) : 0);
+    int r = 1;
+    while (b) {
+        if (b & 1) r *= a;
+        a *= a;
+        b >>= 1;
+    }
+    return r;
+}
 template <int OP> struct Apply<OP, int> {
     static __device__ __forceinline__ int f(int a, int b) {
         switch (OP) {
@@ -74,7 +85,7 @@ template <int OP> struct Apply<OP, int> {
             case OP_NEQ: return a != b;
             case OP_MAX: return max(a, b);
             case OP_MIN: return min(a, b);
-            case OP_POW: return (int)pow((double)a, (double)b);
+            case OP_POW: return ipow(a, b);
             case OP_NEG: return -a;
             case OP_ABS: return abs(a);
             case OP_SGN: return (0 < a) - (a < 0);

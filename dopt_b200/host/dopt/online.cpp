@@ -1,0 +1,126 @@
+// dopt/online.cpp -- see online.hpp.
+#include "online.hpp"
+
+namespace dopt {
+namespace online {
+
+static LastUpdate g_last;
+const LastUpdate& lastUpdate() { return g_last; }
+
+// data-parallel: the mean over ranks of every gradient, as a registered `allreduce` op between grad() and the update rule
+static std::vector<Operation> exchange(std::vector<Operation> grads) {
+    if (dataParallelWorld() <= 1) return grads;
+    for (auto& g : grads) g = createOperation("allreduce", {g});
+    return grads;
+}
+
+static Updater finish(const std::vector<Operation>& outputs, std::vector<Operation> planOutputs,
+                      const std::vector<Operation>& stateVars) {
+    // sgd.d:76-91 / adam.d:75-90
+    auto updatePlan = compile(planOutputs);
+    std::vector<Buffer> newbufs;
+    std::vector<Operation> dests;
+    for (auto& o : outputs) {
+        newbufs.push_back(allocate(o->volume() * sizeOf(o->elementType())));
+        dests.push_back(nullptr);
+    }
+    for (auto& v : stateVars) {
+        newbufs.push_back(v->value());
+        dests.push_back(v);
+    }
+    g_last = LastUpdate{updatePlan, planOutputs, dests, newbufs};
+    size_t nOut = outputs.size();
+    return [updatePlan, newbufs, nOut](const std::map<Operation, Buffer>& args) mutable {
+        updatePlan->execute(args, newbufs);
+        return std::vector<Buffer>(newbufs.begin(), newbufs.begin() + nOut);
+    };
+}
+
+static void applyProjections(const std::vector<Operation>& wrt, const std::map<Operation, Projection>& projs,
+                             std::vector<Operation>& newvals) {
+    for (size_t i = 0; i < newvals.size(); ++i) {
+        auto it = projs.find(wrt[i]);
+        if (it != projs.end() && it->second) newvals[i] = it->second(newvals[i]);
+    }
+}
+
+Updater sgd(const std::vector<Operation>& outputs, const std::vector<Operation>& wrt,
+            const std::map<Operation, Projection>& projs, Operation learningRate, Operation momentumRate, bool nesterov) {
+    // sgd.d:28-94
+    if (!learningRate) learningRate = float32({}, {0.01f});
+    if (!momentumRate) momentumRate = float32({}, {0.0f});
+    auto objective = outputs[0];
+    auto grads = exchange(grad(objective, wrt));
+    std::vector<Operation> momentum, newMomentum, newvals;
+    for (auto& g : grads) momentum.push_back(float32(g->shape()));
+    if (nesterov) {
+        for (size_t i = 0; i < grads.size(); ++i) newMomentum.push_back(momentum[i] * momentumRate - learningRate * grads[i]);
+        for (size_t i = 0; i < grads.size(); ++i)
+            newvals.push_back(wrt[i] + momentumRate * newMomentum[i] - learningRate * grads[i]);
+    } else {
+        for (size_t i = 0; i < grads.size(); ++i) newMomentum.push_back(momentum[i] * momentumRate + learningRate * grads[i]);
+        for (size_t i = 0; i < grads.size(); ++i) newvals.push_back(wrt[i] - newMomentum[i]);
+    }
+    applyProjections(wrt, projs, newvals);
+    std::vector<Operation> planOutputs(outputs);
+    planOutputs.insert(planOutputs.end(), newvals.begin(), newvals.end());
+    planOutputs.insert(planOutputs.end(), newMomentum.begin(), newMomentum.end());
+    std::vector<Operation> state(wrt);
+    state.insert(state.end(), momentum.begin(), momentum.end());
+    return finish(outputs, planOutputs, state);
+}
+
+static Updater adamImpl(const std::vector<Operation>& outputs, const std::vector<Operation>& wrt,
+                        const std::map<Operation, Projection>& projs, Operation alpha, Operation beta1, Operation beta2,
+                        Operation eps, bool ams) {
+    // adam.d:32-93, amsgrad.d:32-99
+    if (!alpha) alpha = float32({}, {0.001f});
+    if (!beta1) beta1 = float32({}, {0.9f});
+    if (!beta2) beta2 = float32({}, {0.999f});
+    if (!eps) eps = float32({}, {1e-8f});
+    auto objective = outputs[0];
+    auto grads = exchange(grad(objective, wrt));
+    std::vector<Operation> means, vars, varhats;
+    for (auto& w : wrt) means.push_back(float32(w->shape()));
+    for (auto& w : wrt) vars.push_back(float32(w->shape()));
+    if (ams)
+        for (auto& w : wrt) varhats.push_back(float32(w->shape()));
+    auto b1 = float32({}, {1.0f});
+    auto b2 = float32({}, {1.0f});
+    auto nb1 = b1 * beta1;
+    auto nb2 = b2 * beta2;
+    auto eta = alpha * sqrt(1.0f - nb2) / (1.0f - nb1);
+    std::vector<Operation> newMeans, newVars, newVarhats, newvals;
+    for (size_t i = 0; i < wrt.size(); ++i) newMeans.push_back(beta1 * means[i] + (1.0f - beta1) * grads[i]);
+    for (size_t i = 0; i < wrt.size(); ++i) newVars.push_back(beta2 * vars[i] + (1.0f - beta2) * grads[i] * grads[i]);
+    if (ams)
+        for (size_t i = 0; i < wrt.size(); ++i) newVarhats.push_back(max(varhats[i], vars[i]));   // amsgrad.d:63-66 (survey F11)
+    for (size_t i = 0; i < wrt.size(); ++i) newvals.push_back(wrt[i] - eta * (newMeans[i] / (sqrt(newVars[i]) + eps)));
+    applyProjections(wrt, projs, newvals);
+    std::vector<Operation> planOutputs(outputs);
+    planOutputs.insert(planOutputs.end(), newvals.begin(), newvals.end());
+    planOutputs.insert(planOutputs.end(), newMeans.begin(), newMeans.end());
+    planOutputs.insert(planOutputs.end(), newVars.begin(), newVars.end());
+    if (ams) planOutputs.insert(planOutputs.end(), newVarhats.begin(), newVarhats.end());
+    planOutputs.push_back(nb1);
+    planOutputs.push_back(nb2);
+    std::vector<Operation> state(wrt);
+    state.insert(state.end(), means.begin(), means.end());
+    state.insert(state.end(), vars.begin(), vars.end());
+    if (ams) state.insert(state.end(), varhats.begin(), varhats.end());
+    state.push_back(b1);
+    state.push_back(b2);
+    return finish(outputs, planOutputs, state);
+}
+
+Updater adam(const std::vector<Operation>& outputs, const std::vector<Operation>& wrt,
+             const std::map<Operation, Projection>& projs, Operation alpha, Operation beta1, Operation beta2, Operation eps) {
+    return adamImpl(outputs, wrt, projs, alpha, beta1, beta2, eps, false);
+}
+Updater amsgrad(const std::vector<Operation>& outputs, const std::vector<Operation>& wrt,
+                const std::map<Operation, Projection>& projs, Operation alpha, Operation beta1, Operation beta2, Operation eps) {
+    return adamImpl(outputs, wrt, projs, alpha, beta1, beta2, eps, true);
+}
+
+}  // namespace online
+}  // namespace dopt

@@ -1,0 +1,259 @@
+"""Host logic on CPU: the C++ mirror of dopt.core / dopt.nnet / dopt.online builds the same graphs the D code would
+(checked structurally and by evaluating them with the CPU oracle against the reference's own unit-test vectors).
+No GPU and no compute through the product here: the oracle is the evaluator."""
+import numpy as np
+import pytest
+
+from dopt_b200 import host as H
+from oracle import graph_eval as G
+
+F = np.float32
+
+
+@pytest.fixture(autouse=True)
+def _fresh():
+    H.init()
+    H.reset()
+    H.set_data_parallel_world(1)
+    yield
+    H.reset()
+
+
+def ev(ops, args=None):
+    return G.evaluate_ops(H, ops, args)
+
+
+def types(ops):
+    return [n["type"] for n in H.export(ops)]
+
+
+# ---- reference unit tests re-run through the mirrored graph API + oracle evaluator -----------------------------------
+def test_core_ops_kats():
+    # core/source/dopt/core/ops/math.d:212-231
+    c = H.matmul(H.float32((2, 1), [1, 2]), H.float32((1, 2), [3, 4]))
+    assert ev([c])[0].ravel().tolist() == [3, 4, 6, 8]
+    # math.d:285-298 (incl. the matmul-with-ones lowering of rank-2 single-axis sums)
+    m = H.float32((2, 2), [0, 1, 2, 5])
+    s1, s2, s3, s4 = H.sum_(H.float32((2,), [0.5, 1.5])), H.sum_(m), H.sum_(m, [0]), H.sum_(m, [1])
+    r = ev([s1, s2, s3, s4])
+    assert [x.ravel().tolist() for x in r] == [[2.0], [8.0], [2.0, 6.0], [1.0, 7.0]]
+    assert "matmul" in types([s3]) and "sum" not in types([s3])
+    assert "sum" in types([s2])
+    # math.d:318-331, 361-373
+    assert ev([H.argmin(H.float32((5,), [4, 2, 6, 1, 2]), 0)])[0].ravel().tolist() == [3]
+    a = H.float32((2, 2), [1, 4, 3, 6])
+    assert [x.ravel().tolist() for x in ev([H.max_element(a), H.max_element(a, [0]), H.max_element(a, [1])])] == \
+        [[6.0], [3.0, 6.0], [4.0, 6.0]]
+
+
+def test_basic_ops_kats():
+    # core/source/dopt/core/ops/basic.d:212-395
+    s = H.slice_(H.int32((3, 3), list(range(1, 10))), [1, 1], [3, 3])
+    assert ev([s])[0].ravel().tolist() == [5, 6, 8, 9]
+    p = H.pad(H.int32((1, 1), [3]), [2, 1], [3, 3])
+    got = ev([p])[0]
+    assert got.shape == (6, 5) and got[2, 1] == 3 and got.sum() == 3
+    r = H.reshape(H.float32((2, 2), [1, 2, 3, 4]), [1, 4])
+    assert r.shape == (1, 4) and ev([r])[0].ravel().tolist() == [1, 2, 3, 4]
+    t = H.transpose(H.float32((2, 2), [1, 2, 3, 4]), [1, 0])
+    assert ev([t])[0].ravel().tolist() == [1, 3, 2, 4]
+    r2 = H.repeat(H.float32((2, 2), [1, 2, 3, 4]), [3, 2])
+    assert ev([r2])[0].ravel().tolist() == [1, 2, 1, 2, 3, 4, 3, 4] * 3
+    r3 = H.repeat(H.float32((2,), [1, 2]), 3)
+    assert r3.shape == (3, 2) and ev([r3])[0].ravel().tolist() == [1, 2, 1, 2, 1, 2]
+    assert types([r3]).count("matmul") == 1   # repeat(n) is a matmul with a ones column (basic.d:370-381)
+
+
+def test_verifiers_reject_like_the_reference():
+    with pytest.raises(H.HostError):
+        H.matmul(H.float32((2, 3)), H.float32((2, 3)))            # inner dimensions differ
+    with pytest.raises(H.HostError):
+        H.binary("add", H.float32((2,)), H.float32((3,)))         # pointwise operands must have identical types
+    with pytest.raises(H.HostError):
+        H.slice_(H.float32((3,)), [2], [2])                       # start < stop
+    with pytest.raises(H.HostError):
+        H.reshape(H.float32((3,)), [2, 2])
+    with pytest.raises(H.HostError):
+        H.create("noSuchOp", [])
+    with pytest.raises(H.HostError):
+        H.grad(H.float32((2,)), [H.float32((2,))])                # objective must have volume one
+
+
+def test_nnet_ops_kats():
+    # core/source/dopt/core/ops/nnet.d:270-293, 333-352, 424-435
+    y = H.convolution(H.float32((1, 1, 3, 5), [1, 1, 1, 0, 0] * 3), H.float32((1, 1, 1, 2), [-1, 1]))
+    assert y.shape == (1, 1, 3, 4) and ev([y])[0].ravel().tolist() == [0, 0, 1, 0] * 3
+    mp = H.maxpool(H.float32((1, 1, 4, 4), [1, 2, 4, 3, 5, 3, 2, 2, 0.1, -4, 3, 2, 0, 0, 2, 2]), [2, 2])
+    assert ev([mp])[0].ravel().tolist() == [F(5), F(4), F(0.1), F(3)]
+    sm = H.softmax(H.float32((1, 5), [1, 2, 3, 1, 2]))
+    np.testing.assert_allclose(ev([sm])[0].ravel(), [0.0674508, 0.18335, 0.498398, 0.0674508, 0.18335], atol=1e-6)
+    # convolutionTranspose's shape rule (nnet.d:305-315)
+    ct = H.convolution_transpose(H.float32((2, 8, 5, 5)), H.float32((8, 3, 3, 3)), (1, 1), (2, 2))
+    assert ct.shape == (2, 3, 9, 9)
+
+
+def test_scalar_broadcast_lowering():
+    # Operation.opBinary (ops/package.d:96-103): rank-0 operand -> repeat(volume).reshape(shape) -> matmul with ones
+    x = H.float32((2, 3), np.arange(6))
+    y = x * 2.0
+    assert ev([y])[0].ravel().tolist() == [0, 2, 4, 6, 8, 10]
+    ts = types([y])
+    assert ts.count("matmul") == 1 and ts.count("constant") == 2 and ts[-1] == "mul"
+    z = 1.0 - x
+    assert ev([z])[0].ravel().tolist() == [1, 0, -1, -2, -3, -4]
+
+
+def test_autodiff_kats():
+    # core/source/dopt/core/grads/package.d:113-129: d(sum(x*x))/dx == 2x
+    rng = np.random.RandomState(0)
+    xv = rng.randn(3, 4).astype(F)
+    x = H.float32((3, 4), xv)
+    g = H.grad(H.sum_(x * x), [x])[0]
+    np.testing.assert_allclose(ev([g])[0], 2 * xv, rtol=1e-6)
+    # core/source/dopt/core/grads/basic.d:49-67: sliceGrad -> pad
+    a = H.float32((4, 4), [1, 2, 3, 4] * 4)
+    b = H.float32((4, 4), [5, 6, 7, 8] * 4)
+    c = H.slice_(a * b, [1, 1], [2, 2])
+    ga = H.grad(c, [a])[0]
+    assert ev([ga])[0].ravel().tolist() == [0, 0, 0, 0, 0, 6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert "pad" in types([ga])
+
+
+def test_gradient_graph_matches_finite_differences_for_a_small_net():
+    rng = np.random.RandomState(1)
+    H.seed(3)
+    x = H.float32((4, 3, 6, 6))
+    labels = H.float32((4, 5))
+    out = H.data_source(x).conv2d(4, (3, 3), padding=(1, 1), weight_decay=1e-2).batch_norm().relu().max_pool((2, 2)) \
+        .dense(5).softmax()
+    net = H.Network([x], [out])
+    loss = H.cross_entropy(out.train_output, labels) + net.param_loss
+    params = net.params
+    grads = H.grad(loss, params[:2])   # conv filters and conv bias
+    xs = rng.randn(4, 3, 6, 6).astype(F)
+    ls = np.eye(5, dtype=F)[rng.randint(0, 5, 4)]
+    base = ev([loss] + grads, {x: xs, labels: ls})
+    w0 = params[0].get()
+    eps = 1e-2
+    for idx in [(0, 0, 0, 0), (3, 2, 1, 2), (1, 1, 2, 0)]:
+        wp, wm = w0.copy(), w0.copy()
+        wp[idx] += eps
+        wm[idx] -= eps
+        params[0].set(wp)
+        lp = ev([loss], {x: xs, labels: ls})[0]
+        params[0].set(wm)
+        lm = ev([loss], {x: xs, labels: ls})[0]
+        params[0].set(w0)
+        fd = (float(lp) - float(lm)) / (2 * eps)
+        assert abs(fd - base[1][idx]) < 5e-3 + 5e-2 * abs(fd), (idx, fd, base[1][idx])
+
+
+def test_batchnorm_layer_structure_and_running_mean_kat():
+    # nnet/source/dopt/nnet/layers/batchnorm.d:158-177 with dopt.online.adam and the mean/var "projections"
+    x = H.float32((3, 2), [1, 2, 3, 4, 5, 6])
+    layer = H.data_source(x).batch_norm()
+    net = H.Network([x], [layer])
+    params = net.params
+    assert [p.shape for p in params] == [(1, 2, 1, 1), (2,), (2,), (2,)]
+    trloss = H.sum_(layer.train_output)
+    upd = H.Updater(H.ADAM, [trloss], network=net)
+    plan_ops, dests = upd.plan_outputs()
+    # outputs ~ newvals(4) ~ means(4) ~ vars(4) ~ [nb1, nb2]
+    assert len(plan_ops) == 1 + 4 + 4 + 4 + 2
+    ts = types(plan_ops)
+    assert ts.count("batchNormTrain") == 1 and ts.count("batchNormGrad") == 1
+    oracle = G.UpdaterOracle(upd)
+    for _ in range(1000):
+        oracle.step({})
+    np.testing.assert_allclose(oracle.value_of(params[2]), [3.0, 4.0], rtol=1e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", [H.SGD, H.ADAM, H.AMSGRAD])
+def test_optimisers_fit_a_line(kind):
+    # online/source/dopt/online/{sgd.d:97-141, adam.d:96-140, amsgrad.d:102-146}: fit y = 3x + 2 (the reference only prints)
+    rng = np.random.RandomState(2)
+    xdata = rng.rand(100).astype(F)
+    ydata = 3.0 * xdata + 2.0
+    m, c = H.float32((), [0.0]), H.float32((), [0.0])
+    x, y = H.float32((100,)), H.float32((100,))
+    yhat = m * x + c
+    diff = yhat - y
+    loss = H.sum_(diff * diff) * (1.0 / 100)
+    if kind == H.SGD:
+        upd = H.Updater(kind, [loss], wrt=[m, c], hyper=[H.float32((), [0.1]), H.float32((), [0.5])])
+        steps = 600
+    else:
+        upd = H.Updater(kind, [loss], wrt=[m, c], hyper=[H.float32((), [0.1]), None, None, None])
+        steps = 600
+    oracle = G.UpdaterOracle(upd)
+    first = last = None
+    for i in range(steps):
+        out = oracle.step({x: xdata, y: ydata})[0]
+        first = out if first is None else first
+        last = out
+    assert float(last) < 1e-3 < float(first)
+    assert abs(float(oracle.value_of(m)) - 3.0) < 0.1 and abs(float(oracle.value_of(c)) - 2.0) < 0.1
+
+
+def test_sgd_graph_shape_and_amsgrad_quirk():
+    w = H.float32((5,), np.arange(5))
+    loss = H.sum_(w * w)
+    upd = H.Updater(H.SGD, [loss], wrt=[w])
+    plan_ops, dests = upd.plan_outputs()
+    assert len(plan_ops) == 3 and dests[0] is None and dests[1].serial == w.serial
+    # m' = m*mu + lr*g ; w' = w - m' : mul, mul, add, sub after the gradient (sgd.d:57-64)
+    tail = [t for t in types(plan_ops) if t in ("add", "sub", "mul")]
+    assert tail.count("sub") == 1
+    upd = H.Updater(H.AMSGRAD, [loss], wrt=[w])
+    plan_ops, dests = upd.plan_outputs()
+    assert len(plan_ops) == 1 + 4 + 2
+    # varhat' = max(varhat, OLD var) and is never read by the update (survey F11): after one step it is still zero
+    oracle = G.UpdaterOracle(upd)
+    oracle.step({})
+    assert not oracle.value_of(dests[4]).any()
+
+
+def test_wrn_graph_inventory():
+    """Wide ResNet 16-4 (examples/cifar100.d:40-48): the op inventory the kernels see."""
+    H.seed(1)
+    x = H.float32((2, 3, 32, 32))
+    labels = H.float32((2, 100))
+    preds = H.wide_resnet(x, 16, 4).dense(100).softmax()
+    net = H.Network([x], [preds])
+    # 13 convs (1 stem + 3 blocks x (2x2 + shortcut)) no bias, 13 BNs (4 params each), dense weight + bias
+    convs = [p for p in net.params if len(p.shape) == 4 and p.shape[0] != 1]
+    assert len(convs) == 1 + 3 * (2 * 2 + 1)
+    assert len(net.params) == len(convs) + 13 * 4 + 2
+    loss = H.cross_entropy(preds.train_output, labels) + net.param_loss
+    upd = H.Updater(H.SGD, [loss, preds.train_output], network=net,
+                    hyper=[H.float32((), [0.1]), H.float32((), [0.9])])
+    plan_ops, dests = upd.plan_outputs()
+    assert len(plan_ops) == 2 + 2 * len(net.params)
+    ts = types(plan_ops)
+    assert ts.count("convolution") == len(convs)
+    assert ts.count("convolutionFiltersGrad") == len(convs)
+    assert ts.count("convolutionFeaturesGrad") == len(convs) - 1     # the stem's features are the network input
+    assert ts.count("batchNormTrain") == 13 and ts.count("batchNormGrad") == 13
+    assert ts.count("relu") == 13 and ts.count("reluGrad") == 13
+    assert ts.count("sum") == len(convs) + 1                          # weight decay per conv + the cross-entropy sum
+
+
+def test_data_parallel_wraps_gradients_in_allreduce():
+    w = H.float32((4,), np.arange(4))
+    loss = H.sum_(w * w)
+    H.set_data_parallel_world(8)
+    upd = H.Updater(H.SGD, [loss], wrt=[w])
+    assert types(upd.plan_outputs()[0]).count("allreduce") == 1
+    H.set_data_parallel_world(1)
+    upd = H.Updater(H.SGD, [loss], wrt=[w])
+    assert types(upd.plan_outputs()[0]).count("allreduce") == 0
+
+
+def test_no_backend_means_no_evaluation():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = H.float32((2,), [1, 2])
+    with pytest.raises(H.HostError) as e:
+        H.evaluate([x + x])
+    assert "no backend" in str(e.value) or "no CPU" in str(e.value)

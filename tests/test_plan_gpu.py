@@ -1,0 +1,268 @@
+"""Whole-graph parity on the GPU: graphs built by the dopt mirror, executed by (a) the reference-style node-by-node
+CUDAPlan over the per-op C ABI and (b) the lowered / fused / CUDA-graph B200Plan, against the graph-level CPU oracle.
+Includes the reference's own end-to-end unit tests and multi-step loss curves for the BASELINE model families at sizes the
+oracle finishes in seconds.
+
+Tolerances: fp32 math -> rtol 1e-4 per step on losses (summation order); bf16 tensor-core math -> losses within 2e-2
+relative, parameters within 3e-2 of the largest update-scaled magnitude after a few steps."""
+import numpy as np
+import pytest
+
+import dopt_b200 as db
+from dopt_b200 import host as H
+from oracle import graph_eval as G
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+FUSE, GRAPH = db._lib.PLAN_FUSE, db._lib.PLAN_CUDA_GRAPH
+MODES = [("cudaplan", 1, 0), ("plain", 0, 0), ("fused", 0, FUSE), ("fused+graph", 0, FUSE | GRAPH)]
+
+
+@pytest.fixture(autouse=True)
+def _fresh():
+    assert H.init(), H.init_error()
+    H.reset()
+    H.set_math(db.MATH_FP32)
+    H.set_plan_flags(FUSE | GRAPH)
+    yield
+    H.reset()
+    H.set_math(db.MATH_DEFAULT)
+
+
+def run_modes(outputs, args=None, reps=1):
+    res = {}
+    for name, kind, flags in MODES:
+        H.set_plan_flags(flags)
+        p = H.Plan(outputs, kind=kind)
+        for _ in range(reps):
+            out = p.execute(args)
+        res[name] = out
+    return res
+
+
+def test_reference_cuda_backend_unittest():
+    # cuda/source/dopt/cuda/package.d:533-542
+    a, b, c = H.float32((), [3.0]), H.float32((), [4.0]), H.float32((), [-1.0])
+    y = a * b + c
+    for name, out in run_modes([y], reps=3).items():
+        assert out[0] == F(11.0), name
+
+
+def test_core_kats_on_gpu():
+    m = H.float32((2, 2), [0, 1, 2, 5])
+    outs = [H.matmul(H.float32((2, 1), [1, 2]), H.float32((1, 2), [3, 4])), H.sum_(m), H.sum_(m, [0]), H.sum_(m, [1]),
+            H.argmin(H.float32((2, 3), [5, 1, 3, 6, 7, 2]), 1), H.max_element(m, [0]),
+            H.repeat(H.float32((2,), [1, 2]), 3), H.transpose(m, [1, 0]),
+            H.convolution(H.float32((1, 1, 3, 5), [1, 1, 1, 0, 0] * 3), H.float32((1, 1, 1, 2), [-1, 1])),
+            H.softmax(H.float32((1, 5), [1, 2, 3, 1, 2]))]
+    want = [[3, 4, 6, 8], [8], [2, 6], [1, 7], [1, 2], [2, 5], [1, 2, 1, 2, 1, 2], [0, 2, 1, 5], [0, 0, 1, 0] * 3, None]
+    for name, out in run_modes(outs, reps=3).items():
+        for o, w in zip(out, want):
+            if w is not None:
+                assert o.ravel().tolist() == w, name
+        np.testing.assert_allclose(out[-1].ravel(), [0.0674508, 0.18335, 0.498398, 0.0674508, 0.18335], atol=1e-6)
+
+
+def test_autodiff_kats_on_gpu():
+    rng = np.random.RandomState(0)
+    xv = rng.randn(3, 4).astype(F)
+    x = H.float32((3, 4), xv)
+    g = H.grad(H.sum_(x * x), [x])[0]
+    a = H.float32((4, 4), [1, 2, 3, 4] * 4)
+    b = H.float32((4, 4), [5, 6, 7, 8] * 4)
+    ga = H.grad(H.slice_(a * b, [1, 1], [2, 2]), [a])[0]
+    for name, out in run_modes([g, ga], reps=2).items():
+        np.testing.assert_array_equal(out[0], 2 * xv)      # (1*x) + (1*x): exact
+        assert out[1].ravel().tolist() == [0, 0, 0, 0, 0, 6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0], name
+
+
+def test_lowering_removes_bn_scaffolding_and_broadcasts():
+    H.seed(5)
+    x = H.float32((8, 16, 8, 8))
+    y = H.float32((8, 10))
+    out = H.data_source(x).conv2d(16, (3, 3), padding=(1, 1), use_bias=False, weight_decay=1e-4).batch_norm().relu() \
+        .dense(10).softmax()
+    net = H.Network([x], [out])
+    loss = H.cross_entropy(out.train_output, y) + net.param_loss
+    stats = {}
+    for name, kind, flags in MODES[1:]:
+        H.set_plan_flags(flags)
+        upd = H.Updater(H.SGD, [loss], network=net, hyper=[H.float32((), [0.1]), H.float32((), [0.9])])
+        rng = np.random.RandomState(1)
+        upd.step({x: rng.randn(8, 16, 8, 8).astype(F), y: np.eye(10, dtype=F)[rng.randint(0, 10, 8)]})
+        stats[name] = upd.stats()
+    assert stats["fused"]["lowered_nodes"] < stats["plain"]["lowered_nodes"]
+    assert stats["fused"]["launches"] < stats["plain"]["launches"]
+
+
+def _train_compare(build, steps, math, loss_rtol, param_tol, flags=FUSE | GRAPH, kind=H.SGD, hyper=None):
+    """build() -> (loss op, extra outputs, network, feed function).  Steps the GPU updater and the oracle side by side."""
+    H.set_math(math)
+    H.set_plan_flags(flags)
+    loss, extra, net, feed = build()
+    hyper = hyper if hyper is not None else [H.float32((), [0.05]), H.float32((), [0.9])]
+    upd = H.Updater(kind, [loss] + extra, network=net, hyper=hyper)
+    oracle = G.UpdaterOracle(upd)
+    losses = []
+    for s in range(steps):
+        args = feed(s)
+        got = upd.step(args)
+        want = oracle.step(args)
+        losses.append((float(got[0]), float(want[0])))
+        assert abs(got[0] - want[0]) <= loss_rtol * max(1.0, abs(float(want[0]))), (s, losses)
+        for g, w in zip(got[1:], want[1:]):
+            assert np.abs(g - w).max() <= max(loss_rtol * 10, 1e-5) * max(1.0, float(np.abs(w).max())), s
+    for p in net.params:
+        gv, wv = p.get(), oracle.value_of(p)
+        scale = max(float(np.abs(wv).max()), 1e-3)
+        assert float(np.abs(gv - wv).max()) <= param_tol * scale, (p.shape, float(np.abs(gv - wv).max()), scale)
+    return losses
+
+
+def _small_convnet(batch=8, bias=True, bn=True, pool=True):
+    def build():
+        H.seed(11)
+        x = H.float32((batch, 16, 8, 8))
+        y = H.float32((batch, 10))
+        l = H.data_source(x).conv2d(32, (3, 3), padding=(1, 1), weight_decay=1e-3, use_bias=bias)
+        if bn:
+            l = l.batch_norm()
+        l = l.relu()
+        if pool:
+            l = l.max_pool((2, 2))
+        l = l.conv2d(32, (3, 3), padding=(1, 1), stride=(2, 2), weight_decay=1e-3, use_bias=bias).relu().dense(10).softmax()
+        net = H.Network([x], [l])
+        loss = H.cross_entropy(l.train_output, y) + net.param_loss
+        rng = np.random.RandomState(3)
+        data = [(rng.randn(batch, 16, 8, 8).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, batch)]) for _ in range(8)]
+        return loss, [l.train_output], net, lambda s: {x: data[s % 8][0], y: data[s % 8][1]}
+    return build
+
+
+@pytest.mark.parametrize("mode", MODES[1:], ids=[m[0] for m in MODES[1:]])
+def test_small_convnet_sgd_fp32_all_plan_modes(mode):
+    _train_compare(_small_convnet(), 5, db.MATH_FP32, 2e-4, 2e-3, flags=mode[2])
+
+
+def test_small_convnet_sgd_bf16():
+    _train_compare(_small_convnet(batch=16), 5, db.MATH_BF16, 2e-2, 5e-2)
+
+
+@pytest.mark.parametrize("kind", [H.ADAM, H.AMSGRAD, H.SGD_NESTEROV])
+def test_small_convnet_other_optimisers(kind):
+    hyper = [H.float32((), [1e-3]), None, None, None] if kind in (H.ADAM, H.AMSGRAD) else None
+    _train_compare(_small_convnet(bn=False), 4, db.MATH_FP32, 2e-4, 5e-3, kind=kind, hyper=hyper)
+
+
+def test_mnist_logistic_regression_adam():
+    # examples/mnistlogit.d:34-51: softmax regression written by hand ([100,784] x [784,10]); BASELINE configs[0]
+    def build():
+        rng = np.random.RandomState(4)
+        x, y = H.float32((100, 784)), H.float32((100, 10))
+        W = H.float32((784, 10), (rng.randn(784, 10) * 0.01).astype(F))
+        b = H.float32((10,))
+        logits = H.matmul(x, W) + H.repeat(b, 100)
+        e = H.unary("exp", logits)
+        denom = H.repeat(H.reshape(H.sum_(e, [1]), [100, 1]), [1, 10])
+        p = e / denom
+        loss = H.sum_(y * H.unary("log", p + 1e-6)) * (-1.0 / 100)
+        data = [(rng.rand(100, 784).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, 100)]) for _ in range(4)]
+
+        class Net(object):
+            params = [W, b]
+            h = -1
+        return loss, [], Net, lambda s: {x: data[s % 4][0], y: data[s % 4][1]}
+    H.set_math(db.MATH_FP32)
+    loss, extra, net, feed = build()
+    upd = H.Updater(H.ADAM, [loss], wrt=net.params, hyper=[H.float32((), [1e-3]), None, None, None])
+    oracle = G.UpdaterOracle(upd)
+    for s in range(6):
+        got, want = upd.step(feed(s)), oracle.step(feed(s))
+        assert abs(got[0] - want[0]) < 2e-4 * abs(float(want[0]))
+    for p in net.params:
+        np.testing.assert_allclose(p.get(), oracle.value_of(p), rtol=0, atol=2e-5)
+
+
+def test_mnist_cnn_adam():
+    # examples/mnist.d:35-58: conv5x5(32)-relu-pool-conv5x5(32)-relu-pool-dense(10)-softmax, Adam 1e-3 (batch reduced)
+    def build():
+        H.seed(12)
+        x, y = H.float32((10, 1, 28, 28)), H.float32((10, 10))
+        l = H.data_source(x).conv2d(32, (5, 5)).relu().max_pool((2, 2)).conv2d(32, (5, 5)).relu().max_pool((2, 2)) \
+            .dense(10).softmax()
+        net = H.Network([x], [l])
+        loss = H.cross_entropy(l.train_output, y) + net.param_loss
+        rng = np.random.RandomState(5)
+        data = [(rng.rand(10, 1, 28, 28).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, 10)]) for _ in range(3)]
+        return loss, [l.train_output], net, lambda s: {x: data[s % 3][0], y: data[s % 3][1]}
+    _train_compare(build, 3, db.MATH_FP32, 2e-4, 5e-3, kind=H.ADAM, hyper=[H.float32((), [1e-3]), None, None, None])
+
+
+def _wrn(depth, width, batch, hw, classes, strides=(1, 2, 2)):
+    def build():
+        H.seed(13)
+        x, y = H.float32((batch, 3, hw, hw)), H.float32((batch, classes))
+        preds = H.wide_resnet(x, depth, width, stride=strides).dense(classes).softmax()
+        net = H.Network([x], [preds])
+        loss = H.cross_entropy(preds.train_output, y) + net.param_loss
+        rng = np.random.RandomState(6)
+        data = [((rng.rand(batch, 3, hw, hw) * 2 - 1).astype(F), np.eye(classes, dtype=F)[rng.randint(0, classes, batch)])
+                for _ in range(4)]
+        return loss, [preds.train_output], net, lambda s: {x: data[s % 4][0], y: data[s % 4][1]}
+    return build
+
+
+def test_wrn_16_2_sgd_fp32():
+    # the cifar100.d recipe (SGD lr 0.1 momentum 0.9, wd 1e-4) on a narrow WRN at 16x16 so the oracle stays fast
+    _train_compare(_wrn(16, 2, 4, 16, 10), 3, db.MATH_FP32, 5e-4, 1e-2,
+                   hyper=[H.float32((), [0.1]), H.float32((), [0.9])])
+
+
+def test_wrn_16_4_sgd_bf16_loss_curve():
+    losses = _train_compare(_wrn(16, 4, 8, 16, 10), 4, db.MATH_BF16, 3e-2, 0.25,
+                            hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+    assert all(np.isfinite(l[0]) for l in losses)
+
+
+def test_wrn_strided_stem_sins_like_amsgrad():
+    # sins10.d uses strides [2,2,2]; BASELINE configs[4] trains it with AMSGrad
+    _train_compare(_wrn(10, 2, 4, 24, 10, strides=(2, 2, 2)), 2, db.MATH_FP32, 5e-4, 1e-2, kind=H.AMSGRAD,
+                   hyper=[H.float32((), [1e-3]), None, None, None])
+
+
+def test_vgg_with_batchnorm_sgd():
+    # configs[2]: VGG-style CIFAR net with batchNorm + SGD (narrow extractor so the oracle stays fast)
+    def build():
+        H.seed(14)
+        x, y = H.float32((4, 3, 32, 32)), H.float32((4, 10))
+        l = H.data_source(x)
+        for c in (8, -1, 16, -1, 16, -1, 32, -1, 32, -1):
+            l = l.max_pool((2, 2)) if c == -1 else l.conv2d(c, (3, 3), padding=(1, 1)).batch_norm().relu()
+        l = l.dense(32).relu().dense(10).softmax()
+        net = H.Network([x], [l])
+        loss = H.cross_entropy(l.train_output, y) + net.param_loss
+        rng = np.random.RandomState(7)
+        data = [((rng.rand(4, 3, 32, 32) * 2 - 1).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, 4)]) for _ in range(3)]
+        return loss, [l.train_output], net, lambda s: {x: data[s % 3][0], y: data[s % 3][1]}
+    _train_compare(build, 3, db.MATH_FP32, 5e-4, 1e-2)
+
+
+def test_inference_plan_and_checkpoint_roundtrip(tmp_path):
+    H.seed(15)
+    x = H.float32((4, 8, 8, 8))
+    l = H.data_source(x).conv2d(8, (3, 3), padding=(1, 1)).batch_norm().relu().dense(5).softmax()
+    net = H.Network([x], [l])
+    xs = np.random.RandomState(8).randn(4, 8, 8, 8).astype(F)
+    got = H.Plan([l.output]).execute({x: xs})[0]          # test-time graph: batchNormInference
+    want = G.evaluate_ops(H, [l.output], {x: xs})[0]
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+    path = str(tmp_path / "net.bin")
+    net.save(path)
+    before = [p.get() for p in net.params]
+    for p in net.params:
+        p.set(np.zeros(p.shape, F))
+    net.load(path)
+    for p, b in zip(net.params, before):
+        np.testing.assert_array_equal(p.get(), b)
+    import os
+    assert os.path.getsize(path) == 4 * sum(p.volume for p in net.params)   # raw fp32, no header (networks.d:130-164)

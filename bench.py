@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: Wide-ResNet-28-10 CIFAR-shaped training images/sec on N B200s (one process per GPU).
+
+  python bench.py --gpus N --steps K --warmup W              this repo's sm_100a kernels behind dopt's plugin API
+  python bench.py --impl reference --gpus N --steps K ...    the reference path on the host CPU (oracle port), bounded sample
+
+One "step" = one execution of the plan dopt.online.sgd compiles for WRN-28-10 + dense(100) + softmax + cross-entropy +
+weight decay (examples/cifar100.d:33-49 with the BASELINE model/batch): forward, backward, SGD-momentum update of all 130
+parameter tensors and the BN running-statistics write-back, on 128 synthetic 3x32x32 images per GPU.
+
+Printed JSON (one line, rank 0):
+  value        images/s over all ranks with the step's inputs already resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e          the same metric through the public call a dopt program makes -- updater([features: buffer(fs), labels: buffer(ls)])
+               followed by reading loss and predictions back -- with the H2D copy from pinned host memory and the D2H read
+               inside the timed region
+  roofline     the dominant kernel (the tcgen05 implicit-GEMM kernel behind the three convolution ops): algorithmic conv
+               FLOPs it executes per step / its summed launch time, both measured in this process with CUDA events
+  cpu_baseline the oracle (CPU restatement of the reference) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+if WORLD > 1:
+    # one process per GPU, each seeing exactly its own device as ordinal 0 -- the reference hard-codes ordinal 0
+    # (cuda/source/dopt/cuda/package.d:44), so this is also how the D host would be launched
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    ids = vis.split(",") if vis else [str(i) for i in range(64)]
+    PHYS_GPU = ids[LOCAL_RANK]
+    os.environ["CUDA_VISIBLE_DEVICES"] = PHYS_GPU
+else:
+    PHYS_GPU = (os.environ.get("CUDA_VISIBLE_DEVICES") or "0").split(",")[0]
+
+import numpy as np  # noqa: E402
+
+MODEL = dict(depth=28, width=10, batch=128, hw=32, classes=100, lr=0.1, momentum=0.9, wd=1e-4)
+# algorithmic conv+matmul FLOPs per image for one WRN-28-10 training step (3x forward minus the
+# stem's unreachable dgrad); the three convolution ops carry all but ~0.01 % of it
+TRAIN_GFLOP_PER_IMAGE = 31.459
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        p.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))))
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+def build_wrn(H, batch, depth=MODEL["depth"], width=MODEL["width"], reset=True):
+    if reset:
+        H.reset()
+    H.seed(1234)
+    x = H.float32((batch, 3, MODEL["hw"], MODEL["hw"]))
+    y = H.float32((batch, MODEL["classes"]))
+    preds = H.wide_resnet(x, depth, width, weight_decay=MODEL["wd"]).dense(MODEL["classes"]).softmax()
+    net = H.Network([x], [preds])
+    loss = H.cross_entropy(preds.train_output, y) + net.param_loss
+    upd = H.Updater(H.SGD, [loss, preds.train_output], network=net,
+                    hyper=[H.float32((), [MODEL["lr"]]), H.float32((), [MODEL["momentum"]])])
+    return x, y, net, upd
+
+
+def synthetic_batch(batch, seed):
+    rng = np.random.RandomState(seed)
+    fs = (rng.rand(batch, 3, MODEL["hw"], MODEL["hw"]) * 2 - 1).astype(np.float32)   # loader normalisation x/128-1
+    ls = np.eye(MODEL["classes"], dtype=np.float32)[rng.randint(0, MODEL["classes"], batch)]
+    return fs, ls
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_batch, standalone=True):
+    """The reference algorithm on the host: the oracle evaluates the very same dopt graph (built by the host mirror, which
+    needs no GPU for that) for a bounded sample of `sample_batch` images per step."""
+    from dopt_b200 import host as H
+    from oracle import graph_eval as G
+    H.init()
+    x, y, net, upd = build_wrn(H, sample_batch, reset=standalone)
+    oracle = G.UpdaterOracle(upd)
+    fs, ls = synthetic_batch(sample_batch, 99)
+    for _ in range(warmup):
+        oracle.step({x: fs, y: ls})
+    t0 = time.perf_counter()
+    loss = None
+    for _ in range(steps):
+        loss = oracle.step({x: fs, y: ls})[0]
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    if standalone:
+        H.reset()
+    return sample_batch / dt, dt, float(loss)
+
+
+def reference_arm(args):
+    if RANK != 0:
+        return
+    sample = 2
+    steps = max(1, min(args.steps, 3))
+    warm = min(args.warmup, 1)
+    ips, dt, loss = cpu_reference_run(steps, warm, sample)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "WRN-28-10 CIFAR train images/sec", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "WRN-28-10 + dense(100), 3x32x32, SGD lr 0.1 momentum 0.9 wd 1e-4 (examples/cifar100.d recipe)",
+                   "sample": "%d images per step (bounded sample of the 128-image batch)" % sample},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps of %d images, numpy/OpenBLAS oracle over the exported dopt graph" % (steps, sample)},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is D and cannot be built here (no D compiler); its CPU backend also lacks conv-gradient / "
+                "batch-norm kernels, so the port supplies them from the cuDNN definitions (oracle/dopt_ref.py)",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.f.name):
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dopt_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=MODEL["depth"])
+    ap.add_argument("--width", type=int, default=MODEL["width"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import dopt_b200 as db
+    from dopt_b200 import host as H
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(0)
+    world = WORLD
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+    assert H.init(), H.init_error()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if RANK == 0:
+            buf = C.create_string_buffer(128)
+            db.check(db.lib.dopt_b200_comm_unique_id(buf))
+            uid.copy_(torch.tensor(list(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        H.init_data_parallel(RANK, world, bytes(uid.cpu().tolist()))
+
+    B = MODEL["batch"]
+    x, y, net, upd = build_wrn(H, B, args.depth, args.width)
+    n_params = sum(p.volume for p in net.params)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # rotating synthetic batches (different data every step), identical weights on every rank, rank-specific data
+    NB = 4
+    batches = [synthetic_batch(B, 1234 + RANK * 100 + i) for i in range(NB)]
+    pinned = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(l).pin_memory()) for f, l in batches]
+    device = [(f.cuda(), l.cuda()) for f, l in pinned]
+    handles = (C.c_int * 2)(x.h, y.h)
+    nbytes = (C.c_size_t * 2)(pinned[0][0].numel() * 4, pinned[0][1].numel() * 4)
+    loss_out = np.zeros((), np.float32)
+    pred_out = np.zeros((B, MODEL["classes"]), np.float32)
+    out_ptrs = (C.c_void_p * 2)(loss_out.ctypes.data, pred_out.ctypes.data)
+
+    def step_e2e(i):
+        f, l = pinned[i % NB]
+        upd.step_raw(handles, (C.c_void_p * 2)(f.data_ptr(), l.data_ptr()), nbytes, out_ptrs)
+
+    def step_dev(i):
+        f, l = device[i % NB]
+        upd.step_device(handles, (C.c_void_p * 2)(f.data_ptr(), l.data_ptr()))
+
+    # ---- warm-up (sizes workspaces, captures the CUDA graph) ----
+    for i in range(args.warmup):
+        step_dev(i)
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    first_loss = float(loss_out)
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(PHYS_GPU) if RANK == 0 else None
+    launches0 = db.lib.dopt_b200_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = db.lib.dopt_b200_launch_count() - launches0
+
+    # ---- timed: end to end through the public call (H2D from pinned memory + D2H of loss and predictions) ----
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if sampler else None
+    last_loss = float(loss_out)
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of the tcgen05 kernel inside the same step ----
+    roof = None
+    prof = {}
+    if RANK == 0:
+        upd.profile(True)
+        for i in range(2):
+            step_dev(i)
+        torch.cuda.synchronize()
+        prof = upd.profile(False)
+        pk = peaks()
+        tc_us = prof.get("tc_kernel", 0) / 2.0
+        conv_flops = TRAIN_GFLOP_PER_IMAGE * 1e9 * B if (args.depth, args.width) == (28, 10) else None
+        if tc_us > 0 and conv_flops:
+            achieved = conv_flops / (tc_us * 1e-6) / 1e12
+            roof = {"bound": "tensor", "kernel": "tc_kernel<CONV|WGRAD> (tcgen05 implicit GEMM)", "achieved": achieved,
+                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                    "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3}
+    barrier()
+
+    if RANK == 0:
+        st = upd.stats()
+        cpu = None
+        if not args.no_cpu_baseline:
+            ips, dt, _ = cpu_reference_run(1, 0, 2, standalone=False)
+            cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "1 step of 2 images of the same WRN-28-10 train graph, numpy/OpenBLAS oracle (%.1f s)" % dt}
+        ms_step = dev_ms / args.steps
+        line = {
+            "metric": "WRN-28-10 CIFAR train images/sec", "value": B * world * args.steps / (dev_ms * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "WRN-%d-%d + dense(100) + softmax/cross-entropy + weight decay, 3x32x32, batch %d/GPU, "
+                                   "SGD lr 0.1 momentum 0.9 wd 1e-4 (examples/cifar100.d graph)" % (args.depth, args.width, B),
+                       "parallelism": "dp%d" % world, "params": n_params,
+                       "cache": "inputs larger than L2: one step streams several GB of activations through the 126 MB L2",
+                       "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; everything else fp32"},
+            "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(nbytes[0] + nbytes[1]), "d2h_bytes_per_step": int(4 + pred_out.nbytes),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "launches_per_step": st["launches"], "plan_nodes": st["lowered_nodes"],
+            "plan_device_bytes": st["device_bytes"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "loss_first": first_loss, "loss_last": last_loss,
+            "per_op_us_per_step": dict((k, v / 2.0) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:14]),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,8 @@
 
 namespace db {
 uint64_t tc_stage_generation();
+void tc_prof_enable(bool on);
+void tc_prof_read(double* us, int64_t* launches);
 
 namespace {
 
@@ -64,6 +66,8 @@ struct dopt_b200_plan_s {
     int64_t device_bytes = 0;
     int64_t launches_per_exec = 0;
     std::unordered_map<int, void*> var_stage;   // device staging for variables passed as host pointers
+    std::unordered_map<int, void*> var_last;    // last device address seen per variable
+    std::set<int> var_moves;                    // variables whose address changed between executions
     // CUDA graph
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -309,7 +313,23 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             DB_CUDA(cudaMemcpyAsync(st, var_ptrs[i], (size_t)N[id].bytes, cudaMemcpyHostToDevice, s));
             N[id].ptr = st;
         } else {
-            N[id].ptr = const_cast<void*>(var_ptrs[i]);
+            // A device argument whose address changes between executions (a fresh input batch each step) is copied into a
+            // plan-owned buffer from then on, so the captured CUDA graph keeps seeing one address.  Parameters never
+            // move (dopt.online writes new values INTO their buffers, package.d:419-422), so they are read in place.
+            void* ptr = const_cast<void*>(var_ptrs[i]);
+            auto last = p.var_last.find(id);
+            if (last != p.var_last.end() && last->second != ptr && (p.flags & DOPT_B200_PLAN_CUDA_GRAPH))
+                p.var_moves.insert(id);
+            p.var_last[id] = ptr;
+            bool is_ret = false;
+            for (int r = 0; r < n_rets && !is_ret; ++r) is_ret = (rets[r] == ptr);
+            if (p.var_moves.count(id) && !is_ret) {
+                void*& st = p.var_stage[id];
+                if (!st) DB_CUDA(cudaMalloc(&st, (size_t)std::max<int64_t>(N[id].bytes, 16)));
+                DB_CUDA(cudaMemcpyAsync(st, ptr, (size_t)N[id].bytes, cudaMemcpyDeviceToDevice, s));
+                ptr = st;
+            }
+            N[id].ptr = ptr;
         }
         mix((uint64_t)(uintptr_t)N[id].ptr);
     }
@@ -478,13 +498,20 @@ int dopt_b200_plan_profile(dopt_b200_plan_t p, int enable, char* buf, size_t buf
     if (buf && buf_len) {
         std::string s;
         for (auto& kv : p->prof_us) s += kv.first + "=" + std::to_string((long long)kv.second) + "\n";
+        double tus = 0;
+        int64_t tl = 0;
+        db::tc_prof_read(&tus, &tl);
+        s += "tc_kernel=" + std::to_string((long long)tus) + "\ntc_kernel_launches=" + std::to_string((long long)tl) + "\n";
         snprintf(buf, buf_len, "%s", s.c_str());
     }
     if (enable && !p->ev0) {
         DB_CUDA(cudaEventCreate(&p->ev0));
         DB_CUDA(cudaEventCreate(&p->ev1));
     }
-    if (enable != (int)p->profiling) p->prof_us.clear();
+    if (enable != (int)p->profiling) {
+        p->prof_us.clear();
+        db::tc_prof_enable(enable != 0);
+    }
     p->profiling = enable != 0;
     PLAN_CATCH
 }

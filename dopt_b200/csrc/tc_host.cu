@@ -157,6 +157,25 @@ static uint8_t* stage_get(size_t bytes) {
 }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// optional per-launch timing of the tcgen05 kernel alone (bench.py's roofline): enabled together with plan profiling
+static bool g_tc_prof = false;
+static double g_tc_prof_us = 0;
+static int64_t g_tc_prof_launches = 0;
+static cudaEvent_t g_tc_e0 = nullptr, g_tc_e1 = nullptr;
+void tc_prof_enable(bool on) {
+    g_tc_prof = on;
+    g_tc_prof_us = 0;
+    g_tc_prof_launches = 0;
+    if (on && !g_tc_e0) {
+        DB_CUDA(cudaEventCreate(&g_tc_e0));
+        DB_CUDA(cudaEventCreate(&g_tc_e1));
+    }
+}
+void tc_prof_read(double* us, int64_t* launches) {
+    *us = g_tc_prof_us;
+    *launches = g_tc_prof_launches;
+}
+
 template <int MODE>
 static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int n_ctas, cudaStream_t s) {
     TcSmemLayout L = tc_smem_layout(a);
@@ -166,8 +185,17 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         configured = 227 * 1024;
     }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
+    if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_e0, s));
     tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     DB_LAUNCH_CHECK();
+    if (g_tc_prof) {
+        DB_CUDA(cudaEventRecord(g_tc_e1, s));
+        DB_CUDA(cudaEventSynchronize(g_tc_e1));
+        float ms = 0;
+        DB_CUDA(cudaEventElapsedTime(&ms, g_tc_e0, g_tc_e1));
+        g_tc_prof_us += ms * 1000.0;
+        ++g_tc_prof_launches;
+    }
 }
 
 static int pick_stages(TcArgs& a) {

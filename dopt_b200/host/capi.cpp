@@ -455,7 +455,9 @@ int dh_updater_step(int u, const int* arg_ops, const void* const* arg_ptrs, cons
     DH_TRY
     auto& rec = g_updaters.at(u);
     std::map<Operation, Buffer> args;
-    for (int i = 0; i < nargs; ++i) args[op(arg_ops[i])] = buffer(arg_ptrs[i], arg_bytes[i]);
+    // the caller's (pinned) host memory is wrapped, not copied: the H2D copy reads it directly
+    for (int i = 0; i < nargs; ++i)
+        args[op(arg_ops[i])] = std::make_shared<HostBuffer>(const_cast<void*>(arg_ptrs[i]), arg_bytes[i]);
     auto rets = rec.fn(args);
     for (size_t i = 0; i < rets.size(); ++i)
         if (out_ptrs && out_ptrs[i]) rets[i]->get(out_ptrs[i], rets[i]->numBytes());

@@ -21,12 +21,12 @@ void DeviceBuffer::set(const DeviceBuffer& other) {
     set(tmp.data(), tmp.size());
 }
 void HostBuffer::set(const void* buf, size_t bytes) {
-    enforce(bytes == mData.size(), "input buffer is the wrong length.");
-    if (bytes) std::memcpy(mData.data(), buf, bytes);
+    enforce(bytes == numBytes(), "input buffer is the wrong length.");
+    if (bytes) std::memcpy(raw(), buf, bytes);
 }
 void HostBuffer::get(void* buf, size_t bytes) const {
-    enforce(bytes == mData.size(), "output buffer is the wrong length.");
-    if (bytes) std::memcpy(buf, mData.data(), bytes);
+    enforce(bytes == numBytes(), "output buffer is the wrong length.");
+    if (bytes) std::memcpy(buf, raw(), bytes);
 }
 
 // ---- Variant ------------------------------------------------------------------------------------------------------------

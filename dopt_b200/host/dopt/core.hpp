@@ -61,14 +61,18 @@ using Buffer = std::shared_ptr<DeviceBuffer>;
 // plain host memory: what dopt.cpu's CPUBuffer is (cpu/source/dopt/cpu/package.d:34-71); `buffer(fs)` makes these
 class HostBuffer : public DeviceBuffer {
 public:
-    explicit HostBuffer(size_t bytes) : mData(bytes, 0) {}
-    size_t numBytes() const override { return mData.size(); }
+    explicit HostBuffer(size_t bytes) : mData(bytes, 0), mExt(nullptr), mExtBytes(0) {}
+    // non-owning view of caller memory (e.g. a pinned staging buffer): no copy is made
+    HostBuffer(void* external, size_t bytes) : mExt((uint8_t*)external), mExtBytes(bytes) {}
+    size_t numBytes() const override { return mExt ? mExtBytes : mData.size(); }
     void set(const void* buf, size_t bytes) override;
     void get(void* buf, size_t bytes) const override;
-    const void* raw() const { return mData.data(); }
-    void* raw() { return mData.data(); }
+    const void* raw() const { return mExt ? mExt : mData.data(); }
+    void* raw() { return mExt ? mExt : mData.data(); }
 private:
     std::vector<uint8_t> mData;
+    uint8_t* mExt;
+    size_t mExtBytes;
 };
 
 // ---- attributes (std.variant.Variant in D) ---------------------------------------------------------------------------

@@ -14,13 +14,19 @@
 //     core/source/dopt/core/grads/nnet.d:66-83) cost nothing.
 //   * slice(pad(x)) that cuts out exactly x is x (the gradient of the y-slice of the packed BN tensor).
 //   * scalar broadcasts `reshape(matmul(ones[V,1], reshape(s,[1,1])))` (core/source/dopt/core/ops/package.d:96-103,
-//     core/source/dopt/core/ops/basic.d:370-381) are never materialised when their consumers are pointwise binaries: the
-//     pointwise kernel reads the rank-0 operand from device memory.
+//     core/source/dopt/core/ops/basic.d:370-381) are never materialised when their consumers are pointwise ops: the
+//     kernels read the rank-0 operand from device memory.
+//   * connected pointwise nodes of equal volume are fused into regions executed by one interpreter kernel (fused.cu);
+//     regions whose results are only plan outputs (the optimiser updates) are moved to the end of the step, batched by
+//     program into multi-tensor launches, and write straight into the destination buffers when that is hazard-free.
 //   * dead nodes (left over after the rewrites) are dropped.
 // DOPT_B200_PLAN_CUDA_GRAPH captures the launch sequence once and replays it.
 #include "common.cuh"
+#include "fused.cuh"
 #include "pointwise.cuh"
+#include <algorithm>
 #include <map>
+#include <queue>
 #include <set>
 #include <unordered_map>
 
@@ -43,13 +49,32 @@ struct Node {
     int bcast_of = -1;          // this node is a broadcast of the rank-0 node `bcast_of`
     bool folded = false;        // broadcast never materialised
     bool needed = false;
-    // pointwise-with-scalar rewrite
+    // pointwise nodes (float32): op id, which operand is a folded scalar, effective operands
     int pw_op = -1, pw_mode = dbk::B_TENSOR;
+    bool pw_unary = false;
     int eff_in[2] = {-1, -1};
+    int region = -1;
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
     void* ptr = nullptr;        // resolved pointer for this execution
     Kernel* kernel = nullptr;
+};
+
+struct Region {
+    std::vector<int> nodes;     // ascending node ids (topological)
+    bool fused = false;         // >= 2 nodes
+    bool terminal = false;      // every value leaving the region is a plan output only
+    int launch = -1;            // index into Plan::launches
+    int row = -1;
+    std::vector<std::pair<int, int64_t>> tensor_in;   // (root node, byte offset)
+    std::vector<int> scalar_in;                       // scalar node ids
+    std::vector<int> out_nodes;                       // region nodes whose value is needed outside
+};
+
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2 };
+struct Item {
+    int kind;
+    int id;   // node id, or launch index for ITEM_FUSED
 };
 
 static int64_t dtype_size(int) { return 4; }
@@ -62,7 +87,11 @@ struct dopt_b200_plan_s {
     std::vector<int> outputs;
     bool finalized = false;
     int flags = 0;
-    std::vector<int> order;                 // materialised nodes in execution order
+    std::vector<db::Item> order;
+    std::vector<db::Region> regions;
+    std::vector<db::FzLaunch> launches;
+    std::vector<std::vector<int>> launch_regions;   // regions of each launch, row order
+    std::vector<char> direct_out;                   // per plan output: written in place by a fused region
     int64_t device_bytes = 0;
     int64_t launches_per_exec = 0;
     std::unordered_map<int, void*> var_stage;   // device staging for variables passed as host pointers
@@ -71,7 +100,7 @@ struct dopt_b200_plan_s {
     // CUDA graph
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_key = 0;
+    uint64_t graph_key = 0, bound_key = 0;
     int warm_runs = 0;
     // profiler
     bool profiling = false;
@@ -83,6 +112,7 @@ struct dopt_b200_plan_s {
             delete n.kernel;
             if (n.buf) cudaFree(n.buf);
         }
+        for (auto& l : launches) db::fused_free(l);
         for (auto& kv : var_stage) cudaFree(kv.second);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -138,7 +168,18 @@ static bool slice_is_contiguous(const dopt_b200_op& d, int64_t* elem_off) {
     return true;
 }
 
-static void lower(Plan& p) {
+// operands a node really reads after lowering (ids, not roots)
+static std::vector<int> effective_deps(const Node& n) {
+    if (n.alias_of >= 0) return {n.alias_of};
+    if (n.pw_op >= 0) {
+        if (n.pw_unary) return {n.eff_in[0]};
+        return {n.eff_in[0], n.eff_in[1]};
+    }
+    return n.deps;
+}
+
+// ---- pass 1: views, broadcasts ---------------------------------------------------------------------------------------
+static void lower_views(Plan& p) {
     const bool fuse = (p.flags & DOPT_B200_PLAN_FUSE) != 0;
     auto& N = p.nodes;
     for (size_t i = 0; i < N.size(); ++i) {
@@ -151,7 +192,6 @@ static void lower(Plan& p) {
         if (!fuse) continue;
         if (n.type == "slice") {
             int64_t eo = 0;
-            // slice(pad(x)) == x ?
             int src = n.deps[0];
             int64_t src_off = 0;
             int r = root_of(p, src, &src_off);
@@ -179,74 +219,314 @@ static void lower(Plan& p) {
                 n.bcast_of = b;
         }
     }
-    if (fuse) {
-        // consumers of broadcast nodes: pointwise binaries take the scalar directly
-        std::vector<std::vector<int>> users(N.size());
-        for (size_t i = 0; i < N.size(); ++i) {
-            if (N[i].alias_of >= 0) continue;
-            for (int d : N[i].deps) users[root_of(p, d)].push_back((int)i);
-        }
-        std::set<int> out_roots;
-        for (int o : p.outputs) out_roots.insert(root_of(p, o));
-        for (size_t i = 0; i < N.size(); ++i) {
-            Node& n = N[i];
-            if (n.bcast_of < 0) continue;
-            bool ok = !out_roots.count((int)i) && !users[i].empty();
-            for (int u : users[i]) {
-                const Node& c = N[u];
-                int op = pointwise_op_id(c.type.c_str());
-                if (op < 0 || pointwise_is_unary(op) || c.op.output.dtype != DOPT_B200_FLOAT32) { ok = false; break; }
-                int r0 = root_of(p, c.deps[0]), r1 = root_of(p, c.deps[1]);
-                bool b0 = (r0 == (int)i) || (N[r0].bcast_of >= 0), b1 = (r1 == (int)i) || (N[r1].bcast_of >= 0);
-                if (b0 && b1) { ok = false; break; }   // scalar (op) scalar broadcast: keep it simple, materialise
-            }
-            n.folded = ok;
-        }
-        for (size_t i = 0; i < N.size(); ++i) {
-            Node& c = N[i];
-            if (c.alias_of >= 0 || c.deps.size() != 2) continue;
+    if (!fuse) return;
+    std::vector<std::vector<int>> users(N.size());
+    for (size_t i = 0; i < N.size(); ++i) {
+        if (N[i].alias_of >= 0) continue;
+        for (int d : N[i].deps) users[root_of(p, d)].push_back((int)i);
+    }
+    std::set<int> out_roots;
+    for (int o : p.outputs) out_roots.insert(root_of(p, o));
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& n = N[i];
+        if (n.bcast_of < 0) continue;
+        bool ok = !out_roots.count((int)i) && !users[i].empty();
+        for (int u : users[i]) {
+            const Node& c = N[u];
             int op = pointwise_op_id(c.type.c_str());
-            if (op < 0 || pointwise_is_unary(op)) continue;
+            if (op < 0 || pointwise_is_unary(op) || c.op.output.dtype != DOPT_B200_FLOAT32) { ok = false; break; }
             int r0 = root_of(p, c.deps[0]), r1 = root_of(p, c.deps[1]);
-            c.pw_op = op;
-            c.eff_in[0] = c.deps[0];
-            c.eff_in[1] = c.deps[1];
-            if (N[r1].folded) {
-                c.pw_mode = dbk::B_SCALAR_B;
-                c.eff_in[1] = N[r1].bcast_of;
-            } else if (N[r0].folded) {
-                c.pw_mode = dbk::B_SCALAR_A;
-                c.eff_in[0] = N[r0].bcast_of;
-            }
+            bool b0 = (r0 == (int)i) || (N[r0].bcast_of >= 0), b1 = (r1 == (int)i) || (N[r1].bcast_of >= 0);
+            if (b0 && b1) { ok = false; break; }
+        }
+        n.folded = ok;
+    }
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& c = N[i];
+        if (c.alias_of >= 0 || c.op.output.dtype != DOPT_B200_FLOAT32) continue;
+        int op = pointwise_op_id(c.type.c_str());
+        if (op < 0) continue;
+        c.pw_op = op;
+        c.pw_unary = pointwise_is_unary(op);
+        c.eff_in[0] = c.deps[0];
+        if (c.pw_unary) continue;
+        c.eff_in[1] = c.deps[1];
+        int r0 = root_of(p, c.deps[0]), r1 = root_of(p, c.deps[1]);
+        if (N[r1].folded) {
+            c.pw_mode = dbk::B_SCALAR_B;
+            c.eff_in[1] = N[r1].bcast_of;
+        } else if (N[r0].folded) {
+            c.pw_mode = dbk::B_SCALAR_A;
+            c.eff_in[0] = N[r0].bcast_of;
         }
     }
-    // liveness from the outputs
+}
+
+static void mark_needed(Plan& p) {
+    auto& N = p.nodes;
+    for (auto& n : N) n.needed = false;
     std::vector<int> stack(p.outputs.begin(), p.outputs.end());
     while (!stack.empty()) {
         int id = stack.back();
         stack.pop_back();
         if (N[id].needed) continue;
         N[id].needed = true;
-        if (N[id].alias_of >= 0) {
-            stack.push_back(N[id].alias_of);
-            continue;
-        }
-        if (N[id].pw_op >= 0) {
-            stack.push_back(N[id].eff_in[0]);
-            stack.push_back(N[id].eff_in[1]);
-            continue;
-        }
-        for (int d : N[id].deps) stack.push_back(d);
+        for (int d : effective_deps(N[id])) stack.push_back(d);
     }
+}
+
+// ---- pass 2: pointwise regions -------------------------------------------------------------------------------------------
+// does `from` (transitively) read any node of region `rid`?  Nodes older than the region's first node cannot.
+static bool depends_on_region(Plan& p, int from, int rid, int region_first, std::vector<int>& stamp, int mark) {
+    auto& N = p.nodes;
+    std::vector<int> stack{from};
+    while (!stack.empty()) {
+        int id = stack.back();
+        stack.pop_back();
+        if (id < region_first || stamp[id] == mark) continue;
+        stamp[id] = mark;
+        if (N[id].region == rid) return true;
+        for (int d : effective_deps(N[id])) stack.push_back(d);
+    }
+    return false;
+}
+
+static void build_regions(Plan& p) {
+    auto& N = p.nodes;
+    std::vector<int> stamp(N.size(), -1);
+    int mark = 0;
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& v = N[i];
+        if (!v.needed || v.alias_of >= 0 || v.pw_op < 0 || volume(v.op.output) < 1) continue;
+        const int64_t vol = volume(v.op.output);
+        std::vector<int> tens;
+        if (v.pw_unary) tens = {v.eff_in[0]};
+        else {
+            if (v.pw_mode != dbk::B_SCALAR_A) tens.push_back(v.eff_in[0]);
+            if (v.pw_mode != dbk::B_SCALAR_B) tens.push_back(v.eff_in[1]);
+        }
+        int joined = -1;
+        for (int t : tens) {
+            int64_t off = 0;
+            int r = root_of(p, t, &off);
+            if (off != 0 || N[r].region < 0 || volume(N[r].op.output) != vol) continue;
+            int rid = N[r].region;
+            Region& R = p.regions[rid];
+            if ((int)R.nodes.size() >= FZ_MAX_INSTR - 2) continue;
+            // every other operand must be computable before the region runs
+            bool safe = true;
+            for (int d : effective_deps(v)) {
+                int64_t doff = 0;
+                int rd = root_of(p, d, &doff);
+                if (N[rd].region == rid) {
+                    // a partial view of a value produced inside the region would have to be read from memory the same
+                    // launch writes: not fusable
+                    if (doff != 0 || volume(N[rd].op.output) != vol) { safe = false; break; }
+                    continue;
+                }
+                if (depends_on_region(p, rd, rid, R.nodes.front(), stamp, mark++)) { safe = false; break; }
+            }
+            if (!safe) continue;
+            joined = rid;
+            break;
+        }
+        if (joined < 0) {
+            joined = (int)p.regions.size();
+            p.regions.push_back(Region());
+        }
+        p.regions[joined].nodes.push_back((int)i);
+        v.region = joined;
+    }
+    // external inputs / outputs of every region; regions that exceed the interpreter's limits fall back to single nodes
+    std::vector<std::vector<int>> users(N.size());
+    for (size_t i = 0; i < N.size(); ++i) {
+        if (!N[i].needed || N[i].alias_of >= 0) continue;
+        for (int d : effective_deps(N[i])) users[root_of(p, d)].push_back((int)i);
+    }
+    std::set<int> out_roots;
+    for (int o : p.outputs) out_roots.insert(root_of(p, o));
+    for (size_t rid = 0; rid < p.regions.size(); ++rid) {
+        Region& R = p.regions[rid];
+        R.fused = R.nodes.size() >= 2;
+        if (!R.fused) {
+            N[R.nodes[0]].region = -1;
+            continue;
+        }
+        R.terminal = true;
+        for (int id : R.nodes) {
+            Node& v = N[id];
+            auto add_tensor = [&](int t) {
+                int64_t off = 0;
+                int r = root_of(p, t, &off);
+                if (N[r].region == (int)rid && off == 0) return;
+                auto key = std::make_pair(r, off);
+                if (std::find(R.tensor_in.begin(), R.tensor_in.end(), key) == R.tensor_in.end()) R.tensor_in.push_back(key);
+            };
+            auto add_scalar = [&](int s) {
+                if (std::find(R.scalar_in.begin(), R.scalar_in.end(), s) == R.scalar_in.end()) R.scalar_in.push_back(s);
+            };
+            if (v.pw_unary) add_tensor(v.eff_in[0]);
+            else {
+                if (v.pw_mode == dbk::B_SCALAR_A) add_scalar(v.eff_in[0]); else add_tensor(v.eff_in[0]);
+                if (v.pw_mode == dbk::B_SCALAR_B) add_scalar(v.eff_in[1]); else add_tensor(v.eff_in[1]);
+            }
+            bool outside = out_roots.count(id) > 0;
+            bool used_outside = false;
+            for (int u : users[id])
+                if (N[u].region != (int)rid) used_outside = true;
+            if (outside || used_outside) R.out_nodes.push_back(id);
+            if (used_outside) R.terminal = false;
+        }
+        bool fits = (int)R.tensor_in.size() <= FZ_MAX_TENSORS && (int)R.scalar_in.size() <= FZ_MAX_SCALARS &&
+                    (int)R.out_nodes.size() <= FZ_MAX_OUTPUTS && !R.out_nodes.empty() &&
+                    (int)(R.tensor_in.size() + R.scalar_in.size() + R.nodes.size()) <= FZ_MAX_REGS;
+        if (!fits) {
+            for (int id : R.nodes) N[id].region = -1;
+            R.fused = false;
+            R.nodes.clear();
+        }
+    }
+}
+
+static FzProgram make_program(Plan& p, const Region& R) {
+    auto& N = p.nodes;
+    FzProgram g;
+    memset(&g, 0, sizeof(g));
+    g.n_tensors = (int)R.tensor_in.size();
+    g.n_scalars = (int)R.scalar_in.size();
+    std::map<int, int> reg_of;   // region node -> register
+    int next = g.n_tensors + g.n_scalars;
+    auto tensor_reg = [&](int t) {
+        int64_t off = 0;
+        int r = root_of(p, t, &off);
+        if (off == 0) {
+            auto it = reg_of.find(r);
+            if (it != reg_of.end()) return it->second;
+        }
+        auto key = std::make_pair(r, off);
+        return (int)(std::find(R.tensor_in.begin(), R.tensor_in.end(), key) - R.tensor_in.begin());
+    };
+    auto scalar_reg = [&](int s) {
+        return g.n_tensors + (int)(std::find(R.scalar_in.begin(), R.scalar_in.end(), s) - R.scalar_in.begin());
+    };
+    for (int id : R.nodes) {
+        const Node& v = N[id];
+        FzInstr ins;
+        ins.op = (uint8_t)v.pw_op;
+        if (v.pw_unary) {
+            ins.a = ins.b = (uint8_t)tensor_reg(v.eff_in[0]);
+        } else {
+            ins.a = (uint8_t)(v.pw_mode == dbk::B_SCALAR_A ? scalar_reg(v.eff_in[0]) : tensor_reg(v.eff_in[0]));
+            ins.b = (uint8_t)(v.pw_mode == dbk::B_SCALAR_B ? scalar_reg(v.eff_in[1]) : tensor_reg(v.eff_in[1]));
+        }
+        ins.dst = (uint8_t)next;
+        reg_of[id] = next++;
+        g.instr[g.n_instr++] = ins;
+    }
+    g.n_outputs = (int)R.out_nodes.size();
+    for (int o = 0; o < g.n_outputs; ++o) g.out_reg[o] = (uint8_t)reg_of[R.out_nodes[o]];
+    return g;
+}
+
+// ---- pass 3: schedule ------------------------------------------------------------------------------------------------------
+static void schedule(Plan& p) {
+    auto& N = p.nodes;
+    // launches: every non-terminal fused region is its own launch; terminal ones are grouped by program
+    std::map<std::string, int> by_program;
+    std::vector<char> launch_terminal;
+    for (size_t rid = 0; rid < p.regions.size(); ++rid) {
+        Region& R = p.regions[rid];
+        if (!R.fused) continue;
+        FzProgram g = make_program(p, R);
+        int li = -1;
+        if (R.terminal) {
+            std::string key((const char*)&g, sizeof(g));
+            auto it = by_program.find(key);
+            if (it != by_program.end()) li = it->second;
+            else by_program[key] = li = (int)p.launches.size();
+        } else {
+            li = (int)p.launches.size();
+        }
+        if (li == (int)p.launches.size()) {
+            p.launches.push_back(FzLaunch());
+            p.launches.back().prog = g;
+            p.launch_regions.push_back({});
+            launch_terminal.push_back(R.terminal ? 1 : 0);
+        }
+        R.launch = li;
+        R.row = (int)p.launch_regions[li].size();
+        p.launch_regions[li].push_back((int)rid);
+        FzRow blank;
+        memset(&blank, 0, sizeof(blank));
+        p.launches[li].rows.push_back(blank);
+    }
+    // condensed graph: item per materialised non-region node, item per non-terminal launch; terminal launches go last
+    std::vector<int> item_of_node(N.size(), -1);
+    std::vector<Item> items;
+    std::vector<int> item_key;
+    std::map<int, int> item_of_launch;
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& n = N[i];
+        if (!n.needed || n.alias_of >= 0 || n.type == "variable" || n.type == "constant") continue;
+        if (n.region >= 0) {
+            Region& R = p.regions[n.region];
+            if (launch_terminal[R.launch]) continue;
+            auto it = item_of_launch.find(R.launch);
+            if (it == item_of_launch.end()) {
+                items.push_back({ITEM_FUSED, R.launch});
+                item_key.push_back((int)i);
+                it = item_of_launch.emplace(R.launch, (int)items.size() - 1).first;
+            }
+            item_of_node[i] = it->second;
+            continue;
+        }
+        bool scalar_pw = n.pw_op >= 0 && (n.pw_mode != dbk::B_TENSOR);
+        items.push_back({scalar_pw ? ITEM_PW_SCALAR : ITEM_KERNEL, (int)i});
+        item_key.push_back((int)i);
+        item_of_node[i] = (int)items.size() - 1;
+    }
+    std::vector<std::set<int>> succ(items.size());
+    std::vector<int> indeg(items.size(), 0);
+    for (size_t i = 0; i < N.size(); ++i) {
+        int item = item_of_node[i];
+        if (item < 0) continue;
+        for (int d : effective_deps(N[i])) {
+            int src = item_of_node[root_of(p, d)];
+            if (src >= 0 && src != item && succ[src].insert(item).second) ++indeg[item];
+        }
+    }
+    std::priority_queue<std::pair<int, int>, std::vector<std::pair<int, int>>, std::greater<std::pair<int, int>>> ready;
+    for (size_t k = 0; k < items.size(); ++k)
+        if (indeg[k] == 0) ready.push({item_key[k], (int)k});
+    size_t done = 0;
+    while (!ready.empty()) {
+        int k = ready.top().second;
+        ready.pop();
+        p.order.push_back(items[k]);
+        ++done;
+        for (int s : succ[k])
+            if (--indeg[s] == 0) ready.push({item_key[s], s});
+    }
+    DB_REQUIRE(done == items.size(), "plan scheduling failed: cyclic dependency between fused regions");
+    for (size_t li = 0; li < p.launches.size(); ++li)
+        if (launch_terminal[li]) p.order.push_back({ITEM_FUSED, (int)li});
 }
 
 static void build(Plan& p) {
     auto& N = p.nodes;
-    lower(p);
+    lower_views(p);
+    mark_needed(p);
+    if (p.flags & DOPT_B200_PLAN_FUSE) build_regions(p);
     for (size_t i = 0; i < N.size(); ++i) {
         Node& n = N[i];
         if (!n.needed || n.alias_of >= 0) continue;
         if (n.type == "variable") continue;
+        bool interior = false;   // value never leaves its fused region: no buffer
+        if (n.region >= 0) {
+            const Region& R = p.regions[n.region];
+            interior = std::find(R.out_nodes.begin(), R.out_nodes.end(), (int)i) == R.out_nodes.end();
+        }
+        if (interior) continue;
         DB_CUDA(cudaMalloc(&n.buf, (size_t)std::max<int64_t>(n.bytes, 16)));
         p.device_bytes += n.bytes;
         if (n.type == "constant") {
@@ -257,37 +537,101 @@ static void build(Plan& p) {
         // buffers are zeroed once at creation like CUDABuffer.create (package.d:152); batchNormGrad relies on it for the
         // unused tail of its over-allocated result (survey F4)
         DB_CUDA(cudaMemset(n.buf, 0, (size_t)std::max<int64_t>(n.bytes, 16)));
-        if (n.pw_op >= 0 && n.pw_mode != dbk::B_TENSOR) {
-            p.order.push_back((int)i);   // handled by pointwise_launch with a scalar operand
-            continue;
-        }
+        if (n.region >= 0 || (n.pw_op >= 0 && n.pw_mode != dbk::B_TENSOR)) continue;
         Factory f = find_kernel(n.type.c_str());
         if (!f) throw Error("Could not construct a CUDA kernel for operation of type '" + n.type + "'");
         n.op.op_type = n.type.c_str();
         n.kernel = f(n.op);
-        p.order.push_back((int)i);
+    }
+    schedule(p);
+    p.direct_out.assign(p.outputs.size(), 0);
+}
+
+// fill the row tables of the fused launches from the resolved pointers; decide which plan outputs a terminal region may
+// write in place
+static void bind_fused(Plan& p, void* const* rets) {
+    auto& N = p.nodes;
+    std::fill(p.direct_out.begin(), p.direct_out.end(), 0);
+    std::map<int, int> out_index;   // node id -> plan output index (first)
+    for (size_t i = 0; i < p.outputs.size(); ++i) out_index.emplace(p.outputs[i], (int)i);
+    // address -> terminal regions reading it
+    std::map<const char*, std::set<int>> terminal_readers;
+    for (size_t rid = 0; rid < p.regions.size(); ++rid) {
+        const Region& R = p.regions[rid];
+        if (!R.fused || !R.terminal) continue;
+        for (auto& t : R.tensor_in) terminal_readers[(const char*)N[t.first].ptr + t.second].insert((int)rid);
+        for (int s : R.scalar_in) terminal_readers[(const char*)N[s].ptr].insert((int)rid);
+    }
+    for (size_t li = 0; li < p.launches.size(); ++li) {
+        FzLaunch& L = p.launches[li];
+        for (size_t ri = 0; ri < p.launch_regions[li].size(); ++ri) {
+            int rid = p.launch_regions[li][ri];
+            const Region& R = p.regions[rid];
+            FzRow row;
+            memset(&row, 0, sizeof(row));
+            row.n = volume(N[R.nodes[0]].op.output);
+            for (size_t t = 0; t < R.tensor_in.size(); ++t)
+                row.in[t] = (const float*)((const char*)N[R.tensor_in[t].first].ptr + R.tensor_in[t].second);
+            for (size_t s = 0; s < R.scalar_in.size(); ++s) row.scalar[s] = (const float*)N[R.scalar_in[s]].ptr;
+            for (size_t o = 0; o < R.out_nodes.size(); ++o) {
+                int id = R.out_nodes[o];
+                void* dst = N[id].ptr;
+                auto oi = out_index.find(id);
+                if (R.terminal && oi != out_index.end() && rets[oi->second] != nullptr) {
+                    // In-place write-back is safe when nobody else in the end-of-step batch reads the destination: every
+                    // other reader ran earlier, and this region reads an element before it overwrites that element.
+                    char* target = (char*)rets[oi->second];
+                    bool other_reader = false;
+                    for (auto& kv : terminal_readers) {
+                        if (kv.first < target || kv.first >= target + N[id].bytes) continue;
+                        for (int reader : kv.second)
+                            if (reader != rid || kv.first != target) other_reader = true;
+                    }
+                    int dup = 0;
+                    for (size_t k = 0; k < p.outputs.size(); ++k)
+                        if (rets[k] == (void*)target || p.outputs[k] == id) ++dup;
+                    if (!other_reader && dup == 1) {
+                        dst = target;
+                        p.direct_out[oi->second] = 1;
+                    }
+                }
+                row.out[o] = (float*)dst;
+            }
+            row.chunk0 = L.rows[ri].chunk0;
+            if (memcmp(&row, &L.rows[ri], sizeof(row)) != 0) {
+                L.rows[ri] = row;
+                L.dirty = true;
+            }
+        }
     }
 }
 
-static void run_nodes(Plan& p, cudaStream_t s) {
+static void run_items(Plan& p, cudaStream_t s) {
     auto& N = p.nodes;
-    for (int id : p.order) {
-        Node& n = N[id];
+    for (const Item& it : p.order) {
         if (p.profiling) DB_CUDA(cudaEventRecord(p.ev0, s));
-        if (n.kernel) {
+        const char* label;
+        if (it.kind == ITEM_KERNEL) {
+            Node& n = N[it.id];
             const void* in[DOPT_B200_MAX_INPUTS];
             for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.deps[k]].ptr;
             n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
-        } else {
+            label = n.type.c_str();
+        } else if (it.kind == ITEM_PW_SCALAR) {
+            Node& n = N[it.id];
             pointwise_launch(n.pw_op, n.op.output.dtype, n.pw_mode, N[n.eff_in[0]].ptr, N[n.eff_in[1]].ptr, n.ptr,
                              volume(n.op.output), s);
+            label = n.type.c_str();
+        } else {
+            fused_launch(p.launches[it.id], s);
+            label = "fusedRegion";
         }
         if (p.profiling) {
             DB_CUDA(cudaEventRecord(p.ev1, s));
             DB_CUDA(cudaEventSynchronize(p.ev1));
             float ms = 0;
             DB_CUDA(cudaEventElapsedTime(&ms, p.ev0, p.ev1));
-            p.prof_us[n.type] += ms * 1000.0;
+            p.prof_us[label] += ms * 1000.0;
         }
     }
 }
@@ -297,9 +641,7 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
     DB_REQUIRE(p.finalized, "plan not finalized");
     DB_REQUIRE(n_rets == (int)p.outputs.size(), "wrong number of return buffers");
     auto& N = p.nodes;
-    // bind variables
-    for (auto& n : N)
-        if (n.type == "variable") n.ptr = nullptr;
+    std::vector<void*> bound(N.size(), nullptr);
     uint64_t key = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
     for (int i = 0; i < n_vars; ++i) {
@@ -311,7 +653,7 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             void*& st = p.var_stage[id];
             if (!st) DB_CUDA(cudaMalloc(&st, (size_t)std::max<int64_t>(N[id].bytes, 16)));
             DB_CUDA(cudaMemcpyAsync(st, var_ptrs[i], (size_t)N[id].bytes, cudaMemcpyHostToDevice, s));
-            N[id].ptr = st;
+            bound[id] = st;
         } else {
             // A device argument whose address changes between executions (a fresh input batch each step) is copied into a
             // plan-owned buffer from then on, so the captured CUDA graph keeps seeing one address.  Parameters never
@@ -329,33 +671,38 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
                 DB_CUDA(cudaMemcpyAsync(st, ptr, (size_t)N[id].bytes, cudaMemcpyDeviceToDevice, s));
                 ptr = st;
             }
-            N[id].ptr = ptr;
+            bound[id] = ptr;
         }
-        mix((uint64_t)(uintptr_t)N[id].ptr);
+        mix((uint64_t)(uintptr_t)id * 1315423911ull + (uint64_t)(uintptr_t)bound[id]);
     }
     for (int i = 0; i < n_rets; ++i) mix((uint64_t)(uintptr_t)rets[i]);
     mix(tc_stage_generation());
-    // resolve pointers
-    for (size_t i = 0; i < N.size(); ++i) {
-        Node& n = N[i];
-        if (!n.needed) continue;
-        if (n.type == "variable") {
-            DB_REQUIRE(n.ptr != nullptr, "plan_execute: a variable the plan reads was not bound");
-        } else if (n.alias_of < 0) {
-            n.ptr = n.buf;
+    if (key != p.bound_key) {
+        for (size_t i = 0; i < N.size(); ++i) {
+            Node& n = N[i];
+            if (!n.needed) continue;
+            if (n.type == "variable") {
+                DB_REQUIRE(bound[i] != nullptr, "plan_execute: a variable the plan reads was not bound");
+                n.ptr = bound[i];
+            } else if (n.alias_of < 0) {
+                n.ptr = n.buf;
+            }
         }
-    }
-    for (size_t i = 0; i < N.size(); ++i) {
-        Node& n = N[i];
-        if (!n.needed || n.alias_of < 0) continue;
-        int64_t off = 0;
-        int r = root_of(p, (int)i, &off);
-        n.ptr = (char*)N[r].ptr + off;
+        for (size_t i = 0; i < N.size(); ++i) {
+            Node& n = N[i];
+            if (!n.needed || n.alias_of < 0) continue;
+            int64_t off = 0;
+            int r = root_of(p, (int)i, &off);
+            n.ptr = (char*)N[r].ptr + off;
+        }
+        bind_fused(p, rets);
+        p.bound_key = key;
     }
     auto body = [&](cudaStream_t st) {
-        run_nodes(p, st);
+        run_items(p, st);
         for (int i = 0; i < n_rets; ++i) {
             const Node& o = N[p.outputs[i]];
+            if (p.direct_out[i]) continue;
             if (o.bytes > 0 && rets[i] != o.ptr) {
                 DB_CUDA(cudaMemcpyAsync(rets[i], o.ptr, (size_t)o.bytes, cudaMemcpyDeviceToDevice, st));
                 count_launch();
@@ -374,8 +721,11 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
         count_launch((int)p.launches_per_exec);
         return;
     }
-    if (p.warm_runs < 1) {
-        // first execution runs eagerly: it sizes every workspace so that nothing allocates during capture
+    bool dirty = false;
+    for (auto& L : p.launches) dirty = dirty || L.dirty;
+    if (p.warm_runs < 1 || dirty) {
+        // eager execution: the first one sizes every workspace so that nothing allocates during capture; later ones
+        // re-upload fused row tables after a pointer change (uploads cannot happen inside a capture)
         uint64_t l0 = g_launches.load();
         body(s);
         p.launches_per_exec = (int64_t)(g_launches.load() - l0);

@@ -186,7 +186,23 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
     if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_e0, s));
-    tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+    if (a.cluster > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)n_ctas);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = L.total;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)a.cluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE>, tmA, tmB, a));
+    } else {
+        tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+    }
     DB_LAUNCH_CHECK();
     if (g_tc_prof) {
         DB_CUDA(cudaEventRecord(g_tc_e1, s));
@@ -207,6 +223,22 @@ static int pick_stages(TcArgs& a) {
     if (st > 8) st = 8;
     if (st < 2) st = 2;
     return st;
+}
+
+// CTAs per cluster that share one filter tile through TMA multicast.  The implicit-GEMM kernel is bound by L2->SM
+// bandwidth (profiles/r01a_tc_kernel.md): every CTA of a 128 x BN tile pulls the full BN x 64 filter slab per k-step.
+// With a cluster of c CTAs working on c different pixel tiles, each CTA pulls 1/c of it.
+static int g_max_cluster = 4;
+void tc_set_max_cluster(int c) { g_max_cluster = c; }
+static int pick_cluster(int m_tiles, int bn) {
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char* e = getenv("DOPT_B200_MAX_CLUSTER")) g_max_cluster = atoi(e);   // tuning knob for experiments
+    }
+    for (int c = g_max_cluster; c > 1; c >>= 1)
+        if (m_tiles >= 2 * c && bn % (8 * c) == 0) return c;
+    return 1;
 }
 
 static int pick_bn(int nout) {
@@ -244,7 +276,9 @@ TcGemm* tc_gemm_create(int64_t M, int64_t N, int64_t K) {
     a.out_kind = TC_OUT_F32;
     a.o_sn = N; a.o_sc = 1;
     a.stages = pick_stages(a);
-    g->n_ctas = (int)(ceil_div(M, TC_BM) * a.n_tiles);
+    a.m_tiles = (int)ceil_div(M, TC_BM);
+    a.cluster = 1;
+    g->n_ctas = a.m_tiles * a.n_tiles;
     return g;
 }
 void tc_gemm_run(TcGemm* g, const float* A, const float* B, float* C, cudaStream_t s) {
@@ -351,7 +385,11 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     TcArgs a{};
     a.mode = TC_MODE_CONV;
     a.BN = pick_bn(g.K);
-    make_map_2d(&tmB, wp, (uint64_t)RS * Cp, (uint64_t)g.K, (uint64_t)RS * Cp, 64, (uint32_t)a.BN, "convolution w");
+    a.m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
+    a.cluster = pick_cluster(a.m_tiles, a.BN);
+    a.m_tiles = (int)align_up(a.m_tiles, a.cluster);
+    make_map_2d(&tmB, wp, (uint64_t)RS * Cp, (uint64_t)g.K, (uint64_t)RS * Cp, 64, (uint32_t)(a.BN / a.cluster),
+                "convolution w");
     a.n_tiles = (int)ceil_div(g.K, a.BN);
     a.splits = 1;
     a.taps = RS;
@@ -374,8 +412,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
     a.stages = pick_stages(a);
-    int n_ctas = b.tiles_n * b.tiles_p * b.tiles_q * a.n_tiles;
-    tc_launch<TC_MODE_CONV>(tmA, tmB, a, n_ctas, s);
+    tc_launch<TC_MODE_CONV>(tmA, tmB, a, a.m_tiles * a.n_tiles, s);
 }
 
 static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cudaStream_t s) {
@@ -392,7 +429,10 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, b.bh, b.bw, 1, 1, "convolutionFeaturesGrad dy");
     int BN = pick_bn(g.C);
-    make_map_2d(&tmB, wp, (uint64_t)RS * Kp, (uint64_t)g.C, (uint64_t)RS * Kp, 64, (uint32_t)BN,
+    int m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
+    int cluster = pick_cluster(m_tiles, BN);
+    m_tiles = (int)align_up(m_tiles, cluster);
+    make_map_2d(&tmB, wp, (uint64_t)RS * Kp, (uint64_t)g.C, (uint64_t)RS * Kp, 64, (uint32_t)(BN / cluster),
                 "convolutionFeaturesGrad w");
     bool need_zero = false;
     std::vector<TcArgs> launches;
@@ -401,6 +441,8 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             TcArgs a{};
             a.mode = TC_MODE_CONV;
             a.BN = BN;
+            a.m_tiles = m_tiles;
+            a.cluster = cluster;
             a.n_tiles = (int)ceil_div(g.C, BN);
             a.splits = 1;
             a.c_iters = (int)ceil_div(g.K, TC_BK);
@@ -439,10 +481,7 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
         DB_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.N * g.C * g.H * g.W * sizeof(float), s));
         count_launch();
     }
-    for (auto& a : launches) {
-        int n_ctas = b.tiles_n * b.tiles_p * b.tiles_q * a.n_tiles;
-        tc_launch<TC_MODE_CONV>(tmA, tmB, a, n_ctas, s);
-    }
+    for (auto& a : launches) tc_launch<TC_MODE_CONV>(tmA, tmB, a, a.m_tiles * a.n_tiles, s);
 }
 
 static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cudaStream_t s) {
@@ -488,6 +527,8 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     int want = 2 * sm_count();
     a.splits = std::max(1, std::min(a.pix_tiles, (int)ceil_div(want, tiles)));
     a.stages = pick_stages(a);
+    a.m_tiles = RS * mt;
+    a.cluster = 1;
     tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, tiles * a.splits, s);
 }
 

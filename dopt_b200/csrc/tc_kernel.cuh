@@ -28,7 +28,9 @@ struct TcArgs {
     int mode;
     int BN;             // accumulator columns (multiple of 16, <= 256)
     int stages;
-    int n_tiles;        // tiles along N; blockIdx.x = (m_tile * n_tiles + n_tile) * splits + split
+    int n_tiles;        // tiles along N; blockIdx.x = ((n_tile * splits) + split) * m_tiles + m_tile
+    int m_tiles;        // tiles along M (padded to a multiple of `cluster`)
+    int cluster;        // CTAs per cluster sharing one B tile through TMA multicast (1, 2 or 4; CONV mode)
     int splits;
     int k_iters;        // total k-iterations of the problem (divided over splits)
     // ---- GEMM
@@ -93,10 +95,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
 
     // ---- tile coordinates
     int bid = blockIdx.x;
+    const int m_tile = bid % args.m_tiles;   // fastest: the CTAs of one cluster differ only in their M tile
+    bid /= args.m_tiles;
     const int split = bid % args.splits;
-    bid /= args.splits;
-    const int n_tile = bid % args.n_tiles;
-    const int m_tile = bid / args.n_tiles;
+    const int n_tile = bid / args.splits;
+    const int csize = (MODE == TC_MODE_CONV) ? args.cluster : 1;
+    const uint32_t crank = csize > 1 ? tcg::cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
     int it_begin, it_end;
     {
         int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : args.k_iters;
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         tcg::tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) {
             tcg::mbar_init(&full_bar[i], 1);
-            tcg::mbar_init(&empty_bar[i], 1);
+            tcg::mbar_init(&empty_bar[i], (uint32_t)csize);   // every CTA that receives multicast data must release the stage
         }
         tcg::mbar_init(tmem_full_bar, 1);
         tcg::fence_barrier_init();
@@ -141,7 +146,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         tcg::tmem_relinquish();
     }
     tcg::tc_fence_before();
-    __syncthreads();
+    if (csize > 1) tcg::cluster_sync();   // peers' barriers must exist before the first remote arrive / multicast write
+    else __syncthreads();
     tcg::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -167,7 +173,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     tcg::mbar_arrive_expect_tx(&full_bar[st], a_bytes + (uint32_t)BN * 128u);
                     tcg::tma_load_4d(sa, &tmA, &full_bar[st], cb * TC_BK, q0 * args.a_sv + args.tap_dw[t],
                                      p0 * args.a_su + args.tap_dh[t], img0);
-                    tcg::tma_load_2d(sb, &tmB, &full_bar[st], args.tap_bcol[t] + cb * TC_BK, n_tile * BN);
+                    if (csize == 1) {
+                        tcg::tma_load_2d(sb, &tmB, &full_bar[st], args.tap_bcol[t] + cb * TC_BK, n_tile * BN);
+                    } else {
+                        // this CTA fetches 1/csize of the filter tile and multicasts it to the whole cluster
+                        const int rows = BN / csize;
+                        tcg::tma_load_2d_mcast(sb + (size_t)crank * rows * 128, &tmB, &full_bar[st],
+                                               args.tap_bcol[t] + cb * TC_BK, n_tile * BN + (int)crank * rows, cmask);
+                    }
                 } else {
                     // WGRAD: `it` is a pixel box index -> (image group, row tile, col tile)
                     int tq = it % args.tiles_q;
@@ -220,7 +233,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         tcg::umma_bf16(tmem_base, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                     }
                 }
-                tcg::umma_commit(&empty_bar[st]);   // frees the stage once these MMAs have read it
+                // frees the stage once these MMAs have read it (cluster-wide when the stage holds multicast data)
+                if (csize == 1) tcg::umma_commit(&empty_bar[st]);
+                else tcg::umma_commit_mcast(&empty_bar[st], cmask);
             }
             tcg::umma_commit(tmem_full_bar);        // accumulator complete
         }
@@ -291,8 +306,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         }
     }
 
+    __syncwarp();   // the single-lane producer / issuer loops diverged their warps; the cluster barrier is warp-aligned
     tcg::tc_fence_before();
-    __syncthreads();
+    if (csize > 1) tcg::cluster_sync();   // nobody leaves while a peer may still write into / arrive on this CTA
+    else __syncthreads();
     if (warp == 1) {
         tcg::tc_fence_after();
         tcg::tmem_dealloc(tmem_base, tmem_cols);

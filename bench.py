@@ -277,13 +277,13 @@ def main():
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of the tcgen05 kernel inside the same step ----
     roof = None
-    prof = {}
+    # every rank runs the profiled steps (the plan contains the gradient all-reduce); rank 0 reports
+    upd.profile(True)
+    for i in range(2):
+        step_dev(i)
+    torch.cuda.synchronize()
+    prof = upd.profile(False)
     if RANK == 0:
-        upd.profile(True)
-        for i in range(2):
-            step_dev(i)
-        torch.cuda.synchronize()
-        prof = upd.profile(False)
         pk = peaks()
         tc_us = prof.get("tc_kernel", 0) / 2.0
         conv_flops = TRAIN_GFLOP_PER_IMAGE * 1e9 * B if (args.depth, args.width) == (28, 10) else None

@@ -14,7 +14,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat = 7, ncclSum = 0 };
+enum { ncclFloat = 7, ncclSum = 0, ncclAvg = 4 };
 
 struct Nccl {
     void* h = nullptr;
@@ -57,6 +57,14 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, int64
 }  // namespace
 
 int comm_world() { return g_world; }
+
+// mean over ranks, in place, one NCCL call (ncclAvg); used by the plan's gradient buckets
+void allreduce_mean(float* buf, int64_t n, cudaStream_t s) {
+    if (n <= 0 || g_world <= 1) return;
+    DB_REQUIRE(g_comm != nullptr, "allreduce: communicator not initialised (dopt_b200_comm_init)");
+    nccl_check(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclAvg, g_comm, s), "ncclAllReduce");
+    count_launch();
+}
 
 namespace {
 // `allreduce` graph node (registered through dopt's registerOperation / registerCUDAKernel like any other op): the mean

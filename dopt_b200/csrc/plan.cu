@@ -34,6 +34,8 @@ namespace db {
 uint64_t tc_stage_generation();
 void tc_prof_enable(bool on);
 void tc_prof_read(double* us, int64_t* launches);
+void allreduce_mean(float* buf, int64_t n, cudaStream_t s);
+int comm_world();
 
 namespace {
 
@@ -54,6 +56,8 @@ struct Node {
     bool pw_unary = false;
     int eff_in[2] = {-1, -1};
     int region = -1;
+    int bucket = -1;            // allreduce node reduced in place as part of gradient bucket `bucket` (node is a view of its operand)
+    int lvl = 0;                // ASAP level (scheduling priority)
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
     void* ptr = nullptr;        // resolved pointer for this execution
@@ -71,10 +75,18 @@ struct Region {
     std::vector<int> out_nodes;                       // region nodes whose value is needed outside
 };
 
-enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2 };
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4 };
 struct Item {
     int kind;
-    int id;   // node id, or launch index for ITEM_FUSED
+    int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
+    bool join_comm;     // reads a reduced gradient: the compute stream must first wait for the communication stream
+};
+
+// gradients that are all-reduced together: their buffers are carved from one arena so that ONE ncclAllReduce covers them
+struct Bucket {
+    std::vector<int> members;   // allreduce node ids
+    void* arena = nullptr;
+    int64_t bytes = 0;
 };
 
 static int64_t dtype_size(int) { return 4; }
@@ -92,6 +104,9 @@ struct dopt_b200_plan_s {
     std::vector<db::FzLaunch> launches;
     std::vector<std::vector<int>> launch_regions;   // regions of each launch, row order
     std::vector<char> direct_out;                   // per plan output: written in place by a fused region
+    std::vector<db::Bucket> buckets;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     int64_t device_bytes = 0;
     int64_t launches_per_exec = 0;
     std::unordered_map<int, void*> var_stage;   // device staging for variables passed as host pointers
@@ -113,6 +128,11 @@ struct dopt_b200_plan_s {
             if (n.buf) cudaFree(n.buf);
         }
         for (auto& l : launches) db::fused_free(l);
+        for (auto& b : buckets)
+            if (b.arena) cudaFree(b.arena);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
+        if (comm_fork) cudaEventDestroy(comm_fork);
+        if (comm_join) cudaEventDestroy(comm_join);
         for (auto& kv : var_stage) cudaFree(kv.second);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -241,6 +261,21 @@ static void lower_views(Plan& p) {
         }
         n.folded = ok;
     }
+    // `allreduce` in place: when the gradient it reduces has no other reader, the node becomes a view of its operand and the
+    // reduction is performed on that buffer as part of a bucket (see schedule())
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& n = N[i];
+        if (n.type != "allreduce" || comm_world() <= 1) continue;
+        int64_t off = 0;
+        int r = root_of(p, n.deps[0], &off);
+        n.bucket = -2;   // bucket assigned in form_buckets()
+        // gradients that are views (BN scale / bias slices of the packed result), variables or shared with other readers
+        // are copied into the bucket arena instead of being reduced where they are
+        if (off != 0 || N[r].type == "variable" || N[r].type == "constant" || out_roots.count(r)) continue;
+        if (users[r].size() != 1 || volume(N[r].op.output) != volume(n.op.output)) continue;
+        n.alias_of = n.deps[0];
+        n.alias_off = 0;
+    }
     for (size_t i = 0; i < N.size(); ++i) {
         Node& c = N[i];
         if (c.alias_of >= 0 || c.op.output.dtype != DOPT_B200_FLOAT32) continue;
@@ -291,6 +326,16 @@ static bool depends_on_region(Plan& p, int from, int rid, int region_first, std:
     return false;
 }
 
+// does the view chain of `id` pass through an in-place allreduce?  Such a value only exists after its bucket was reduced, so
+// pointwise fusion must not reach across it.
+static bool crosses_reduce(Plan& p, int id) {
+    while (p.nodes[id].alias_of >= 0) {
+        if (p.nodes[id].bucket != -1) return true;
+        id = p.nodes[id].alias_of;
+    }
+    return p.nodes[id].bucket != -1;   // a copy-in bucket member is its own root
+}
+
 static void build_regions(Plan& p) {
     auto& N = p.nodes;
     std::vector<int> stamp(N.size(), -1);
@@ -309,7 +354,7 @@ static void build_regions(Plan& p) {
         for (int t : tens) {
             int64_t off = 0;
             int r = root_of(p, t, &off);
-            if (off != 0 || N[r].region < 0 || volume(N[r].op.output) != vol) continue;
+            if (off != 0 || N[r].region < 0 || volume(N[r].op.output) != vol || crosses_reduce(p, t)) continue;
             int rid = N[r].region;
             Region& R = p.regions[rid];
             if ((int)R.nodes.size() >= FZ_MAX_INSTR - 2) continue;
@@ -320,8 +365,8 @@ static void build_regions(Plan& p) {
                 int rd = root_of(p, d, &doff);
                 if (N[rd].region == rid) {
                     // a partial view of a value produced inside the region would have to be read from memory the same
-                    // launch writes: not fusable
-                    if (doff != 0 || volume(N[rd].op.output) != vol) { safe = false; break; }
+                    // launch writes, and a reduced gradient does not exist before its bucket ran: not fusable
+                    if (doff != 0 || volume(N[rd].op.output) != vol || crosses_reduce(p, d)) { safe = false; break; }
                     continue;
                 }
                 if (depends_on_region(p, rd, rid, R.nodes.front(), stamp, mark++)) { safe = false; break; }
@@ -460,11 +505,15 @@ static void schedule(Plan& p) {
         memset(&blank, 0, sizeof(blank));
         p.launches[li].rows.push_back(blank);
     }
-    // condensed graph: item per materialised non-region node, item per non-terminal launch; terminal launches go last
+    // condensed graph: item per materialised non-region node, per non-terminal launch, per gradient bucket; terminal
+    // launches go last.  Ready items are issued in ASAP-level order, so a filter gradient (and the all-reduce of its bucket)
+    // is launched as soon as its inputs exist instead of where the host's depth-first order happened to put it.
     std::vector<int> item_of_node(N.size(), -1);
     std::vector<Item> items;
-    std::vector<int> item_key;
+    std::vector<int64_t> item_key;
     std::map<int, int> item_of_launch;
+    std::vector<int> item_of_bucket(p.buckets.size(), -1);
+    auto key_of = [&](int node) { return ((int64_t)N[node].lvl << 32) | (int64_t)node; };
     for (size_t i = 0; i < N.size(); ++i) {
         Node& n = N[i];
         if (!n.needed || n.alias_of >= 0 || n.type == "variable" || n.type == "constant") continue;
@@ -473,29 +522,61 @@ static void schedule(Plan& p) {
             if (launch_terminal[R.launch]) continue;
             auto it = item_of_launch.find(R.launch);
             if (it == item_of_launch.end()) {
-                items.push_back({ITEM_FUSED, R.launch});
-                item_key.push_back((int)i);
+                items.push_back({ITEM_FUSED, R.launch, false});
+                item_key.push_back(0);
                 it = item_of_launch.emplace(R.launch, (int)items.size() - 1).first;
             }
             item_of_node[i] = it->second;
+            item_key[it->second] = std::max(item_key[it->second], key_of((int)i));
             continue;
         }
         bool scalar_pw = n.pw_op >= 0 && (n.pw_mode != dbk::B_TENSOR);
-        items.push_back({scalar_pw ? ITEM_PW_SCALAR : ITEM_KERNEL, (int)i});
-        item_key.push_back((int)i);
+        int kind = n.bucket >= 0 ? ITEM_COPY : (scalar_pw ? ITEM_PW_SCALAR : ITEM_KERNEL);
+        items.push_back({kind, (int)i, false});
+        item_key.push_back(key_of((int)i));
         item_of_node[i] = (int)items.size() - 1;
     }
+    for (size_t b = 0; b < p.buckets.size(); ++b) {
+        items.push_back({ITEM_BUCKET, (int)b, false});
+        int64_t k = 0;
+        for (int m : p.buckets[b].members) k = std::max(k, key_of(root_of(p, m)));
+        item_key.push_back(k + 1);
+        item_of_bucket[b] = (int)items.size() - 1;
+    }
+    // the item that makes the value read through `d` available: the bucket when the view chain passes an in-place allreduce
+    auto producer_item = [&](int d, bool* via_bucket) {
+        int id = d;
+        while (N[id].alias_of >= 0) {
+            if (N[id].bucket >= 0) {
+                if (via_bucket) *via_bucket = true;
+                return item_of_bucket[N[id].bucket];
+            }
+            id = N[id].alias_of;
+        }
+        if (N[id].bucket >= 0) {   // copy-in member
+            if (via_bucket) *via_bucket = true;
+            return item_of_bucket[N[id].bucket];
+        }
+        return item_of_node[id];
+    };
     std::vector<std::set<int>> succ(items.size());
     std::vector<int> indeg(items.size(), 0);
+    auto add_edge = [&](int src, int dst) {
+        if (src >= 0 && src != dst && succ[src].insert(dst).second) ++indeg[dst];
+    };
     for (size_t i = 0; i < N.size(); ++i) {
         int item = item_of_node[i];
         if (item < 0) continue;
         for (int d : effective_deps(N[i])) {
-            int src = item_of_node[root_of(p, d)];
-            if (src >= 0 && src != item && succ[src].insert(item).second) ++indeg[item];
+            bool via = false;
+            add_edge(producer_item(d, &via), item);
+            if (via) items[item].join_comm = true;
         }
     }
-    std::priority_queue<std::pair<int, int>, std::vector<std::pair<int, int>>, std::greater<std::pair<int, int>>> ready;
+    for (size_t b = 0; b < p.buckets.size(); ++b)
+        for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
+    using QE = std::pair<int64_t, int>;
+    std::priority_queue<QE, std::vector<QE>, std::greater<QE>> ready;
     for (size_t k = 0; k < items.size(); ++k)
         if (indeg[k] == 0) ready.push({item_key[k], (int)k});
     size_t done = 0;
@@ -509,7 +590,46 @@ static void schedule(Plan& p) {
     }
     DB_REQUIRE(done == items.size(), "plan scheduling failed: cyclic dependency between fused regions");
     for (size_t li = 0; li < p.launches.size(); ++li)
-        if (launch_terminal[li]) p.order.push_back({ITEM_FUSED, (int)li});
+        if (launch_terminal[li]) {
+            bool join = false;
+            for (int rid : p.launch_regions[li])
+                for (int nid : p.regions[rid].nodes)
+                    for (int d : effective_deps(N[nid])) {
+                        bool via = false;
+                        producer_item(d, &via);
+                        join = join || via;
+                    }
+            p.order.push_back({ITEM_FUSED, (int)li, join});
+        }
+}
+
+// ASAP levels and gradient buckets (before buffers are allocated: bucket members share one arena)
+static void form_buckets(Plan& p) {
+    auto& N = p.nodes;
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& n = N[i];
+        n.lvl = 0;
+        if (!n.needed || n.type == "variable" || n.type == "constant") continue;
+        int l = 0;
+        for (int d : effective_deps(n)) l = std::max(l, N[n.alias_of >= 0 ? d : root_of(p, d)].lvl + (n.alias_of >= 0 ? 0 : 1));
+        n.lvl = l;
+    }
+    std::vector<int> members;
+    for (size_t i = 0; i < N.size(); ++i)
+        if (N[i].needed && N[i].bucket == -2) members.push_back((int)i);
+    std::sort(members.begin(), members.end(), [&](int a, int b) {
+        return std::make_pair(N[a].lvl, a) < std::make_pair(N[b].lvl, b);
+    });
+    static const int64_t kBucketBytes = 32ll << 20;
+    for (int m : members) {
+        if (p.buckets.empty() || p.buckets.back().bytes >= kBucketBytes) p.buckets.push_back(Bucket());
+        Bucket& b = p.buckets.back();
+        b.members.push_back(m);
+        b.bytes += (N[m].bytes + 255) / 256 * 256;
+        N[m].bucket = (int)p.buckets.size() - 1;
+    }
+    for (auto& n : N)
+        if (n.bucket == -2) n.bucket = -1;   // not needed after all
 }
 
 static void build(Plan& p) {
@@ -517,6 +637,18 @@ static void build(Plan& p) {
     lower_views(p);
     mark_needed(p);
     if (p.flags & DOPT_B200_PLAN_FUSE) build_regions(p);
+    form_buckets(p);
+    std::map<int, void*> arena_slot;   // root node of a bucket member -> its slice of the bucket arena
+    for (auto& b : p.buckets) {
+        DB_CUDA(cudaMalloc(&b.arena, (size_t)std::max<int64_t>(b.bytes, 256)));
+        DB_CUDA(cudaMemset(b.arena, 0, (size_t)std::max<int64_t>(b.bytes, 256)));
+        p.device_bytes += b.bytes;
+        int64_t off = 0;
+        for (int m : b.members) {
+            arena_slot[root_of(p, m)] = (char*)b.arena + off;
+            off += (N[m].bytes + 255) / 256 * 256;
+        }
+    }
     for (size_t i = 0; i < N.size(); ++i) {
         Node& n = N[i];
         if (!n.needed || n.alias_of >= 0) continue;
@@ -527,8 +659,13 @@ static void build(Plan& p) {
             interior = std::find(R.out_nodes.begin(), R.out_nodes.end(), (int)i) == R.out_nodes.end();
         }
         if (interior) continue;
-        DB_CUDA(cudaMalloc(&n.buf, (size_t)std::max<int64_t>(n.bytes, 16)));
-        p.device_bytes += n.bytes;
+        auto slot = arena_slot.find((int)i);
+        if (slot != arena_slot.end()) {
+            n.ptr = slot->second;   // lives in a gradient bucket arena (n.buf stays null: the arena owns the memory)
+        } else {
+            DB_CUDA(cudaMalloc(&n.buf, (size_t)std::max<int64_t>(n.bytes, 16)));
+            p.device_bytes += n.bytes;
+        }
         if (n.type == "constant") {
             DB_REQUIRE((int64_t)n.const_value.size() == n.bytes, "constant node without a value");
             DB_CUDA(cudaMemcpy(n.buf, n.const_value.data(), (size_t)n.bytes, cudaMemcpyHostToDevice));
@@ -536,8 +673,8 @@ static void build(Plan& p) {
         }
         // buffers are zeroed once at creation like CUDABuffer.create (package.d:152); batchNormGrad relies on it for the
         // unused tail of its over-allocated result (survey F4)
-        DB_CUDA(cudaMemset(n.buf, 0, (size_t)std::max<int64_t>(n.bytes, 16)));
-        if (n.region >= 0 || (n.pw_op >= 0 && n.pw_mode != dbk::B_TENSOR)) continue;
+        if (n.buf) DB_CUDA(cudaMemset(n.buf, 0, (size_t)std::max<int64_t>(n.bytes, 16)));
+        if (n.region >= 0 || (n.pw_op >= 0 && n.pw_mode != dbk::B_TENSOR) || n.bucket >= 0) continue;
         Factory f = find_kernel(n.type.c_str());
         if (!f) throw Error("Could not construct a CUDA kernel for operation of type '" + n.type + "'");
         n.op.op_type = n.type.c_str();
@@ -608,10 +745,40 @@ static void bind_fused(Plan& p, void* const* rets) {
 
 static void run_items(Plan& p, cudaStream_t s) {
     auto& N = p.nodes;
+    bool comm_pending = false;
     for (const Item& it : p.order) {
         if (p.profiling) DB_CUDA(cudaEventRecord(p.ev0, s));
         const char* label;
-        if (it.kind == ITEM_KERNEL) {
+        if (it.join_comm && comm_pending) {
+            // reduced gradients are needed now: the compute stream waits for the communication stream
+            DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
+            DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
+            comm_pending = false;
+        }
+        if (it.kind == ITEM_BUCKET) {
+            // one all-reduce for the whole bucket, on the communication stream so that it overlaps the rest of backward
+            Bucket& b = p.buckets[it.id];
+            if (!p.comm_stream) {
+                DB_CUDA(cudaStreamCreateWithFlags(&p.comm_stream, cudaStreamNonBlocking));
+                DB_CUDA(cudaEventCreateWithFlags(&p.comm_fork, cudaEventDisableTiming));
+                DB_CUDA(cudaEventCreateWithFlags(&p.comm_join, cudaEventDisableTiming));
+            }
+            DB_CUDA(cudaEventRecord(p.comm_fork, s));
+            DB_CUDA(cudaStreamWaitEvent(p.comm_stream, p.comm_fork, 0));
+            allreduce_mean((float*)b.arena, b.bytes / 4, p.comm_stream);
+            comm_pending = true;
+            if (p.profiling) {   // serialise so that the profile attributes the time
+                DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
+                DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
+                comm_pending = false;
+            }
+            label = "allreduceBucket";
+        } else if (it.kind == ITEM_COPY) {
+            Node& n = N[it.id];
+            DB_CUDA(cudaMemcpyAsync(n.ptr, N[n.deps[0]].ptr, (size_t)n.bytes, cudaMemcpyDeviceToDevice, s));
+            count_launch();
+            label = "bucketCopyIn";
+        } else if (it.kind == ITEM_KERNEL) {
             Node& n = N[it.id];
             const void* in[DOPT_B200_MAX_INPUTS];
             for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.deps[k]].ptr;
@@ -633,6 +800,10 @@ static void run_items(Plan& p, cudaStream_t s) {
             DB_CUDA(cudaEventElapsedTime(&ms, p.ev0, p.ev1));
             p.prof_us[label] += ms * 1000.0;
         }
+    }
+    if (comm_pending) {   // nothing may be left running on the side stream when the step (or the capture) ends
+        DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
+        DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
     }
 }
 
@@ -684,8 +855,8 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             if (n.type == "variable") {
                 DB_REQUIRE(bound[i] != nullptr, "plan_execute: a variable the plan reads was not bound");
                 n.ptr = bound[i];
-            } else if (n.alias_of < 0) {
-                n.ptr = n.buf;
+            } else if (n.alias_of < 0 && n.buf) {
+                n.ptr = n.buf;   // (bucket members already point into their arena)
             }
         }
         for (size_t i = 0; i < N.size(); ++i) {

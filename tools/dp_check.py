@@ -1,0 +1,87 @@
+"""Run under torchrun (N ranks, one GPU each): data-parallel SGD steps through the real NCCL gradient buckets, checked
+against the single-process CPU oracle on the concatenated batch.  Prints PASS/FAIL on rank 0."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
+
+import ctypes as C  # noqa: E402
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dopt_b200 as db  # noqa: E402
+from dopt_b200 import host as H  # noqa: E402
+from oracle import graph_eval as G  # noqa: E402
+
+F = np.float32
+PER_RANK = 4
+
+
+def build(batch):
+    H.reset()
+    H.seed(31)
+    x = H.float32((batch, 16, 8, 8))
+    y = H.float32((batch, 10))
+    l = H.data_source(x).conv2d(32, (3, 3), padding=(1, 1), weight_decay=1e-3, use_bias=False).relu() \
+        .conv2d(32, (3, 3), padding=(1, 1), weight_decay=1e-3).relu().dense(10).softmax()
+    net = H.Network([x], [l])
+    loss = H.cross_entropy(l.train_output, y) + net.param_loss
+    upd = H.Updater(H.SGD, [loss], network=net, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+    return x, y, net, upd
+
+
+def main():
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+    assert H.init(), H.init_error()
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if RANK == 0:
+        buf = C.create_string_buffer(128)
+        db.check(db.lib.dopt_b200_comm_unique_id(buf))
+        uid.copy_(torch.tensor(list(buf.raw), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    H.init_data_parallel(RANK, WORLD, bytes(uid.cpu().tolist()))
+    H.set_math(db.MATH_FP32)
+    rng = np.random.RandomState(9)
+    total = PER_RANK * WORLD
+    data = [(rng.randn(total, 16, 8, 8).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, total)]) for _ in range(4)]
+    x, y, net, upd = build(PER_RANK)
+    lo, hi = RANK * PER_RANK, (RANK + 1) * PER_RANK
+    for s in range(4):
+        upd.step({x: data[s][0][lo:hi], y: data[s][1][lo:hi]})
+    mine = [p.get() for p in net.params]
+    stats = upd.stats()
+    # replicas identical?
+    ok = True
+    for p in mine:
+        t = torch.from_numpy(p).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        ok = ok and bool(torch.equal(t, ref))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if RANK == 0:
+        H.set_data_parallel_world(1)
+        x1, y1, net1, upd1 = build(total)
+        oracle = G.UpdaterOracle(upd1)
+        for s in range(4):
+            oracle.step({x1: data[s][0], y1: data[s][1]})
+        worst = 0.0
+        for p, got in zip(net1.params, mine):
+            want = oracle.value_of(p)
+            worst = max(worst, float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)))
+        good = bool(flag.item()) and worst < 1e-4
+        print("dp_check world=%d replicas_identical=%s max_rel_err_vs_single_process_oracle=%.3g launches=%d -> %s"
+              % (WORLD, bool(flag.item()), worst, stats["launches"], "PASS" if good else "FAIL"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,15 @@ inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
 struct Kernel {
     virtual ~Kernel() {}
     virtual void run(const void* const* in, int n_in, void* out, cudaStream_t s) = 0;
+    // Tensor-core convolutions read their activation operands as NHWC bf16.  The plan can stage an activation once and hand
+    // the staged copy to every convolution op that reads it (forward + filter gradient share x; feature + filter gradient
+    // share dy).  staged_bytes(i) > 0 means input i can be supplied pre-staged; set_staged_input(i, p) supplies it.
+    virtual size_t staged_bytes(int /*input*/) const { return 0; }
+    virtual void set_staged_input(int /*input*/, const void* /*nhwc_bf16*/) {}
 };
+// NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use
+void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s);
+size_t staged_nhwc_bytes(int N, int C, int64_t HW);
 using Factory = Kernel* (*)(const dopt_b200_op&);
 void register_kernel(const char* op_type, Factory f);   // == registerCUDAKernel (package.d:479-485)
 Factory find_kernel(const char* op_type);

@@ -41,6 +41,8 @@ struct ConvKernel : Kernel {
         if (resolve_math(d.math) == DOPT_B200_MATH_BF16 && conv_tc_supported(g, kind)) tc = conv_tc_create(g, kind);
     }
     ~ConvKernel() { conv_tc_destroy(tc); }
+    size_t staged_bytes(int input) const override { return conv_tc_staged_bytes(tc, input); }
+    void set_staged_input(int input, const void* p) override { conv_tc_set_staged(tc, input, p); }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == 2, "convolution ops take two inputs");
         const float* a = (const float*)in[0];

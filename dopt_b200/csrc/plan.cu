@@ -28,6 +28,7 @@
 #include <map>
 #include <queue>
 #include <set>
+#include <tuple>
 #include <unordered_map>
 
 namespace db {
@@ -75,11 +76,20 @@ struct Region {
     std::vector<int> out_nodes;                       // region nodes whose value is needed outside
 };
 
-enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4 };
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5 };
 struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
     bool join_comm;     // reads a reduced gradient: the compute stream must first wait for the communication stream
+};
+
+// an activation staged once as NHWC bf16 for all the tensor-core convolution ops that read it
+struct Stage {
+    int src_dep;        // node id the consumers name as their operand
+    int n, c;
+    int64_t hw;
+    void* buf = nullptr;
+    std::vector<std::pair<int, int>> users;   // (node, input index)
 };
 
 // gradients that are all-reduced together: their buffers are carved from one arena so that ONE ncclAllReduce covers them
@@ -105,6 +115,7 @@ struct dopt_b200_plan_s {
     std::vector<std::vector<int>> launch_regions;   // regions of each launch, row order
     std::vector<char> direct_out;                   // per plan output: written in place by a fused region
     std::vector<db::Bucket> buckets;
+    std::vector<db::Stage> stages;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     int64_t device_bytes = 0;
@@ -130,6 +141,8 @@ struct dopt_b200_plan_s {
         for (auto& l : launches) db::fused_free(l);
         for (auto& b : buckets)
             if (b.arena) cudaFree(b.arena);
+        for (auto& st : stages)
+            if (st.buf) cudaFree(st.buf);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
         if (comm_join) cudaEventDestroy(comm_join);
@@ -575,6 +588,19 @@ static void schedule(Plan& p) {
     }
     for (size_t b = 0; b < p.buckets.size(); ++b)
         for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        const Stage& st = p.stages[si];
+        if (st.users.empty()) continue;
+        items.push_back({ITEM_STAGE, (int)si, false});
+        item_key.push_back(key_of(root_of(p, st.src_dep)) + 1);
+        succ.emplace_back();
+        indeg.push_back(0);
+        int item = (int)items.size() - 1;
+        bool via = false;
+        add_edge(producer_item(st.src_dep, &via), item);
+        items[item].join_comm = via;
+        for (auto& u : st.users) add_edge(item, item_of_node[u.first]);
+    }
     using QE = std::pair<int64_t, int>;
     std::priority_queue<QE, std::vector<QE>, std::greater<QE>> ready;
     for (size_t k = 0; k < items.size(); ++k)
@@ -680,6 +706,43 @@ static void build(Plan& p) {
         n.op.op_type = n.type.c_str();
         n.kernel = f(n.op);
     }
+    if (p.flags & DOPT_B200_PLAN_FUSE) {
+        // shared operand staging for the tensor-core convolutions
+        std::map<std::tuple<int, int64_t, int, int, int64_t>, int> by_source;
+        for (size_t i = 0; i < N.size(); ++i) {
+            Node& n = N[i];
+            if (!n.kernel) continue;
+            for (int k = 0; k < 2 && k < (int)n.deps.size(); ++k) {
+                if (n.kernel->staged_bytes(k) == 0) continue;
+                const dopt_b200_tensor& t = n.op.inputs[k];
+                int64_t off = 0, hw = 1;
+                int r = root_of(p, n.deps[k], &off);
+                for (int d = 2; d < t.rank; ++d) hw *= t.shape[d];
+                auto key = std::make_tuple(r, off, (int)t.shape[0], (int)t.shape[1], hw);
+                auto it = by_source.find(key);
+                if (it == by_source.end()) {
+                    Stage st;
+                    st.src_dep = n.deps[k];
+                    st.n = (int)t.shape[0];
+                    st.c = (int)t.shape[1];
+                    st.hw = hw;
+                    p.stages.push_back(st);
+                    it = by_source.emplace(key, (int)p.stages.size() - 1).first;
+                }
+                p.stages[it->second].users.push_back({(int)i, k});
+            }
+        }
+        for (auto& st : p.stages) {
+            if (st.users.size() < 2) {
+                st.users.clear();   // a single reader stages for itself
+                continue;
+            }
+            size_t bytes = staged_nhwc_bytes(st.n, st.c, st.hw);
+            DB_CUDA(cudaMalloc(&st.buf, bytes));
+            p.device_bytes += (int64_t)bytes;
+            for (auto& u : st.users) N[u.first].kernel->set_staged_input(u.second, st.buf);
+        }
+    }
     schedule(p);
     p.direct_out.assign(p.outputs.size(), 0);
 }
@@ -773,6 +836,10 @@ static void run_items(Plan& p, cudaStream_t s) {
                 comm_pending = false;
             }
             label = "allreduceBucket";
+        } else if (it.kind == ITEM_STAGE) {
+            const Stage& st = p.stages[it.id];
+            stage_nchw_to_nhwc_bf16((const float*)N[st.src_dep].ptr, st.buf, st.n, st.c, st.hw, s);
+            label = "stageNHWC";
         } else if (it.kind == ITEM_COPY) {
             Node& n = N[it.id];
             DB_CUDA(cudaMemcpyAsync(n.ptr, N[n.deps[0]].ptr, (size_t)n.bytes, cudaMemcpyDeviceToDevice, s));

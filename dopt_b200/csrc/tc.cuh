@@ -20,5 +20,7 @@ ConvTc* conv_tc_create(const ConvGeom& g, int kind);
 // fwd: a = x, b = w, out = y;  dgrad: a = dy, b = w, out = dx;  wgrad: a = dy, b = x, out = dw  (all NCHW / KCRS fp32)
 void conv_tc_run(ConvTc* c, const float* a, const float* b, float* out, cudaStream_t s);
 void conv_tc_destroy(ConvTc* c);
+void conv_tc_set_staged(ConvTc* c, int input, const void* nhwc_bf16);
+size_t conv_tc_staged_bytes(const ConvTc* c, int input);
 
 }  // namespace db

@@ -186,7 +186,7 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
     if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_e0, s));
-    if (a.cluster > 1) {
+    if (a.cluster > 1 || a.pair) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)n_ctas);
         cfg.blockDim = dim3(TC_THREADS);
@@ -194,16 +194,34 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)a.cluster;
+        at[0].val.clusterDim.x = (unsigned)(a.pair ? 2 : a.cluster);
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE>, tmA, tmB, a));
+        if (a.pair) {
+            static bool pair_configured = false;
+            if (!pair_configured) {
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                pair_configured = true;
+            }
+            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
+        } else {
+            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE>, tmA, tmB, a));
+        }
     } else {
         tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     }
-    DB_LAUNCH_CHECK();
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            throw Error(std::string("tcgen05 kernel launch failed: ") + cudaGetErrorString(e) + " [mode " + std::to_string(MODE) +
+                        " grid " + std::to_string(n_ctas) + " cluster " + std::to_string(a.cluster) + " pair " +
+                        std::to_string(a.pair) + " m_tiles " + std::to_string(a.m_tiles) + " n_tiles " +
+                        std::to_string(a.n_tiles) + " splits " + std::to_string(a.splits) + " BN " + std::to_string(a.BN) +
+                        " stages " + std::to_string(a.stages) + " smem " + std::to_string(L.total) + "]");
+        count_launch();
+    }
     if (g_tc_prof) {
         DB_CUDA(cudaEventRecord(g_tc_e1, s));
         DB_CUDA(cudaEventSynchronize(g_tc_e1));
@@ -239,6 +257,17 @@ static int pick_cluster(int m_tiles, int bn) {
     for (int c = g_max_cluster; c > 1; c >>= 1)
         if (m_tiles >= 2 * c && bn % (8 * c) == 0) return c;
     return 1;
+}
+
+// cta_group::2 pair tiles (256 x BN): each SM ingests only half of the filter tile
+static int g_use_pair = 1;
+static bool pick_pair(int m_tiles, int bn) {
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char* e = getenv("DOPT_B200_PAIR")) g_use_pair = atoi(e);
+    }
+    return g_use_pair && m_tiles >= 4 && bn % 16 == 0 && (bn / 2) % 8 == 0;
 }
 
 static int pick_bn(int nout) {
@@ -335,7 +364,24 @@ struct ConvTc {
     int kind;
     int Cp, Kp;
     PixelBox box;
+    const void* pre[2] = {nullptr, nullptr};   // operands already staged as NHWC bf16 by the plan
 };
+
+void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
+    nchw_to_nhwc_bf16(in, (__nv_bfloat16*)out, N, C, (int)HW, (int)align_up(C, 8), s);
+}
+size_t staged_nhwc_bytes(int N, int C, int64_t HW) { return align_up((size_t)N * HW * align_up(C, 8) * 2, 1024); }
+void conv_tc_set_staged(ConvTc* c, int input, const void* p) {
+    if (c && input >= 0 && input < 2) c->pre[input] = p;
+}
+size_t conv_tc_staged_bytes(const ConvTc* c, int input) {
+    if (!c) return 0;
+    const ConvGeom& g = c->g;
+    // input 0: x (fwd) / dy (dgrad, wgrad); input 1: filters (fwd, dgrad: never staged by the plan) / x (wgrad)
+    if (input == 0) return c->kind == CONV_FWD ? staged_nhwc_bytes(g.N, g.C, (int64_t)g.H * g.W) : staged_nhwc_bytes(g.N, g.K, (int64_t)g.P * g.Q);
+    if (input == 1 && c->kind == CONV_WGRAD) return staged_nhwc_bytes(g.N, g.C, (int64_t)g.H * g.W);
+    return 0;
+}
 
 bool conv_tc_supported(const ConvGeom& g, int kind) {
     if (g.R * g.S > TC_MAX_TAPS) return false;
@@ -376,7 +422,8 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     uint8_t* st = stage_get(xb + wb);
     auto* xh = (__nv_bfloat16*)st;
     auto* wp = (__nv_bfloat16*)(st + xb);
-    nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
+    if (c->pre[0]) xh = (__nv_bfloat16*)c->pre[0];
+    else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
     pack_filters_kernel<<<stream_grid((int64_t)g.K * RS * Cp, 256, 8), 256, 0, s>>>(w, wp, g.K, g.C, g.R, g.S, c->Kp, Cp, 0);
     DB_LAUNCH_CHECK();
     const PixelBox& b = c->box;
@@ -386,10 +433,11 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.mode = TC_MODE_CONV;
     a.BN = pick_bn(g.K);
     a.m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
-    a.cluster = pick_cluster(a.m_tiles, a.BN);
-    a.m_tiles = (int)align_up(a.m_tiles, a.cluster);
-    make_map_2d(&tmB, wp, (uint64_t)RS * Cp, (uint64_t)g.K, (uint64_t)RS * Cp, 64, (uint32_t)(a.BN / a.cluster),
-                "convolution w");
+    a.pair = pick_pair(a.m_tiles, a.BN) ? 1 : 0;
+    a.cluster = a.pair ? 1 : pick_cluster(a.m_tiles, a.BN);
+    a.m_tiles = (int)align_up(a.m_tiles, a.pair ? 2 : a.cluster);
+    make_map_2d(&tmB, wp, (uint64_t)RS * Cp, (uint64_t)g.K, (uint64_t)RS * Cp, 64,
+                (uint32_t)(a.pair ? a.BN / 2 : a.BN / a.cluster), "convolution w");
     a.n_tiles = (int)ceil_div(g.K, a.BN);
     a.splits = 1;
     a.taps = RS;
@@ -422,7 +470,8 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
     uint8_t* st = stage_get(yb + wb);
     auto* dyh = (__nv_bfloat16*)st;
     auto* wp = (__nv_bfloat16*)(st + yb);
-    nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
+    if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
+    else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
     pack_filters_kernel<<<stream_grid((int64_t)g.C * RS * Kp, 256, 8), 256, 0, s>>>(w, wp, g.K, g.C, g.R, g.S, Kp, c->Cp, 1);
     DB_LAUNCH_CHECK();
     const PixelBox& b = c->box;
@@ -430,10 +479,11 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
     make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, b.bh, b.bw, 1, 1, "convolutionFeaturesGrad dy");
     int BN = pick_bn(g.C);
     int m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
-    int cluster = pick_cluster(m_tiles, BN);
-    m_tiles = (int)align_up(m_tiles, cluster);
-    make_map_2d(&tmB, wp, (uint64_t)RS * Kp, (uint64_t)g.C, (uint64_t)RS * Kp, 64, (uint32_t)(BN / cluster),
-                "convolutionFeaturesGrad w");
+    int pair = pick_pair(m_tiles, BN) ? 1 : 0;
+    int cluster = pair ? 1 : pick_cluster(m_tiles, BN);
+    m_tiles = (int)align_up(m_tiles, pair ? 2 : cluster);
+    make_map_2d(&tmB, wp, (uint64_t)RS * Kp, (uint64_t)g.C, (uint64_t)RS * Kp, 64,
+                (uint32_t)(pair ? BN / 2 : BN / cluster), "convolutionFeaturesGrad w");
     bool need_zero = false;
     std::vector<TcArgs> launches;
     for (int pa = 0; pa < g.u; ++pa)
@@ -443,6 +493,7 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.BN = BN;
             a.m_tiles = m_tiles;
             a.cluster = cluster;
+            a.pair = pair;
             a.n_tiles = (int)ceil_div(g.C, BN);
             a.splits = 1;
             a.c_iters = (int)ceil_div(g.K, TC_BK);
@@ -491,8 +542,10 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     uint8_t* st = stage_get(yb + xb);
     auto* dyh = (__nv_bfloat16*)st;
     auto* xh = (__nv_bfloat16*)(st + yb);
-    nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
-    nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
+    if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
+    else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
+    if (c->pre[1]) xh = (__nv_bfloat16*)c->pre[1];
+    else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
     DB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.K * g.C * RS * sizeof(float), s));
     count_launch();
     const PixelBox& b = c->box;

@@ -31,6 +31,7 @@ struct TcArgs {
     int n_tiles;        // tiles along N; blockIdx.x = ((n_tile * splits) + split) * m_tiles + m_tile
     int m_tiles;        // tiles along M (padded to a multiple of `cluster`)
     int cluster;        // CTAs per cluster sharing one B tile through TMA multicast (1, 2 or 4; CONV mode)
+    int pair;           // CONV mode: cta_group::2 -- two CTAs (one TPC) form a 256 x BN tile, each holding half of the B tile
     int splits;
     int k_iters;        // total k-iterations of the problem (divided over splits)
     // ---- GEMM
@@ -68,7 +69,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * 64u * 128u;           // [n-block][64 k rows][64 n]
     } else {
         L.a_bytes = TC_BM * 128u;
-        L.b_bytes = (uint32_t)a.BN * 128u;
+        L.b_bytes = (uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u;
     }
     L.b_bytes = (L.b_bytes + 1023u) & ~1023u;
     L.stage_bytes = L.a_bytes + L.b_bytes;
@@ -77,7 +78,9 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     return L;
 }
 
-template <int MODE>
+// PAIR = cta_group::2 flavour (CONV mode only).  It is a separate instantiation because a kernel that contains cta_group::2
+// instructions can only be launched with an even cluster size.
+template <int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args) {
@@ -99,7 +102,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
     bid /= args.m_tiles;
     const int split = bid % args.splits;
     const int n_tile = bid / args.splits;
-    const int csize = (MODE == TC_MODE_CONV) ? args.cluster : 1;
+    constexpr bool pair = PAIR && (MODE == TC_MODE_CONV);
+    const int csize = pair ? 2 : ((MODE == TC_MODE_CONV) ? args.cluster : 1);
     const uint32_t crank = csize > 1 ? tcg::cluster_ctarank() : 0;
     const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
     int it_begin, it_end;
@@ -136,14 +140,20 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         tcg::tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) {
             tcg::mbar_init(&full_bar[i], 1);
-            tcg::mbar_init(&empty_bar[i], (uint32_t)csize);   // every CTA that receives multicast data must release the stage
+            // multicast: every CTA that receives the data must release the stage; pair: the leader's commit releases both
+            tcg::mbar_init(&empty_bar[i], pair ? 1u : (uint32_t)csize);
         }
         tcg::mbar_init(tmem_full_bar, 1);
         tcg::fence_barrier_init();
     }
     if (warp == 1) {
-        tcg::tmem_alloc(tmem_slot, tmem_cols);
-        tcg::tmem_relinquish();
+        if constexpr (pair) {
+            tcg::tmem_alloc_2sm(tmem_slot, tmem_cols);
+            tcg::tmem_relinquish_2sm();
+        } else {
+            tcg::tmem_alloc(tmem_slot, tmem_cols);
+            tcg::tmem_relinquish();
+        }
     }
     tcg::tc_fence_before();
     if (csize > 1) tcg::cluster_sync();   // peers' barriers must exist before the first remote arrive / multicast write
@@ -167,6 +177,17 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     tcg::tma_load_2d(sa, &tmA, &full_bar[st], it * TC_BK, m_tile * TC_BM);
                     for (int b = 0; b < nblk; ++b)
                         tcg::tma_load_2d(sb + b * 8192, &tmB, &full_bar[st], n_tile * BN + b * 64, it * TC_BK);
+                } else if constexpr (pair) {
+                    // both CTAs of the pair load their own activation tile and their half of the filter tile; all bytes
+                    // are credited to the leader's barrier, which the leader arms for the pair
+                    const int t = it / args.c_iters, cb = it - t * args.c_iters;
+                    const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
+                    const int rows = BN / 2;
+                    if (crank == 0) tcg::mbar_arrive_expect_tx(&full_bar[st], 2u * (a_bytes + (uint32_t)rows * 128u));
+                    tcg::tma_load_4d_2sm(sa, &tmA, &full_bar[st], cb * TC_BK, q0 * args.a_sv + args.tap_dw[t],
+                                         p0 * args.a_su + args.tap_dh[t], img0);
+                    tcg::tma_load_2d_2sm(sb, &tmB, &full_bar[st], args.tap_bcol[t] + cb * TC_BK,
+                                         n_tile * BN + (int)crank * rows);
                 } else if (MODE == TC_MODE_CONV) {
                     const int t = it / args.c_iters, cb = it - t * args.c_iters;
                     const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
@@ -206,7 +227,27 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && n_iters > 0) {
+        if constexpr (pair) {
+            if (lane == 0 && n_iters > 0 && crank == 0) {
+                const uint32_t idesc2 = tcg::make_idesc_bf16(2 * TC_BM, BN, 0, 0);
+                for (int i = 0; i < n_iters; ++i) {
+                    const int st = i % stages;
+                    const uint32_t ph = (uint32_t)(i / stages) & 1u;
+                    tcg::mbar_wait(&full_bar[st], ph);
+                    tcg::tc_fence_after();
+                    const uint32_t sa = tcg::smem_u32(smem + (size_t)st * L.stage_bytes);
+                    const uint32_t sb = sa + L.a_bytes;
+                    const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
+                    const uint64_t dbb = tcg::make_smem_desc(sb, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        tcg::umma_bf16_2sm(tmem_base, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc2,
+                                           (uint32_t)((i | k) != 0));
+                    tcg::umma_commit_2sm(&empty_bar[st], 3);   // releases the stage in both CTAs
+                }
+                tcg::umma_commit_2sm(tmem_full_bar, 3);        // both halves of the accumulator are complete
+            }
+        } else if (lane == 0 && n_iters > 0) {
             const uint32_t idesc = tcg::make_idesc_bf16(TC_BM, BN, MODE == TC_MODE_WGRAD ? 1 : 0,
                                                         (MODE == TC_MODE_CONV) ? 0 : 1);
             for (int i = 0; i < n_iters; ++i) {
@@ -312,7 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
     else __syncthreads();
     if (warp == 1) {
         tcg::tc_fence_after();
-        tcg::tmem_dealloc(tmem_base, tmem_cols);
+        if constexpr (pair) tcg::tmem_dealloc_2sm(tmem_base, tmem_cols);
+        else tcg::tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 

@@ -318,7 +318,9 @@ def main():
             "gpu_launches": int(launches), "launches_per_step": st["launches"], "plan_nodes": st["lowered_nodes"],
             "plan_device_bytes": st["device_bytes"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "loss_first": first_loss, "loss_last": last_loss,
-            "per_op_us_per_step": dict((k, v / 2.0) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:14]),
+            "per_op_us_per_step": dict((k, [v / 2.0, prof.get(k + "#n", 0) // 2]) for k, v in
+                                       sorted(((k, v) for k, v in prof.items() if "#" not in k and k != "tc_kernel_launches"),
+                                              key=lambda kv: -kv[1])[:16]),
         }
         print(json.dumps(line))
     if world > 1:

@@ -55,7 +55,7 @@ class Param(C.Structure):
 # every symbol include/dopt_b200.h declares; tests/test_abi.py checks the library exports each of them
 SYMBOLS = [
     "dopt_b200_init", "dopt_b200_last_error", "dopt_b200_version", "dopt_b200_device_info",
-    "dopt_b200_set_default_math", "dopt_b200_launch_count", "dopt_b200_list_operations", "dopt_b200_has_operation",
+    "dopt_b200_set_default_math", "dopt_b200_launch_count", "dopt_b200_tc_profile", "dopt_b200_list_operations", "dopt_b200_has_operation",
     "dopt_b200_kernel_create", "dopt_b200_kernel_execute", "dopt_b200_kernel_destroy",
     "dopt_b200_sgd_update", "dopt_b200_adam_update",
     "dopt_b200_plan_create", "dopt_b200_plan_add_node", "dopt_b200_plan_set_outputs", "dopt_b200_plan_finalize",
@@ -79,6 +79,7 @@ def load():
     lib.dopt_b200_set_default_math.argtypes = [C.c_int]
     lib.dopt_b200_set_default_math.restype = None
     lib.dopt_b200_launch_count.restype = C.c_uint64
+    lib.dopt_b200_tc_profile.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.dopt_b200_list_operations.restype = C.POINTER(C.c_char)
     lib.dopt_b200_has_operation.argtypes = [C.c_char_p]
     lib.dopt_b200_kernel_create.argtypes = [C.POINTER(Op), C.POINTER(vp)]

@@ -116,6 +116,11 @@ struct dopt_b200_kernel_s {
     }                                                 \
     return 0;
 
+namespace db {
+void tc_prof_enable(bool on);
+void tc_prof_read(double* us, int64_t* launches);
+}  // namespace db
+
 extern "C" {
 
 int dopt_b200_init(void) {
@@ -146,6 +151,21 @@ void dopt_b200_set_default_math(int math) {
 }
 
 uint64_t dopt_b200_launch_count(void) { return db::g_launches.load(); }
+
+int dopt_b200_tc_profile(int enable, double* us, int64_t* launches) {
+    try {
+        double u = 0;
+        int64_t l = 0;
+        db::tc_prof_read(&u, &l);
+        if (us) *us = u;
+        if (launches) *launches = l;
+        db::tc_prof_enable(enable != 0);
+        return 0;
+    } catch (const std::exception& e) {
+        db::set_last_error(e.what());
+        return -1;
+    }
+}
 
 const char* dopt_b200_list_operations(void) {
     try {

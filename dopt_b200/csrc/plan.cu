@@ -131,7 +131,8 @@ struct dopt_b200_plan_s {
     // profiler
     bool profiling = false;
     std::map<std::string, double> prof_us;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::map<std::string, int64_t> prof_cnt;
+    std::vector<cudaEvent_t> prof_ev;   // one per item boundary
 
     ~dopt_b200_plan_s() {
         for (auto& n : nodes) {
@@ -149,8 +150,7 @@ struct dopt_b200_plan_s {
         for (auto& kv : var_stage) cudaFree(kv.second);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (auto e : prof_ev) cudaEventDestroy(e);
     }
 };
 
@@ -745,6 +745,30 @@ static void build(Plan& p) {
     }
     schedule(p);
     p.direct_out.assign(p.outputs.size(), 0);
+    if (getenv("DOPT_B200_PLAN_DUMP")) {
+        // one line per scheduled item: kind, op type, output volume, the op types of its operands
+        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage"};
+        for (const Item& it : p.order) {
+            if (it.kind == ITEM_KERNEL || it.kind == ITEM_PW_SCALAR || it.kind == ITEM_COPY) {
+                const Node& n = N[it.id];
+                std::string deps;
+                for (int d : n.deps) deps += " " + N[d].type + "(" + std::to_string(volume(N[d].op.output)) + ")";
+                std::string users;
+                for (size_t u = 0; u < N.size(); ++u) {
+                    if (!N[u].needed) continue;
+                    for (int d : N[u].deps)
+                        if (d == it.id) users += " #" + std::to_string(u) + ":" + N[u].type + "/r" + std::to_string(N[u].region);
+                }
+                fprintf(stderr, "PLAN %-9s #%d %s vol=%lld <-%s  users:%s\n", kinds[it.kind], it.id, n.type.c_str(),
+                        (long long)volume(n.op.output), deps.c_str(), users.c_str());
+            } else if (it.kind == ITEM_FUSED) {
+                fprintf(stderr, "PLAN fused     launch %d rows=%zu instr=%d\n", it.id, p.launches[it.id].rows.size(),
+                        p.launches[it.id].prog.n_instr);
+            } else {
+                fprintf(stderr, "PLAN %-9s %d\n", kinds[it.kind], it.id);
+            }
+        }
+    }
 }
 
 // fill the row tables of the fused launches from the resolved pointers; decide which plan outputs a terminal region may
@@ -809,8 +833,20 @@ static void bind_fused(Plan& p, void* const* rets) {
 static void run_items(Plan& p, cudaStream_t s) {
     auto& N = p.nodes;
     bool comm_pending = false;
+    // profiling: an event between every two items, read back after the whole step -- no host synchronisation inside the
+    // step, so small kernels are charged their device time and the launch gap, not a host round trip
+    std::vector<const char*> labels;
+    if (p.profiling) {
+        while (p.prof_ev.size() < p.order.size() + 1) {
+            cudaEvent_t e;
+            DB_CUDA(cudaEventCreate(&e));
+            p.prof_ev.push_back(e);
+        }
+        labels.reserve(p.order.size());
+    }
+    size_t item_no = 0;
     for (const Item& it : p.order) {
-        if (p.profiling) DB_CUDA(cudaEventRecord(p.ev0, s));
+        if (p.profiling) DB_CUDA(cudaEventRecord(p.prof_ev[item_no++], s));
         const char* label;
         if (it.join_comm && comm_pending) {
             // reduced gradients are needed now: the compute stream waits for the communication stream
@@ -860,12 +896,16 @@ static void run_items(Plan& p, cudaStream_t s) {
             fused_launch(p.launches[it.id], s);
             label = "fusedRegion";
         }
-        if (p.profiling) {
-            DB_CUDA(cudaEventRecord(p.ev1, s));
-            DB_CUDA(cudaEventSynchronize(p.ev1));
+        if (p.profiling) labels.push_back(label);
+    }
+    if (p.profiling) {
+        DB_CUDA(cudaEventRecord(p.prof_ev[item_no], s));
+        DB_CUDA(cudaEventSynchronize(p.prof_ev[item_no]));
+        for (size_t i = 0; i < labels.size(); ++i) {
             float ms = 0;
-            DB_CUDA(cudaEventElapsedTime(&ms, p.ev0, p.ev1));
-            p.prof_us[label] += ms * 1000.0;
+            DB_CUDA(cudaEventElapsedTime(&ms, p.prof_ev[i], p.prof_ev[i + 1]));
+            p.prof_us[labels[i]] += ms * 1000.0;
+            p.prof_cnt[labels[i]] += 1;
         }
     }
     if (comm_pending) {   // nothing may be left running on the side stream when the step (or the capture) ends
@@ -1086,18 +1126,16 @@ int dopt_b200_plan_profile(dopt_b200_plan_t p, int enable, char* buf, size_t buf
     if (buf && buf_len) {
         std::string s;
         for (auto& kv : p->prof_us) s += kv.first + "=" + std::to_string((long long)kv.second) + "\n";
+        for (auto& kv : p->prof_cnt) s += kv.first + "#n=" + std::to_string((long long)kv.second) + "\n";
         double tus = 0;
         int64_t tl = 0;
         db::tc_prof_read(&tus, &tl);
         s += "tc_kernel=" + std::to_string((long long)tus) + "\ntc_kernel_launches=" + std::to_string((long long)tl) + "\n";
         snprintf(buf, buf_len, "%s", s.c_str());
     }
-    if (enable && !p->ev0) {
-        DB_CUDA(cudaEventCreate(&p->ev0));
-        DB_CUDA(cudaEventCreate(&p->ev1));
-    }
     if (enable != (int)p->profiling) {
         p->prof_us.clear();
+        p->prof_cnt.clear();
         db::tc_prof_enable(enable != 0);
     }
     p->profiling = enable != 0;

@@ -112,30 +112,83 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
     }
 }
 
-// KCRS fp32 -> packed bf16.  MODE 0 (fwd): out[k][(r*S+s)*Cp + c] = w[k][c][R-1-r][S-1-s]
-//                            MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]
+// KCRS fp32 -> packed bf16 through a shared-memory tile, so that both the fp32 reads (runs of 32*RS contiguous floats) and
+// the bf16 writes (runs of 32 channels) are coalesced.  6 B/element.
+//   MODE 0 (fwd):   out[k][(r*S+s)*Cp + c] = w[k][c][R-1-r][S-1-s]
+//   MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]
+// grid (ceil(Kx/32), ceil(Cx/32)) over the padded extents, 256 threads, dynamic smem 32*(32*RS+1) floats.
+template <int MODE>
 __global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                           int K, int C, int R, int S, int Kp, int Cp, int mode) {
-    const int RS = R * S;
-    int64_t n = mode == 0 ? (int64_t)K * RS * Cp : (int64_t)C * RS * Kp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int k, c, t;
-        if (mode == 0) {
-            c = (int)(i % Cp);
-            int64_t j = i / Cp;
-            t = (int)(j % RS);
-            k = (int)(j / RS);
-        } else {
-            k = (int)(i % Kp);
-            int64_t j = i / Kp;
-            t = (int)(j % RS);
-            c = (int)(j / RS);
-        }
-        int r = t / S, s = t - r * S;
-        float v = 0.f;
-        if (k < K && c < C) v = w[(((int64_t)k * C + c) * R + (R - 1 - r)) * S + (S - 1 - s)];
-        out[i] = __float2bfloat16_rn(v);
+                                                           int K, int C, int RS, int Kp, int Cp) {
+    extern __shared__ float pf_tile[];   // [32 k][32 c * RS (+1)]
+    const int ld = 32 * RS + 1;
+    const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int run = min(32, C - c0) * RS;   // contiguous floats of one k row inside this tile (<= 0: padding tile)
+    for (int kk = threadIdx.x >> 5; kk < 32; kk += 8) {
+        const int k = k0 + kk;
+        const float* src = w + ((int64_t)k * C + c0) * RS;
+        for (int j = threadIdx.x & 31; j < 32 * RS; j += 32) pf_tile[kk * ld + j] = (k < K && j < run) ? src[j] : 0.f;
     }
+    __syncthreads();
+    if (MODE == 0) {
+        // one (k, tap) row of 32 channels per warp trip
+        for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
+            const int kk = row / RS, t = row - kk * RS;
+            const int k = k0 + kk, c = c0 + (threadIdx.x & 31);
+            if (k < Kp && c < Cp)
+                out[((int64_t)k * RS + t) * Cp + c] =
+                    __float2bfloat16_rn(pf_tile[kk * ld + (threadIdx.x & 31) * RS + (RS - 1 - t)]);
+        }
+    } else {
+        // one (c, tap) row of 32 output channels k per warp trip
+        for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
+            const int cc = row / RS, t = row - cc * RS;
+            const int c = c0 + cc, k = k0 + (threadIdx.x & 31);
+            if (c < Cp && k < Kp)
+                out[((int64_t)c * RS + t) * Kp + k] = __float2bfloat16_rn(pf_tile[(threadIdx.x & 31) * ld + cc * RS + (RS - 1 - t)]);
+        }
+    }
+}
+
+// convolutionFiltersGrad: the tensor-core kernel accumulates into a scratch laid out [tap][C][K] (K contiguous = the
+// accumulator's lane dimension, so a warp's 32 atomic adds fall into one 128-byte line); this turns it into dopt's KCRS
+// with the filter flip.  grid (ceil(K/32), ceil(C/32)), 256 threads, dynamic smem 32*(32*RS+1) floats.
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int K,
+                                                           int C, int RS) {
+    extern __shared__ float pf_tile[];   // [32 k][32 c * RS (+1)]
+    const int ld = 32 * RS + 1;
+    const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int kk = threadIdx.x & 31, k = k0 + kk;
+    for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
+        const int t = row / 32, cc = row - t * 32;
+        const int c = c0 + cc;
+        float v = 0.f;
+        if (k < K && c < C) v = scratch[((int64_t)t * C + c) * K + k];
+        pf_tile[kk * ld + cc * RS + (RS - 1 - t)] = v;
+    }
+    __syncthreads();
+    const int run = min(32, C - c0) * RS;
+    for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+        const int kr = k0 + r;
+        if (kr >= K) break;
+        float* dst = dw + ((int64_t)kr * C + c0) * RS;
+        for (int j = threadIdx.x & 31; j < run; j += 32) dst[j] = pf_tile[r * ld + j];
+    }
+}
+
+static void pack_filters(const float* w, __nv_bfloat16* out, int K, int C, int RS, int Kp, int Cp, int mode, cudaStream_t s) {
+    const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);
+    DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the packing kernel");
+    static size_t configured[2] = {48 * 1024, 48 * 1024};
+    if (smem > configured[mode]) {
+        if (mode == 0) DB_CUDA(cudaFuncSetAttribute(pack_filters_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        else DB_CUDA(cudaFuncSetAttribute(pack_filters_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[mode] = 200 * 1024;
+    }
+    dim3 grid((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(Cp, 32));
+    if (mode == 0) pack_filters_kernel<0><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
+    else pack_filters_kernel<1><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
+    DB_LAUNCH_CHECK();
 }
 
 static void nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int N, int C, int HW, int Cp, cudaStream_t s) {
@@ -159,25 +212,28 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // optional per-launch timing of the tcgen05 kernel alone (bench.py's roofline): enabled together with plan profiling
 static bool g_tc_prof = false;
-static double g_tc_prof_us = 0;
-static int64_t g_tc_prof_launches = 0;
-static cudaEvent_t g_tc_e0 = nullptr, g_tc_e1 = nullptr;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_tc_ev;   // event pairs, reused between profiling sessions
+static size_t g_tc_ev_used = 0;
 void tc_prof_enable(bool on) {
     g_tc_prof = on;
-    g_tc_prof_us = 0;
-    g_tc_prof_launches = 0;
-    if (on && !g_tc_e0) {
-        DB_CUDA(cudaEventCreate(&g_tc_e0));
-        DB_CUDA(cudaEventCreate(&g_tc_e1));
-    }
+    if (on) g_tc_ev_used = 0;
 }
+// device time spent in tc_kernel launches since tc_prof_enable(true); synchronises with the recorded events
 void tc_prof_read(double* us, int64_t* launches) {
-    *us = g_tc_prof_us;
-    *launches = g_tc_prof_launches;
+    double total = 0;
+    for (size_t i = 0; i < g_tc_ev_used; ++i) {
+        float ms = 0;
+        DB_CUDA(cudaEventSynchronize(g_tc_ev[i].second));
+        DB_CUDA(cudaEventElapsedTime(&ms, g_tc_ev[i].first, g_tc_ev[i].second));
+        total += ms * 1000.0;
+    }
+    *us = total;
+    *launches = (int64_t)g_tc_ev_used;
 }
 
 template <int MODE>
 static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int n_ctas, cudaStream_t s) {
+    // n_ctas on entry = number of work items (m_tiles * n_tiles * splits)
     TcSmemLayout L = tc_smem_layout(a);
     static int configured = 0;
     if (configured < (int)L.total) {
@@ -185,8 +241,23 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         configured = 227 * 1024;
     }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
-    if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_e0, s));
-    if (a.cluster > 1 || a.pair) {
+    if (g_tc_prof) {
+        if (g_tc_ev_used == g_tc_ev.size()) {
+            cudaEvent_t e0, e1;
+            DB_CUDA(cudaEventCreate(&e0));
+            DB_CUDA(cudaEventCreate(&e1));
+            g_tc_ev.emplace_back(e0, e1);
+        }
+        DB_CUDA(cudaEventRecord(g_tc_ev[g_tc_ev_used].first, s));
+    }
+    // persistent grid: one CTA (pair) per SM, each looping over its share of the n_ctas work items
+    {
+        const int cs = a.pair ? 2 : 1;
+        int clusters = std::min(n_ctas / cs, (a.nacc == 2 ? 1 : 2) * sm_count() / cs);
+        if (clusters < 1) clusters = 1;
+        n_ctas = clusters * cs;
+    }
+    if (a.pair) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)n_ctas);
         cfg.blockDim = dim3(TC_THREADS);
@@ -194,21 +265,17 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)(a.pair ? 2 : a.cluster);
+        at[0].val.clusterDim.x = 2;
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        if (a.pair) {
-            static bool pair_configured = false;
-            if (!pair_configured) {
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                pair_configured = true;
-            }
-            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
-        } else {
-            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<MODE>, tmA, tmB, a));
+        static bool pair_configured = false;
+        if (!pair_configured) {
+            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            pair_configured = true;
         }
+        DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
     } else {
         tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     }
@@ -222,24 +289,36 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
                         " stages " + std::to_string(a.stages) + " smem " + std::to_string(L.total) + "]");
         count_launch();
     }
-    if (g_tc_prof) {
-        DB_CUDA(cudaEventRecord(g_tc_e1, s));
-        DB_CUDA(cudaEventSynchronize(g_tc_e1));
-        float ms = 0;
-        DB_CUDA(cudaEventElapsedTime(&ms, g_tc_e0, g_tc_e1));
-        g_tc_prof_us += ms * 1000.0;
-        ++g_tc_prof_launches;
-    }
+    if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_ev[g_tc_ev_used++].second, s));
 }
 
-static int pick_stages(TcArgs& a) {
+// Persistent CTAs come in two shapes (measured on the WRN layers, profiles/r01c_conv_bisect.md):
+//  * one per SM, two TMEM accumulators, the whole shared memory as operand ring: the epilogue of tile i overlaps the main
+//    loop of tile i+1 inside the CTA.  Best when an SM gets many tiles (C=160 layer: 6.9 tiles per SM) and for wgrad.
+//  * two per SM, one accumulator each and half the ring: two independent pipelines hide each other's tile boundaries
+//    and TMA latency.  Best when an SM only gets a few tiles (C=320/640 layers).
+static int g_ctas_per_sm = 0;   // 0 = choose per problem
+static int pick_stages(TcArgs& a, int64_t items = 0) {
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char* e = getenv("DOPT_B200_CTAS_PER_SM")) g_ctas_per_sm = atoi(e);
+    }
+    int per_sm = g_ctas_per_sm;
+    if (per_sm != 1 && per_sm != 2)
+        per_sm = (a.mode == TC_MODE_WGRAD || items >= (int64_t)6 * sm_count()) ? 1 : 2;
+    a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
-    int st2 = (int)((110 * 1024 - 2048) / L.stage_bytes);   // two CTAs per SM
-    int st1 = (int)((225 * 1024 - 2048) / L.stage_bytes);   // one CTA per SM
-    int st = st2 >= 3 ? st2 : st1;
+    int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - 2048) / L.stage_bytes);
     if (st > 8) st = 8;
-    if (st < 2) st = 2;
+    if (st < 2) {
+        // the tile does not fit twice: fall back to one CTA per SM
+        a.nacc = 2;
+        st = (int)((225 * 1024 - 2048) / L.stage_bytes);
+        if (st > 8) st = 8;
+        if (st < 2) st = 2;
+    }
     return st;
 }
 
@@ -424,8 +503,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     auto* wp = (__nv_bfloat16*)(st + xb);
     if (c->pre[0]) xh = (__nv_bfloat16*)c->pre[0];
     else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
-    pack_filters_kernel<<<stream_grid((int64_t)g.K * RS * Cp, 256, 8), 256, 0, s>>>(w, wp, g.K, g.C, g.R, g.S, c->Kp, Cp, 0);
-    DB_LAUNCH_CHECK();
+    pack_filters(w, wp, g.K, g.C, RS, g.K, Cp, 0, s);
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, xh, g.N, g.H, g.W, Cp, g.C, b.bn, b.bh, b.bw, g.u, g.v, "convolution x");
@@ -434,10 +512,10 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.BN = pick_bn(g.K);
     a.m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
     a.pair = pick_pair(a.m_tiles, a.BN) ? 1 : 0;
-    a.cluster = a.pair ? 1 : pick_cluster(a.m_tiles, a.BN);
-    a.m_tiles = (int)align_up(a.m_tiles, a.pair ? 2 : a.cluster);
+    a.cluster = 1;
+    a.m_tiles = (int)align_up(a.m_tiles, a.pair ? 2 : 1);
     make_map_2d(&tmB, wp, (uint64_t)RS * Cp, (uint64_t)g.K, (uint64_t)RS * Cp, 64,
-                (uint32_t)(a.pair ? a.BN / 2 : a.BN / a.cluster), "convolution w");
+                (uint32_t)(a.pair ? a.BN / 2 : a.BN), "convolution w");
     a.n_tiles = (int)ceil_div(g.K, a.BN);
     a.splits = 1;
     a.taps = RS;
@@ -459,8 +537,33 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_off = 0;
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
-    a.stages = pick_stages(a);
+    a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
+    if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
+    static unsigned long long* trace_dev = nullptr;
+    static int trace_runs = 0;
+    if (getenv("DOPT_B200_TRACE") && trace_runs < 6) {
+        if (!trace_dev) DB_CUDA(cudaMalloc(&trace_dev, 1024 * 8));
+        DB_CUDA(cudaMemsetAsync(trace_dev, 0, 1024 * 8, s));
+        a.trace = trace_dev;
+    }
+    if (const char* e = getenv("DOPT_B200_STAGES")) a.stages = atoi(e);
     tc_launch<TC_MODE_CONV>(tmA, tmB, a, a.m_tiles * a.n_tiles, s);
+    if (a.trace && ++trace_runs == 5) {
+        std::vector<unsigned long long> t(1024);
+        DB_CUDA(cudaStreamSynchronize(s));
+        DB_CUDA(cudaMemcpy(t.data(), trace_dev, 1024 * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = t[0];
+        fprintf(stderr, "TRACE k_iters %d stages %d BN %d pair %d\n", a.k_iters, a.stages, a.BN, a.pair);
+        fprintf(stderr, "producer (after empty wait) : ");
+        for (int i = 0; i < 64; ++i) fprintf(stderr, "%lld ", (long long)(t[i] - t0));
+        fprintf(stderr, "\nproducer B (after empty)    : ");
+        for (int i = 0; i < 64; ++i) fprintf(stderr, "%lld ", (long long)(t[768 + i] - t0));
+        fprintf(stderr, "\nmma (after full wait)       : ");
+        for (int i = 0; i < 64; ++i) fprintf(stderr, "%lld ", (long long)(t[256 + i] - t0));
+        fprintf(stderr, "\nepilogue (start,end) per tile: ");
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "(%lld,%lld) ", (long long)(t[512 + 2 * i] - t0), (long long)(t[512 + 2 * i + 1] - t0));
+        fprintf(stderr, "\n");
+    }
 }
 
 static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cudaStream_t s) {
@@ -472,18 +575,17 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
     auto* wp = (__nv_bfloat16*)(st + yb);
     if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
     else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
-    pack_filters_kernel<<<stream_grid((int64_t)g.C * RS * Kp, 256, 8), 256, 0, s>>>(w, wp, g.K, g.C, g.R, g.S, Kp, c->Cp, 1);
-    DB_LAUNCH_CHECK();
+    pack_filters(w, wp, g.K, g.C, RS, Kp, g.C, 1, s);
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, b.bh, b.bw, 1, 1, "convolutionFeaturesGrad dy");
     int BN = pick_bn(g.C);
     int m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
     int pair = pick_pair(m_tiles, BN) ? 1 : 0;
-    int cluster = pair ? 1 : pick_cluster(m_tiles, BN);
-    m_tiles = (int)align_up(m_tiles, pair ? 2 : cluster);
+    int cluster = 1;
+    m_tiles = (int)align_up(m_tiles, pair ? 2 : 1);
     make_map_2d(&tmB, wp, (uint64_t)RS * Kp, (uint64_t)g.C, (uint64_t)RS * Kp, 64,
-                (uint32_t)(pair ? BN / 2 : BN / cluster), "convolutionFeaturesGrad w");
+                (uint32_t)(pair ? BN / 2 : BN), "convolutionFeaturesGrad w");
     bool need_zero = false;
     std::vector<TcArgs> launches;
     for (int pa = 0; pa < g.u; ++pa)
@@ -525,7 +627,7 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sn = (long long)g.C * g.H * g.W; a.o_sc = (long long)g.H * g.W;
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
-            a.stages = pick_stages(a);
+            a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }
     if (need_zero) {
@@ -539,14 +641,16 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     const ConvGeom& g = c->g;
     const int RS = g.R * g.S, Kp = c->Kp, Cp = c->Cp;
     size_t yb = align_up((size_t)g.N * g.P * g.Q * Kp * 2, 1024), xb = align_up((size_t)g.N * g.H * g.W * Cp * 2, 1024);
-    uint8_t* st = stage_get(yb + xb);
+    const size_t sb = align_up((size_t)RS * g.K * g.C * sizeof(float), 1024);   // [tap][C][K] accumulation scratch
+    uint8_t* st = stage_get(yb + xb + sb);
+    float* acc = (float*)(st + yb + xb);
     auto* dyh = (__nv_bfloat16*)st;
     auto* xh = (__nv_bfloat16*)(st + yb);
     if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
     else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
     if (c->pre[1]) xh = (__nv_bfloat16*)c->pre[1];
     else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
-    DB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.K * g.C * RS * sizeof(float), s));
+    DB_CUDA(cudaMemsetAsync(acc, 0, (size_t)g.K * g.C * RS * sizeof(float), s));
     count_launch();
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
@@ -563,7 +667,7 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
             int t = r * g.S + q;
             a.tap_dh[t] = r - g.ph;
             a.tap_dw[t] = q - g.pw;
-            a.tap_bcol[t] = (g.R - 1 - r) * g.S + (g.S - 1 - q);   // flipped position inside the KCRS filter
+            a.tap_bcol[t] = t * g.C * g.K;   // this tap's [C][K] plane of the scratch
         }
     a.bn = b.bn; a.bh = b.bh; a.bw = b.bw;
     a.tiles_p = b.tiles_p; a.tiles_q = b.tiles_q;
@@ -572,17 +676,50 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     a.pix_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
     a.out_kind = TC_OUT_F32_ATOMIC;
     a.o_off = 0;
-    a.o_sn = (long long)g.C * RS;   // per Kout row
-    a.o_sc = RS;                    // per Cin column
-    a.out = dw;
+    // scratch[tap][c][k]: the accumulator row (TMEM lane) is k, so the 32 atomics of a warp instruction hit 32 consecutive
+    // floats -- one L2 line instead of 32 (the strided KCRS version was bound by L2 atomic throughput)
+    a.o_sn = 1;        // per Kout row
+    a.o_sc = g.K;      // per Cin column
+    a.out = acc;
     int mt = (int)ceil_div(g.K, TC_BM);
     int tiles = RS * mt * a.n_tiles;
-    int want = 2 * sm_count();
-    a.splits = std::max(1, std::min(a.pix_tiles, (int)ceil_div(want, tiles)));
+    // split the pixel range so that the work items fill whole rounds of the persistent grid (one CTA per SM): 18 tiles x 17
+    // splits = 306 items would run as 3 rounds on 148 SMs with the last one nearly empty
+    {
+        const int sms = sm_count();
+        int best = 1;
+        double best_eff = 0;
+        for (int sp = 1; sp <= a.pix_tiles && (int64_t)tiles * sp <= (int64_t)8 * sms; ++sp) {
+            if (a.pix_tiles / sp < 8 && sp > 1) break;   // keep the accumulation runs long enough to amortise the epilogue
+            int64_t items = (int64_t)tiles * sp;
+            int64_t rounds = ceil_div(items, (int64_t)sms);
+            int64_t per = ceil_div((int64_t)a.pix_tiles, (int64_t)sp);
+            // time ~ rounds * (iterations per item + fixed cost of an item's prologue / atomic epilogue)
+            double eff = (double)tiles * a.pix_tiles / ((double)rounds * sms * (per + 4));
+            if (eff > best_eff * 1.02) {
+                best_eff = eff;
+                best = sp;
+            }
+        }
+        a.splits = best;
+    }
+    if (const char* e = getenv("DOPT_B200_WG_SPLITS")) a.splits = std::max(1, std::min(a.pix_tiles, atoi(e)));
     a.stages = pick_stages(a);
     a.m_tiles = RS * mt;
     a.cluster = 1;
     tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, tiles * a.splits, s);
+    {
+        const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);
+        DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the wgrad finish kernel");
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            DB_CUDA(cudaFuncSetAttribute(wgrad_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        dim3 grid((unsigned)ceil_div(g.K, 32), (unsigned)ceil_div(g.C, 32));
+        wgrad_finish_kernel<<<grid, 256, smem, s>>>(acc, dw, g.K, g.C, RS);
+        DB_LAUNCH_CHECK();
+    }
 }
 
 void conv_tc_run(ConvTc* c, const float* a, const float* b, float* out, cudaStream_t s) {

@@ -22,7 +22,8 @@ enum { TC_OUT_F32 = 0, TC_OUT_BF16 = 1, TC_OUT_F32_ATOMIC = 2 };
 static constexpr int TC_MAX_TAPS = 25;
 static constexpr int TC_BM = 128;
 static constexpr int TC_BK = 64;                 // bf16 elements per 128-byte swizzled row
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining every other 16-column chunk
+static constexpr int TC_THREADS = 352;   // warp 0: TMA (A) | warp 1: MMA | warps 2-9: epilogue | warp 10: TMA (B, CONV mode)
 
 struct TcArgs {
     int mode;
@@ -31,6 +32,9 @@ struct TcArgs {
     int n_tiles;        // tiles along N; blockIdx.x = ((n_tile * splits) + split) * m_tiles + m_tile
     int m_tiles;        // tiles along M (padded to a multiple of `cluster`)
     int cluster;        // CTAs per cluster sharing one B tile through TMA multicast (1, 2 or 4; CONV mode)
+    unsigned long long* trace;   // experiments only: CTA 0 records clock64() per pipeline event (see tools/exp_conv.sh)
+    int dbg;            // experiments only: bit 0 = skip A loads, bit 1 = skip B loads (results are then garbage)
+    int nacc;           // TMEM accumulators per CTA: 2 (512 columns, one CTA per SM) or 1 (256 columns, two CTAs per SM)
     int pair;           // CONV mode: cta_group::2 -- two CTAs (one TPC) form a 256 x BN tile, each holding half of the B tile
     int splits;
     int k_iters;        // total k-iterations of the problem (divided over splits)
@@ -80,6 +84,12 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
 
 // PAIR = cta_group::2 flavour (CONV mode only).  It is a separate instantiation because a kernel that contains cta_group::2
 // instructions can only be launched with an even cluster size.
+//
+// The kernel is PERSISTENT: the grid is one CTA (or CTA pair) per SM and every role loops over the work items
+// (m_tile, n_tile, split) assigned to its CTA.  The accumulator is double-buffered in TMEM (2 x 256 columns), so the
+// epilogue of item i (TMEM -> registers -> global) overlaps the main loop of item i+1, and barrier set-up, TMEM allocation
+// and tensor-map prefetch are paid once per SM instead of once per tile (profiles/r01c_conv_bisect.md: in the
+// one-tile-per-CTA version those fixed costs and the exposed epilogue were 60 % of the kernel time).
 template <int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
@@ -89,272 +99,343 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
     const TcSmemLayout L = tc_smem_layout(args);
     uint64_t* full_bar = (uint64_t*)(smem + L.bar_off);
     uint64_t* empty_bar = full_bar + 16;
-    uint64_t* tmem_full_bar = empty_bar + 16;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + 16;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = args.BN;
     const int stages = args.stages;
-
-    // ---- tile coordinates
-    int bid = blockIdx.x;
-    const int m_tile = bid % args.m_tiles;   // fastest: the CTAs of one cluster differ only in their M tile
-    bid /= args.m_tiles;
-    const int split = bid % args.splits;
-    const int n_tile = bid / args.splits;
     constexpr bool pair = PAIR && (MODE == TC_MODE_CONV);
-    const int csize = pair ? 2 : ((MODE == TC_MODE_CONV) ? args.cluster : 1);
-    const uint32_t crank = csize > 1 ? tcg::cluster_ctarank() : 0;
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
-    int it_begin, it_end;
-    {
+    constexpr int csize = pair ? 2 : 1;
+    const uint32_t crank = pair ? tcg::cluster_ctarank() : 0;
+    constexpr uint32_t kAccStride = 256;          // TMEM columns between the two accumulators
+    const uint32_t kTmemCols = args.nacc == 2 ? 512u : 256u;
+    const uint32_t acc_mask = args.nacc == 2 ? 1u : 0u, acc_shift = args.nacc == 2 ? 1u : 0u;
+
+    // work items of this CTA (cluster): cw = cluster id, cluster id + #clusters, ...
+    const int m_groups = args.m_tiles / csize;
+    const int total_cw = m_groups * args.splits * args.n_tiles;
+    const int cw0 = (int)blockIdx.x / csize, cw_step = (int)gridDim.x / csize;
+    struct Work {
+        int m_tile, n_tile, split, it_begin, n_iters, img0, p0, q0, wg_tap;
+    };
+    auto decode = [&](int cw) {
+        Work w;
+        int cm = cw % m_groups;
+        int rest = cw / m_groups;
+        w.split = rest % args.splits;
+        w.n_tile = rest / args.splits;
+        w.m_tile = cm * csize + (int)crank;
         int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : args.k_iters;
         int per = (total + args.splits - 1) / args.splits;
-        it_begin = split * per;
-        it_end = min(total, it_begin + per);
-    }
-    const int n_iters = max(0, it_end - it_begin);
-
-    // conv tile -> pixel box origin
-    int img0 = 0, p0 = 0, q0 = 0, wg_tap = 0;
-    if (MODE == TC_MODE_CONV) {
-        int tq = m_tile % args.tiles_q;
-        int t2 = m_tile / args.tiles_q;
-        int tp = t2 % args.tiles_p;
-        int ng = t2 / args.tiles_p;
-        img0 = ng * args.bn;
-        p0 = tp * args.bh;
-        q0 = tq * args.bw;
-    }
-    if (MODE == TC_MODE_WGRAD) {
-        // m_tile enumerates (tap, Kout tile); Kout tiles = ceil(M / 128)
-        int mt = (args.M + TC_BM - 1) / TC_BM;
-        wg_tap = m_tile / mt;
-    }
-
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+        w.it_begin = w.split * per;
+        w.n_iters = max(0, min(total, w.it_begin + per) - w.it_begin);
+        w.img0 = w.p0 = w.q0 = w.wg_tap = 0;
+        if (MODE == TC_MODE_CONV) {
+            int tq = w.m_tile % args.tiles_q;
+            int t2 = w.m_tile / args.tiles_q;
+            int tp = t2 % args.tiles_p;
+            int ng = t2 / args.tiles_p;
+            w.img0 = ng * args.bn;
+            w.p0 = tp * args.bh;
+            w.q0 = tq * args.bw;
+        }
+        if (MODE == TC_MODE_WGRAD) w.wg_tap = w.m_tile / ((args.M + TC_BM - 1) / TC_BM);   // m_tile = (tap, Kout tile)
+        return w;
+    };
 
     if (warp == 0 && lane == 0) {
         tcg::tma_prefetch_desc(&tmA);
         tcg::tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) {
-            tcg::mbar_init(&full_bar[i], 1);
-            // multicast: every CTA that receives the data must release the stage; pair: the leader's commit releases both
-            tcg::mbar_init(&empty_bar[i], pair ? 1u : (uint32_t)csize);
+            tcg::mbar_init(&full_bar[i], MODE == TC_MODE_CONV ? 2u : 1u);   // CONV: one arrival per producer warp (A and B)
+            tcg::mbar_init(&empty_bar[i], 1);
         }
-        tcg::mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            tcg::mbar_init(&tmem_full_bar[i], 1);
+            // every epilogue thread (of both CTAs in pair mode: the leader's MMAs write both halves) releases the accumulator
+            tcg::mbar_init(&tmem_empty_bar[i], 32u * TC_EPI_WARPS * (uint32_t)csize);
+        }
         tcg::fence_barrier_init();
     }
     if (warp == 1) {
         if constexpr (pair) {
-            tcg::tmem_alloc_2sm(tmem_slot, tmem_cols);
+            tcg::tmem_alloc_2sm(tmem_slot, kTmemCols);
             tcg::tmem_relinquish_2sm();
         } else {
-            tcg::tmem_alloc(tmem_slot, tmem_cols);
+            tcg::tmem_alloc(tmem_slot, kTmemCols);
             tcg::tmem_relinquish();
         }
     }
     tcg::tc_fence_before();
-    if (csize > 1) tcg::cluster_sync();   // peers' barriers must exist before the first remote arrive / multicast write
+    if constexpr (pair) tcg::cluster_sync();   // the peer's barriers must exist before the first remote arrive
     else __syncthreads();
     tcg::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int i = 0; i < n_iters; ++i) {
-                const int it = it_begin + i;
-                const int st = i % stages;
-                const uint32_t ph = (uint32_t)(i / stages) & 1u;
-                tcg::mbar_wait(&empty_bar[st], ph ^ 1u);
-                uint8_t* sa = smem + (size_t)st * L.stage_bytes;
-                uint8_t* sb = sa + L.a_bytes;
-                if (MODE == TC_MODE_GEMM) {
-                    const int nblk = (BN + 63) / 64;
-                    tcg::mbar_arrive_expect_tx(&full_bar[st], TC_BM * 128u + (uint32_t)nblk * 8192u);
-                    tcg::tma_load_2d(sa, &tmA, &full_bar[st], it * TC_BK, m_tile * TC_BM);
-                    for (int b = 0; b < nblk; ++b)
-                        tcg::tma_load_2d(sb + b * 8192, &tmB, &full_bar[st], n_tile * BN + b * 64, it * TC_BK);
-                } else if constexpr (pair) {
-                    // both CTAs of the pair load their own activation tile and their half of the filter tile; all bytes
-                    // are credited to the leader's barrier, which the leader arms for the pair
-                    const int t = it / args.c_iters, cb = it - t * args.c_iters;
-                    const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
-                    const int rows = BN / 2;
-                    if (crank == 0) tcg::mbar_arrive_expect_tx(&full_bar[st], 2u * (a_bytes + (uint32_t)rows * 128u));
-                    tcg::tma_load_4d_2sm(sa, &tmA, &full_bar[st], cb * TC_BK, q0 * args.a_sv + args.tap_dw[t],
-                                         p0 * args.a_su + args.tap_dh[t], img0);
-                    tcg::tma_load_2d_2sm(sb, &tmB, &full_bar[st], args.tap_bcol[t] + cb * TC_BK,
-                                         n_tile * BN + (int)crank * rows);
-                } else if (MODE == TC_MODE_CONV) {
-                    const int t = it / args.c_iters, cb = it - t * args.c_iters;
-                    const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
-                    tcg::mbar_arrive_expect_tx(&full_bar[st], a_bytes + (uint32_t)BN * 128u);
-                    tcg::tma_load_4d(sa, &tmA, &full_bar[st], cb * TC_BK, q0 * args.a_sv + args.tap_dw[t],
-                                     p0 * args.a_su + args.tap_dh[t], img0);
-                    if (csize == 1) {
-                        tcg::tma_load_2d(sb, &tmB, &full_bar[st], args.tap_bcol[t] + cb * TC_BK, n_tile * BN);
-                    } else {
-                        // this CTA fetches 1/csize of the filter tile and multicasts it to the whole cluster
-                        const int rows = BN / csize;
-                        tcg::tma_load_2d_mcast(sb + (size_t)crank * rows * 128, &tmB, &full_bar[st],
-                                               args.tap_bcol[t] + cb * TC_BK, n_tile * BN + (int)crank * rows, cmask);
+    if (warp == 0 || (warp == 2 + TC_EPI_WARPS && MODE == TC_MODE_CONV)) {
+        // ===================== TMA producer(s) =====================
+        // CONV mode splits the two copies of a stage over two warps (activation tile: warp 0, filter tile: warp 6): issuing a
+        // 128-row 4-D box occupies the issuing thread for several hundred cycles (profiles/r01c_conv_bisect.md)
+        const bool doA = warp == 0, doB = (MODE != TC_MODE_CONV) || warp == 2 + TC_EPI_WARPS;
+        // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors and coordinates live in
+        // uniform registers); one elected lane issues the copies.  A single-lane `if (lane == 0)` region instead makes
+        // the compiler wrap every UTMALDG / UTCHMMA in a register-to-uniform waterfall (~150 cycles per MMA, measured).
+        {
+            // ring position (stage, phase) and the (tap, channel block) / pixel-box counters are advanced incrementally: an
+            // integer division per k-iteration costs this single-warp loop more than the copy it issues
+            // (profiles/r01c_conv_bisect.md: 500 cycles per iteration with every copy, MMA and store disabled)
+            uint32_t g = 0;   // k-iterations issued so far, across work items (trace only)
+            int st = 0;
+            uint32_t ph = 0;
+            for (int cw = cw0; cw < total_cw; cw += cw_step) {
+                const Work w = decode(cw);
+                // CONV: it -> (tap t, channel block cb); WGRAD: it -> pixel box (ng, tp, tq)
+                int t = 0, cb = 0, tq = 0, tp = 0, ng = 0;
+                if (MODE == TC_MODE_CONV) {
+                    t = w.it_begin / args.c_iters;
+                    cb = w.it_begin - t * args.c_iters;
+                } else if (MODE == TC_MODE_WGRAD) {
+                    tq = w.it_begin % args.tiles_q;
+                    int t2 = w.it_begin / args.tiles_q;
+                    tp = t2 % args.tiles_p;
+                    ng = t2 / args.tiles_p;
+                }
+                const int mt = (args.M + TC_BM - 1) / TC_BM;
+                const int m_blk = (MODE == TC_MODE_WGRAD) ? w.m_tile % mt : 0;
+                for (int i = 0; i < w.n_iters; ++i, ++g) {
+                    const int it = w.it_begin + i;
+                    tcg::mbar_wait(&empty_bar[st], ph ^ 1u);
+                    if (args.trace && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[(warp == 0 ? 0 : 768) + (g < 255 ? g : 255)] = clock64();
+                    uint8_t* sa = smem + (size_t)st * L.stage_bytes;
+                    uint8_t* sb = sa + L.a_bytes;
+                    uint64_t* fb = &full_bar[st];
+                    const int t_now = t, cb_now = cb, tq_now = tq, tp_now = tp, ng_now = ng;
+                    if (++st == stages) { st = 0; ph ^= 1u; }
+                    if (MODE == TC_MODE_CONV) {
+                        if (++cb == args.c_iters) { cb = 0; ++t; }
+                    } else if (MODE == TC_MODE_WGRAD) {
+                        if (++tq == args.tiles_q) {
+                            tq = 0;
+                            if (++tp == args.tiles_p) { tp = 0; ++ng; }
+                        }
                     }
-                } else {
-                    // WGRAD: `it` is a pixel box index -> (image group, row tile, col tile)
-                    int tq = it % args.tiles_q;
-                    int t2 = it / args.tiles_q;
-                    int tp = t2 % args.tiles_p;
-                    int ng = t2 / args.tiles_p;
-                    const int pix = args.kmma * 16;
-                    const int mt = (args.M + TC_BM - 1) / TC_BM;
-                    const int m_blk = m_tile % mt;
-                    const int nblk = (BN + 63) / 64;
-                    tcg::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(2 + nblk) * (uint32_t)pix * 128u);
-                    // A: dy box, two 64-channel column blocks of Kout
-                    for (int b = 0; b < 2; ++b)
-                        tcg::tma_load_4d(sa + (size_t)b * pix * 128, &tmA, &full_bar[st], m_blk * TC_BM + b * 64,
-                                         tq * args.bw, tp * args.bh, ng * args.bn);
-                    // B: x box shifted by the tap, conv stride as element stride
-                    for (int b = 0; b < nblk; ++b)
-                        tcg::tma_load_4d(sb + (size_t)b * pix * 128, &tmB, &full_bar[st], n_tile * BN + b * 64,
-                                         tq * args.bw * args.a_sv + args.tap_dw[wg_tap],
-                                         tp * args.bh * args.a_su + args.tap_dh[wg_tap], ng * args.bn);
+                    if (!tcg::elect_one()) continue;
+                    if (MODE == TC_MODE_GEMM) {
+                        const int nblk = (BN + 63) / 64;
+                        tcg::mbar_arrive_expect_tx(fb, TC_BM * 128u + (uint32_t)nblk * 8192u);
+                        tcg::tma_load_2d(sa, &tmA, fb, it * TC_BK, w.m_tile * TC_BM);
+                        for (int b = 0; b < nblk; ++b)
+                            tcg::tma_load_2d(sb + b * 8192, &tmB, fb, w.n_tile * BN + b * 64, it * TC_BK);
+                    } else if constexpr (pair) {
+                        // both CTAs of the pair load their own activation tile and their half of the filter tile; all bytes
+                        // are credited to the leader's barrier, which the leader arms for the pair
+                        const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
+                        const int rows = BN / 2;
+                        if (doA) {
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * a_bytes);
+                            tcg::tma_load_4d_2sm(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
+                                                 w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
+                        } else {
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * (uint32_t)rows * 128u);
+                            tcg::tma_load_2d_2sm(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK,
+                                                 w.n_tile * BN + (int)crank * rows);
+                        }
+                    } else if (MODE == TC_MODE_CONV) {
+                        const uint32_t a_bytes = (args.dbg & 1) ? 0u : (uint32_t)(args.bn * args.bh * args.bw) * 128u;
+                        const uint32_t b_bytes = (args.dbg & 2) ? 0u : (uint32_t)BN * 128u;
+                        if (doA) {
+                            if (a_bytes) tcg::mbar_arrive_expect_tx(fb, a_bytes);
+                            else tcg::mbar_arrive(fb);
+                            if (!(args.dbg & 1))
+                                tcg::tma_load_4d(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
+                                                 w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
+                        } else {
+                            if (b_bytes) tcg::mbar_arrive_expect_tx(fb, b_bytes);
+                            else tcg::mbar_arrive(fb);
+                            if (!(args.dbg & 2))
+                                tcg::tma_load_2d(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK, w.n_tile * BN);
+                        }
+                    } else {
+                        // WGRAD: one pixel box (image group, row tile, col tile) per k-iteration
+                        const int pix = args.kmma * 16;
+                        const int nblk = (BN + 63) / 64;
+                        tcg::mbar_arrive_expect_tx(fb, (uint32_t)(2 + nblk) * (uint32_t)pix * 128u);
+                        // A: dy box, two 64-channel column blocks of Kout
+                        for (int b = 0; b < 2; ++b)
+                            tcg::tma_load_4d(sa + (size_t)b * pix * 128, &tmA, fb, m_blk * TC_BM + b * 64,
+                                             tq_now * args.bw, tp_now * args.bh, ng_now * args.bn);
+                        // B: x box shifted by the tap, conv stride as element stride
+                        for (int b = 0; b < nblk; ++b)
+                            tcg::tma_load_4d(sb + (size_t)b * pix * 128, &tmB, fb, w.n_tile * BN + b * 64,
+                                             tq_now * args.bw * args.a_sv + args.tap_dw[w.wg_tap],
+                                             tp_now * args.bh * args.a_su + args.tap_dh[w.wg_tap], ng_now * args.bn);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if constexpr (pair) {
-            if (lane == 0 && n_iters > 0 && crank == 0) {
-                const uint32_t idesc2 = tcg::make_idesc_bf16(2 * TC_BM, BN, 0, 0);
-                for (int i = 0; i < n_iters; ++i) {
-                    const int st = i % stages;
-                    const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        // ===================== MMA issuer (the leader CTA only in pair mode) =====================
+        if (!pair || crank == 0) {
+            const uint32_t idesc = pair ? tcg::make_idesc_bf16(2 * TC_BM, BN, 0, 0)
+                                        : tcg::make_idesc_bf16(TC_BM, BN, MODE == TC_MODE_WGRAD ? 1 : 0,
+                                                               (MODE == TC_MODE_CONV) ? 0 : 1);
+            uint32_t g = 0, t = 0;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int cw = cw0; cw < total_cw; cw += cw_step) {
+                const Work w = decode(cw);
+                if (w.n_iters == 0) continue;
+                const uint32_t acc = t & acc_mask, use = t >> acc_shift;
+                ++t;
+                tcg::mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator
+                tcg::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                for (int i = 0; i < w.n_iters; ++i, ++g) {
                     tcg::mbar_wait(&full_bar[st], ph);
                     tcg::tc_fence_after();
+                    if (args.trace && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[256 + g] = clock64();
                     const uint32_t sa = tcg::smem_u32(smem + (size_t)st * L.stage_bytes);
                     const uint32_t sb = sa + L.a_bytes;
-                    const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
-                    const uint64_t dbb = tcg::make_smem_desc(sb, 16, 1024, 2);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)
-                        tcg::umma_bf16_2sm(tmem_base, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc2,
+                    uint64_t* eb = &empty_bar[st];
+                    if (++st == stages) { st = 0; ph ^= 1u; }
+                    if (!tcg::elect_one()) continue;
+                    if (MODE == TC_MODE_WGRAD) {
+                        const uint32_t pix_bytes = (uint32_t)args.kmma * 16u * 128u;
+                        const uint64_t da = tcg::make_smem_desc(sa, pix_bytes, 1024, 2);
+                        const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);
+                        for (int k = 0; k < args.kmma; ++k)
+                            tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128), idesc,
                                            (uint32_t)((i | k) != 0));
-                    tcg::umma_commit_2sm(&empty_bar[st], 3);   // releases the stage in both CTAs
-                }
-                tcg::umma_commit_2sm(tmem_full_bar, 3);        // both halves of the accumulator are complete
-            }
-        } else if (lane == 0 && n_iters > 0) {
-            const uint32_t idesc = tcg::make_idesc_bf16(TC_BM, BN, MODE == TC_MODE_WGRAD ? 1 : 0,
-                                                        (MODE == TC_MODE_CONV) ? 0 : 1);
-            for (int i = 0; i < n_iters; ++i) {
-                const int st = i % stages;
-                const uint32_t ph = (uint32_t)(i / stages) & 1u;
-                tcg::mbar_wait(&full_bar[st], ph);
-                tcg::tc_fence_after();
-                const uint32_t sa = tcg::smem_u32(smem + (size_t)st * L.stage_bytes);
-                const uint32_t sb = sa + L.a_bytes;
-                if (MODE == TC_MODE_WGRAD) {
-                    const uint32_t pix_bytes = (uint32_t)args.kmma * 16u * 128u;
-                    const uint64_t da = tcg::make_smem_desc(sa, pix_bytes, 1024, 2);
-                    const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);
-                    for (int k = 0; k < args.kmma; ++k)
-                        tcg::umma_bf16(tmem_base, da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128), idesc,
-                                       (uint32_t)((i | k) != 0));
-                } else {
-                    const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
-                    const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
-                                                                : tcg::make_smem_desc(sb, 16, 1024, 2);
+                    } else {
+                        const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
+                        const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
+                                                                    : tcg::make_smem_desc(sb, 16, 1024, 2);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
-                        const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
-                        tcg::umma_bf16(tmem_base, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
+                            if (args.dbg & 4) continue;
+                            if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
+                            else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
+                        }
                     }
+                    // frees the stage once these MMAs have read it (in both CTAs of a pair)
+                    if constexpr (pair) tcg::umma_commit_2sm(eb, 3);
+                    else tcg::umma_commit(eb);
                 }
-                // frees the stage once these MMAs have read it (cluster-wide when the stage holds multicast data)
-                if (csize == 1) tcg::umma_commit(&empty_bar[st]);
-                else tcg::umma_commit_mcast(&empty_bar[st], cmask);
+                // accumulator complete
+                __syncwarp();
+                if (tcg::elect_one()) {
+                    if constexpr (pair) tcg::umma_commit_2sm(&tmem_full_bar[acc], 3);
+                    else tcg::umma_commit(&tmem_full_bar[acc]);
+                }
             }
-            tcg::umma_commit(tmem_full_bar);        // accumulator complete
         }
-    } else {
-        // ===================== epilogue (warps 2..5) =====================
+    } else if (warp < 2 + TC_EPI_WARPS) {
+        // ===================== epilogue (warps 2..9) =====================
+        // A warp may only read the TMEM lane quarter (warp % 4); the two warps of a quarter take alternate 16-column chunks.
+        // The next chunk's tcgen05.ld is in flight while the current one is stored.
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                   // which of the two warps of this quarter
         const int row = quarter * 32 + lane;                // accumulator row == TMEM lane
-        if (n_iters > 0) {
-            tcg::mbar_wait(tmem_full_bar, 0);
-            tcg::tc_fence_after();
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        // row -> output coordinates
-        bool row_ok;
-        long long row_off;
-        if (MODE == TC_MODE_CONV) {
-            int bwh = args.bw * args.bh;
-            int in_ = row / bwh;
-            int rem = row - in_ * bwh;
-            int ih = rem / args.bw, iw = rem - ih * args.bw;
-            int n = img0 + in_, p = p0 + ih, q = q0 + iw;
-            row_ok = (row < args.bn * bwh) && n < args.NI && p < args.OP && q < args.OQ;
-            row_off = args.o_off + (long long)n * args.o_sn + (long long)p * args.o_sh + (long long)q * args.o_sw;
-        } else if (MODE == TC_MODE_GEMM) {
-            int m = m_tile * TC_BM + row;
-            row_ok = m < args.M;
-            row_off = (long long)m * args.o_sn;
-        } else {
-            const int mt = (args.M + TC_BM - 1) / TC_BM;
-            int m = (m_tile % mt) * TC_BM + row;
-            row_ok = m < args.M;
-            // per-tap output offset is folded into tap_bcol[] by the host (flipped filter position)
-            row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[wg_tap];
-        }
-        const int col0 = n_tile * BN;
-        for (int cb = 0; cb < BN; cb += 16) {
-            uint32_t r[16];
-            if (n_iters > 0) {
-                tcg::tmem_ld16(taddr + (uint32_t)cb, r);
-                tcg::tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0u;
+        constexpr int kStep = 16 * (TC_EPI_WARPS / 4);
+        uint32_t t = 0;
+        for (int cw = cw0; cw < total_cw; cw += cw_step) {
+            const Work w = decode(cw);
+            uint32_t acc = 0;
+            if (w.n_iters > 0) {
+                acc = t & acc_mask;
+                const uint32_t use = t >> acc_shift;
+                ++t;
+                tcg::mbar_wait(&tmem_full_bar[acc], use & 1u);
+                tcg::tc_fence_after();
+                if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t < 16) args.trace[512 + 2 * t] = clock64();
             }
-            if (!row_ok) continue;
-            if (args.out_kind == TC_OUT_BF16 && args.o_sc == 1 && col0 + cb + 16 <= args.Nout) {
-                // NHWC bf16: 16 consecutive channels of one pixel = 32 contiguous bytes
-                __nv_bfloat162 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                uint4* dst = (uint4*)((__nv_bfloat16*)args.out + row_off + col0 + cb);
-                dst[0] = *(uint4*)&v[0];
-                dst[1] = *(uint4*)&v[4];
+            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
+            // row -> output coordinates
+            bool row_ok;
+            long long row_off;
+            if (MODE == TC_MODE_CONV) {
+                int bwh = args.bw * args.bh;
+                int in_ = row / bwh;
+                int rem = row - in_ * bwh;
+                int ih = rem / args.bw, iw = rem - ih * args.bw;
+                int n = w.img0 + in_, p = w.p0 + ih, q = w.q0 + iw;
+                row_ok = (row < args.bn * bwh) && n < args.NI && p < args.OP && q < args.OQ;
+                row_off = args.o_off + (long long)n * args.o_sn + (long long)p * args.o_sh + (long long)q * args.o_sw;
+            } else if (MODE == TC_MODE_GEMM) {
+                int m = w.m_tile * TC_BM + row;
+                row_ok = m < args.M;
+                row_off = (long long)m * args.o_sn;
             } else {
+                const int mt = (args.M + TC_BM - 1) / TC_BM;
+                int m = (w.m_tile % mt) * TC_BM + row;
+                row_ok = m < args.M;
+                // per-tap output offset is folded into tap_bcol[] by the host (flipped filter position)
+                row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[w.wg_tap];
+            }
+            const int col0 = w.n_tile * BN;
+            const uint32_t t_done = t;
+            const bool have = w.n_iters > 0;
+            uint32_t r[16], rn[16];
+            int cb = half * 16;
+            if (have && cb < BN) tcg::tmem_ld16(taddr + (uint32_t)cb, rn);
+            for (; cb < BN; cb += kStep) {
+                if (have) {
+                    tcg::tmem_ld_wait16(rn);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    int c = col0 + cb + j;
-                    if (c < args.Nout) {
-                        long long o = row_off + (long long)c * args.o_sc;
-                        float val = __uint_as_float(r[j]);
-                        if (args.out_kind == TC_OUT_F32) ((float*)args.out)[o] = val;
-                        else if (args.out_kind == TC_OUT_BF16) ((__nv_bfloat16*)args.out)[o] = __float2bfloat16_rn(val);
-                        else atomicAdd((float*)args.out + o, val);
+                    for (int j = 0; j < 16; ++j) r[j] = rn[j];
+                    if (cb + kStep < BN) tcg::tmem_ld16(taddr + (uint32_t)(cb + kStep), rn);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+                if (!row_ok || (args.dbg & 8)) continue;
+                if (args.out_kind == TC_OUT_F32_ATOMIC && !have) continue;
+                if (args.out_kind == TC_OUT_BF16 && args.o_sc == 1 && col0 + cb + 16 <= args.Nout) {
+                    // NHWC bf16: 16 consecutive channels of one pixel = 32 contiguous bytes
+                    __nv_bfloat162 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    uint4* dst = (uint4*)((__nv_bfloat16*)args.out + row_off + col0 + cb);
+                    dst[0] = *(uint4*)&v[0];
+                    dst[1] = *(uint4*)&v[4];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        int c = col0 + cb + j;
+                        if (c < args.Nout) {
+                            long long o = row_off + (long long)c * args.o_sc;
+                            float val = __uint_as_float(r[j]);
+                            if (args.out_kind == TC_OUT_F32) ((float*)args.out)[o] = val;
+                            else if (args.out_kind == TC_OUT_BF16) ((__nv_bfloat16*)args.out)[o] = __float2bfloat16_rn(val);
+                            else atomicAdd((float*)args.out + o, val);
+                        }
                     }
                 }
             }
+            if (have) {
+                // every chunk of this thread has been read (the last wait is behind us): hand the accumulator back.  The
+                // stores of the last chunk are already issued and need no ordering with the MMA issuer.
+                tcg::tc_fence_before();
+                if constexpr (pair) tcg::mbar_arrive_cluster(tcg::smem_u32(&tmem_empty_bar[acc]) & 0xFEFFFFFFu);
+                else tcg::mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t_done <= 16 && t_done > 0)
+                args.trace[512 + 2 * (t_done - 1) + 1] = clock64();
         }
     }
 
     __syncwarp();   // the single-lane producer / issuer loops diverged their warps; the cluster barrier is warp-aligned
     tcg::tc_fence_before();
-    if (csize > 1) tcg::cluster_sync();   // nobody leaves while a peer may still write into / arrive on this CTA
+    if constexpr (pair) tcg::cluster_sync();   // nobody leaves while the peer may still arrive on this CTA's barriers
     else __syncthreads();
     if (warp == 1) {
         tcg::tc_fence_after();
-        if constexpr (pair) tcg::tmem_dealloc_2sm(tmem_base, tmem_cols);
-        else tcg::tmem_dealloc(tmem_base, tmem_cols);
+        if constexpr (pair) tcg::tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tcg::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 

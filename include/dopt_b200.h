@@ -91,6 +91,9 @@ int         dopt_b200_device_info(int* sm_count, int* cc_major, int* cc_minor, s
 void        dopt_b200_set_default_math(int math);          /* what DOPT_B200_MATH_DEFAULT resolves to (default BF16) */
 /* number of kernel launches issued by this library since process start (bench.py's "gpu_launches") */
 uint64_t    dopt_b200_launch_count(void);
+/* diagnostics: CUDA-event timing of the tcgen05 implicit-GEMM kernel (tc_kernel) alone.  enable=1 starts a session;
+ * a later call returns the device time (us) and number of tc_kernel launches since then (bench.py's roofline leg) */
+int         dopt_b200_tc_profile(int enable, double* us, int64_t* launches);
 
 /* ---- per-op kernels: registerCUDAKernel / CUDAKernel.execute ----------------------------------------------------- */
 /* NUL-separated, double-NUL-terminated list of op types with a registered kernel */

@@ -17,12 +17,21 @@ except Exception:
     pass
 
 
+def tc_profile(enable):
+    """(us, launches) of tc_kernel since the last tc_profile(True)"""
+    import ctypes as C
+    us, n = C.c_double(0), C.c_int64(0)
+    db.lib.dopt_b200_tc_profile(int(enable), C.byref(us), C.byref(n))
+    return us.value, n.value
+
+
 def time_kernel(k, ins, out, iters=20, warm=3, flush=None):
     s = torch.cuda.current_stream().cuda_stream
     for _ in range(warm):
         k.execute(ins, out, s)
     torch.cuda.synchronize()
     ts = []
+    tc_profile(True)
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
@@ -40,6 +49,8 @@ def conv_bench():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cases = [(128, 160, 32, 160, 3, 1, 1), (128, 320, 16, 320, 3, 1, 1), (128, 640, 8, 640, 3, 1, 1),
              (128, 160, 32, 320, 3, 1, 2), (128, 16, 32, 160, 3, 1, 1), (128, 160, 32, 320, 1, 0, 2)]
+    if os.environ.get("BENCH_OPS_FIRST"):
+        cases = cases[:int(os.environ["BENCH_OPS_FIRST"])]
     for (N, C, H, K, R, pad, st) in cases:
         P = (H + 2 * pad - R) // st + 1
         x = torch.randn(N, C, H, H, device="cuda")
@@ -58,8 +69,10 @@ def conv_bench():
             op = db.make_op(name, [tuple(s) for s in shapes[0]], tuple(shapes[1]), **at)
             k = db.CUDAKernel(op)
             ms = time_kernel(k, ins, out, flush=flush)
-            print("%-26s N%d C%d H%d K%d R%d s%d: %8.3f ms  %7.1f TFLOP/s (%.1f%% of measured bf16 peak) [incl. staging]"
-                  % (name, N, C, H, K, R, st, ms, flops / ms / 1e9, 100 * flops / ms / 1e9 / PEAKS["bf16_tflops"]))
+            us, n = tc_profile(False)
+            kms = us / 1e3 / 20 if n else float("nan")   # tc_kernel alone (all its launches of one op execution)
+            print("%-24s N%d C%d H%d K%d R%d s%d: op %6.3f ms | tc_kernel %6.3f ms %6.1f TFLOP/s (%4.1f%% of bf16 peak)"
+                  % (name, N, C, H, K, R, st, ms, kms, flops / kms / 1e9, 100 * flops / kms / 1e9 / PEAKS["bf16_tflops"]))
             k.close()
 
 

@@ -196,7 +196,69 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     }
 }
 
+// ---- apply + relu + NHWC bf16 staging in one pass -------------------------------------------------------------------------
+// The plan compiler folds relu(batchNormTrain(x).y) and the NHWC bf16 staging of the result (the operand format of the
+// tensor-core convolutions) into the apply pass: x is read once, and per element 4 B (fp32 result, when anybody reads it)
+// + 2 B (bf16 copy) are written, instead of 22 B for apply + relu + staging as three kernels.  The arithmetic is the
+// same as bn_apply_kernel / relu_kernel / nchw_to_nhwc_bf16_kernel, so results are bit-identical.
+// Tile: 64 channels x 32 pixels of one image; grid (ceil(HW/32), ceil(Cp/64), N), 256 threads.
+template <int MODE, bool RELU>
+__global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             const float* __restrict__ coef, float* __restrict__ out,
+                                                             __nv_bfloat16* __restrict__ staged, BnGeom g, int Cp) {
+    __shared__ float tile[64][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int HW = (int)g.HW, C = (int)g.C;
+    const int64_t img = (int64_t)n * C * HW;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+        const int c = c0 + ty + j, hw = hw0 + tx;
+        float r = 0.f;
+        if (c < C && hw < HW) {
+            const int64_t i = img + (int64_t)c * HW + hw;
+            const float v = x[i] - coef[c];
+            if (MODE == 0) {
+                r = fmaf(v, coef[C + c], coef[2 * C + c]);
+                if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
+            } else {
+                r = fmaf(dy[i], coef[C + c], fmaf(v, coef[2 * C + c], coef[3 * C + c]));
+            }
+            if (out) out[i] = r;
+        }
+        tile[ty + j][tx] = r;
+    }
+    if (!staged) return;
+    __syncthreads();
+    __nv_bfloat16* dst = staged + (int64_t)n * HW * Cp;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int hw = hw0 + ty + j;
+        const int c = c0 + tx * 2;
+        if (hw < HW && c < Cp) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(tile[tx * 2][ty + j], tile[tx * 2 + 1][ty + j]);
+            *(__nv_bfloat162*)(dst + (int64_t)hw * Cp + c) = v;
+        }
+    }
+}
+
 namespace {
+
+template <int MODE>
+static void bn_apply_absorbed(const float* x, const float* dy, const float* coef, float* primary, float* relu_out,
+                              void* staged, bool skip_primary, const BnGeom& g, cudaStream_t s) {
+    const int Cp = (int)((g.C + 7) / 8 * 8);
+    dim3 grid((unsigned)ceil_div(g.HW, 32), (unsigned)ceil_div(Cp, 64), (unsigned)g.N);
+    if (relu_out) {
+        DB_REQUIRE(MODE == 0, "relu can only be absorbed by the forward pass");
+        bn_apply_stage_kernel<0, true><<<grid, 256, 0, s>>>(x, nullptr, coef, relu_out, (__nv_bfloat16*)staged, g, Cp);
+    } else {
+        bn_apply_stage_kernel<MODE, false><<<grid, 256, 0, s>>>(x, dy, coef, skip_primary ? nullptr : primary,
+                                                                (__nv_bfloat16*)staged, g, Cp);
+    }
+    DB_LAUNCH_CHECK();
+}
 
 static BnGeom geom_of(const dopt_b200_tensor& x) {
     // shape padded with ones to rank 4 (cudnn7.d:562-566)
@@ -223,6 +285,15 @@ struct BnTrainKernel : Kernel {
     double factor;
     int splits;
     Scratch ws;
+    float* relu_out = nullptr;
+    void* staged = nullptr;
+    bool skip_primary = false;
+    bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
+    void set_absorbed(float* r, void* st, bool skip) override {
+        relu_out = r;
+        staged = st;
+        skip_primary = skip;
+    }
     BnTrainKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 5, "batchNormTrain: deps are [x, scale, bias, mean, var]");
         g = geom_of(d.inputs[0]);
@@ -244,6 +315,10 @@ struct BnTrainKernel : Kernel {
                                                                        (const float*)in[3], (const float*)in[4], coef,
                                                                        y + V, y + V + g.C, g, splits, factor);
         DB_LAUNCH_CHECK();
+        if (relu_out || staged || skip_primary) {
+            bn_apply_absorbed<0>(x, nullptr, coef, y, relu_out, staged, skip_primary, g, s);
+            return;
+        }
         bn_apply_kernel<0, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, nullptr, coef, y, g);
         DB_LAUNCH_CHECK();
     }
@@ -253,6 +328,14 @@ struct BnGradKernel : Kernel {
     BnGeom g;
     int splits;
     Scratch ws;
+    void* staged = nullptr;
+    bool skip_primary = false;
+    bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
+    void set_absorbed(float* r, void* st, bool skip) override {
+        DB_REQUIRE(r == nullptr, "batchNormGrad cannot absorb a relu");
+        staged = st;
+        skip_primary = skip;
+    }
     BnGradKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 3, "batchNormGrad: deps are [parentGrad, x, scale]");
         g = geom_of(d.inputs[1]);
@@ -275,6 +358,10 @@ struct BnGradKernel : Kernel {
         bn_grad_finalize<<<(unsigned)ceil_div(g.C, 128), 128, 0, s>>>(part, x, (const float*)in[2], coef, dx + V,
                                                                       dx + V + g.C, g, splits);
         DB_LAUNCH_CHECK();
+        if (staged || skip_primary) {
+            bn_apply_absorbed<1>(x, dy, coef, dx, nullptr, staged, skip_primary, g, s);
+            return;
+        }
         bn_apply_kernel<1, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g);
         DB_LAUNCH_CHECK();
     }

@@ -74,6 +74,12 @@ struct Kernel {
     // share dy).  staged_bytes(i) > 0 means input i can be supplied pre-staged; set_staged_input(i, p) supplies it.
     virtual size_t staged_bytes(int /*input*/) const { return 0; }
     virtual void set_staged_input(int /*input*/, const void* /*nhwc_bf16*/) {}
+    // Producer-side fusion (plan.cu, pass "absorb"): a kernel that can apply relu to its result and / or also emit the
+    // NHWC bf16 copy the tensor-core convolutions read.  `relu_out` != null: write relu(result) there instead of the
+    // result itself; `staged` != null: also write the (relu'd) result as [N][HW][Cp] bf16; `skip_primary`: nobody reads
+    // the fp32 result, do not write it.  Only the leading V elements of a packed result are affected.
+    virtual bool can_absorb() const { return false; }
+    virtual void set_absorbed(float* /*relu_out*/, void* /*staged*/, bool /*skip_primary*/) {}
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s);

@@ -59,6 +59,12 @@ struct Node {
     int region = -1;
     int bucket = -1;            // allreduce node reduced in place as part of gradient bucket `bucket` (node is a view of its operand)
     int lvl = 0;                // ASAP level (scheduling priority)
+    // producer-side fusion (pass "absorb"): a relu node whose value is written by the batchNormTrain kernel it follows
+    int absorbed_by = -1;       // relu: node whose kernel produces this value
+    int absorb_relu = -1;       // producer: relu node whose buffer receives relu(result)
+    int absorb_stage = -1;      // producer: stage whose NHWC bf16 buffer it also writes
+    bool absorb_skip = false;   // producer: its own fp32 result has no reader left
+    int in_override[DOPT_B200_MAX_INPUTS] = {-1, -1, -1, -1, -1, -1, -1, -1};   // read this node instead of deps[k]
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
     void* ptr = nullptr;        // resolved pointer for this execution
@@ -89,6 +95,7 @@ struct Stage {
     int n, c;
     int64_t hw;
     void* buf = nullptr;
+    int producer = -1;  // node whose kernel writes the staged copy itself (no staging launch)
     std::vector<std::pair<int, int>> users;   // (node, input index)
 };
 
@@ -530,6 +537,10 @@ static void schedule(Plan& p) {
     for (size_t i = 0; i < N.size(); ++i) {
         Node& n = N[i];
         if (!n.needed || n.alias_of >= 0 || n.type == "variable" || n.type == "constant") continue;
+        if (n.absorbed_by >= 0) {
+            item_of_node[i] = item_of_node[n.absorbed_by];   // produced by that kernel (lower id, already has its item)
+            continue;
+        }
         if (n.region >= 0) {
             Region& R = p.regions[n.region];
             if (launch_terminal[R.launch]) continue;
@@ -591,6 +602,10 @@ static void schedule(Plan& p) {
     for (size_t si = 0; si < p.stages.size(); ++si) {
         const Stage& st = p.stages[si];
         if (st.users.empty()) continue;
+        if (st.producer >= 0) {   // written by the producing kernel itself
+            for (auto& u : st.users) add_edge(item_of_node[st.producer], item_of_node[u.first]);
+            continue;
+        }
         items.push_back({ITEM_STAGE, (int)si, false});
         item_key.push_back(key_of(root_of(p, st.src_dep)) + 1);
         succ.emplace_back();
@@ -656,6 +671,92 @@ static void form_buckets(Plan& p) {
     }
     for (auto& n : N)
         if (n.bucket == -2) n.bucket = -1;   // not needed after all
+}
+
+// ---- pass "absorb": relu and NHWC staging folded into the batch-norm apply pass ----------------------------------------
+// dopt's layers are separate ops: batchNormTrain -> slice -> relu -> convolution (nnet/layers/*.d).  On the GPU that is three
+// passes over the activation (apply, relu, NHWC bf16 staging for the tensor-core convolution).  Where the graph allows it
+// the batch-norm kernel produces relu(y) and the staged copy in its apply pass:
+//   * relu(y) where y is the leading slice of a batchNormTrain result and y's only other readers are the reluGrad nodes
+//     of that relu (they test x > 0, which is the same as relu(x) > 0, so they are pointed at the relu output instead);
+//   * the staged copy of that relu output, or of the dx slice of a batchNormGrad result; when every reader of dx is a
+//     convolution that takes the staged copy, the fp32 dx is not written at all.
+static void absorb(Plan& p) {
+    auto& N = p.nodes;
+    // readers of [0, V*4) of a packed result: (node, input index); views are followed through root_of
+    auto readers_of_head = [&](int root, int64_t head_bytes) {
+        std::vector<std::pair<int, int>> r;
+        for (size_t u = 0; u < N.size(); ++u) {
+            if (!N[u].needed || N[u].alias_of >= 0) continue;
+            for (size_t k = 0; k < N[u].deps.size(); ++k) {
+                int64_t off = 0;
+                if (root_of(p, N[u].deps[k], &off) != root) continue;
+                if (off < head_bytes) r.push_back({(int)u, (int)k});
+            }
+        }
+        return r;
+    };
+    auto head_is_output = [&](int root, int64_t head_bytes) {
+        for (int o : p.outputs) {
+            int64_t off = 0;
+            if (root_of(p, o, &off) == root && off < head_bytes) return true;
+        }
+        return false;
+    };
+    auto stage_of = [&](int root) {
+        for (size_t si = 0; si < p.stages.size(); ++si) {
+            int64_t off = 0;
+            if (root_of(p, p.stages[si].src_dep, &off) == root && off == 0 && !p.stages[si].users.empty()) return (int)si;
+        }
+        return -1;
+    };
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& R = N[i];
+        if (!R.needed || R.alias_of >= 0 || R.type != "relu" || R.deps.size() != 1 || !R.kernel) continue;
+        int64_t off = 0;
+        const int b = root_of(p, R.deps[0], &off);
+        Node& B = N[b];
+        if (off != 0 || B.type != "batchNormTrain" || !B.kernel || !B.kernel->can_absorb() || B.absorb_relu >= 0) continue;
+        if (N[R.deps[0]].bytes != R.bytes) continue;
+        const int64_t head = R.bytes;
+        if (head_is_output(b, head)) continue;
+        bool ok = true;
+        std::vector<int> grads;
+        for (auto& rd : readers_of_head(b, head)) {
+            if (rd.first == (int)i) continue;
+            const Node& G = N[rd.first];
+            int64_t o1 = 0;
+            bool is_grad = G.type == "reluGrad" && G.deps.size() == 3 && rd.second == 2 &&
+                           root_of(p, G.deps[1], &o1) == (int)i && o1 == 0;
+            if (!is_grad) { ok = false; break; }
+            grads.push_back(rd.first);
+        }
+        if (!ok) continue;
+        R.absorbed_by = b;
+        B.absorb_relu = (int)i;
+        for (int gi : grads) N[gi].in_override[2] = (int)i;
+        int si = stage_of((int)i);
+        if (si >= 0) {
+            B.absorb_stage = si;
+            p.stages[si].producer = b;
+        }
+    }
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        Stage& st = p.stages[si];
+        if (st.producer >= 0 || st.users.empty()) continue;
+        int64_t off = 0;
+        const int b = root_of(p, st.src_dep, &off);
+        Node& B = N[b];
+        if (off != 0 || B.type != "batchNormGrad" || !B.kernel || !B.kernel->can_absorb() || B.absorb_stage >= 0) continue;
+        const int64_t head = N[st.src_dep].bytes;
+        if (head != (int64_t)st.n * st.c * st.hw * 4) continue;
+        st.producer = b;
+        B.absorb_stage = (int)si;
+        bool all_staged = !head_is_output(b, head);
+        for (auto& rd : readers_of_head(b, head))
+            if (std::find(st.users.begin(), st.users.end(), rd) == st.users.end()) all_staged = false;
+        B.absorb_skip = all_staged;
+    }
 }
 
 static void build(Plan& p) {
@@ -732,8 +833,9 @@ static void build(Plan& p) {
                 p.stages[it->second].users.push_back({(int)i, k});
             }
         }
+        if (!getenv("DOPT_B200_NO_ABSORB")) absorb(p);
         for (auto& st : p.stages) {
-            if (st.users.size() < 2) {
+            if (st.users.size() < 2 && st.producer < 0) {
                 st.users.clear();   // a single reader stages for itself
                 continue;
             }
@@ -884,7 +986,10 @@ static void run_items(Plan& p, cudaStream_t s) {
         } else if (it.kind == ITEM_KERNEL) {
             Node& n = N[it.id];
             const void* in[DOPT_B200_MAX_INPUTS];
-            for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.deps[k]].ptr;
+            for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.in_override[k] >= 0 ? n.in_override[k] : n.deps[k]].ptr;
+            if (n.absorb_relu >= 0 || n.absorb_stage >= 0)
+                n.kernel->set_absorbed(n.absorb_relu >= 0 ? (float*)N[n.absorb_relu].ptr : nullptr,
+                                       n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr, n.absorb_skip);
             n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
             label = n.type.c_str();
         } else if (it.kind == ITEM_PW_SCALAR) {

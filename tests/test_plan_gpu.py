@@ -224,6 +224,32 @@ def test_wrn_16_4_sgd_bf16_loss_curve():
     assert all(np.isfinite(l[0]) for l in losses)
 
 
+def test_bn_relu_staging_absorption_is_bit_exact(monkeypatch):
+    # the plan folds relu and the NHWC bf16 staging into the batch-norm apply pass (plan.cu, pass "absorb"); same arithmetic,
+    # so the forward results are identical bit for bit; parameters only differ by the summation order of the fp32 atomics in
+    # the filter-gradient kernel (which also varies from run to run without the fusion)
+    def run(no_absorb):
+        if no_absorb:
+            monkeypatch.setenv("DOPT_B200_NO_ABSORB", "1")
+        else:
+            monkeypatch.delenv("DOPT_B200_NO_ABSORB", raising=False)
+        H.reset()
+        H.set_math(db.MATH_BF16)
+        H.set_plan_flags(FUSE | GRAPH)
+        loss, extra, net, feed = _wrn(10, 4, 8, 16, 10)()
+        upd = H.Updater(H.SGD, [loss] + extra, network=net, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+        outs = [upd.step(feed(s)) for s in range(2)]
+        st = upd.stats()
+        return outs, [p.get().copy() for p in net.params], st["launches"]
+    o0, p0, n0 = run(True)
+    o1, p1, n1 = run(False)
+    assert n1 < n0, (n0, n1)          # relu + staging launches are gone
+    assert float(o0[0][0]) == float(o1[0][0]) and np.array_equal(o0[0][1], o1[0][1])   # step 0: loss and predictions
+    assert abs(float(o0[1][0]) - float(o1[1][0])) <= 1e-5 * abs(float(o0[1][0]))
+    for a, b in zip(p0, p1):
+        assert float(np.abs(a - b).max()) <= 1e-5 * max(float(np.abs(a).max()), 1e-3)
+
+
 def test_wrn_strided_stem_sins_like_amsgrad():
     # sins10.d uses strides [2,2,2]; BASELINE configs[4] trains it with AMSGrad
     _train_compare(_wrn(10, 2, 4, 24, 10, strides=(2, 2, 2)), 2, db.MATH_FP32, 5e-4, 1e-2, kind=H.AMSGRAD,

@@ -414,11 +414,18 @@ struct PixelBox {
     int bn, bh, bw, tiles_n, tiles_p, tiles_q;
 };
 // cover an (N, P, Q) pixel grid with boxes of at most 128 pixels; `mult16` additionally requires bn*bh*bw % 16 == 0
+static int g_wgrad_pix = 64;   // pixels per wgrad k-block: 64 keeps the stages at ~36 KB so the ring is 6 deep
 static bool pick_box(int N, int P, int Q, bool mult16, PixelBox& b) {
-    int bw = Q <= 128 ? Q : 128;
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char* e = getenv("DOPT_B200_WG_PIX")) g_wgrad_pix = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
+    }
+    const int cap = mult16 ? g_wgrad_pix : 128;
+    int bw = Q <= cap ? Q : cap;
     int best = 0;
-    for (int bh = std::min(P, 128 / bw); bh >= 1; --bh) {
-        int maxn = (bh == P) ? std::min(N, 128 / (bw * bh)) : 1;
+    for (int bh = std::min(P, cap / bw); bh >= 1; --bh) {
+        int maxn = (bh == P) ? std::min(N, cap / (bw * bh)) : 1;
         for (int bn = maxn; bn >= 1; --bn) {
             int pix = bn * bh * bw;
             if (mult16 && pix % 16) continue;
@@ -682,31 +689,49 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     a.o_sc = g.K;      // per Cin column
     a.out = acc;
     int mt = (int)ceil_div(g.K, TC_BM);
-    int tiles = RS * mt * a.n_tiles;
-    // split the pixel range so that the work items fill whole rounds of the persistent grid (one CTA per SM): 18 tiles x 17
-    // splits = 306 items would run as 3 rounds on 148 SMs with the last one nearly empty
-    {
-        const int sms = sm_count();
-        int best = 1;
-        double best_eff = 0;
-        for (int sp = 1; sp <= a.pix_tiles && (int64_t)tiles * sp <= (int64_t)8 * sms; ++sp) {
-            if (a.pix_tiles / sp < 8 && sp > 1) break;   // keep the accumulation runs long enough to amortise the epilogue
-            int64_t items = (int64_t)tiles * sp;
-            int64_t rounds = ceil_div(items, (int64_t)sms);
-            int64_t per = ceil_div((int64_t)a.pix_tiles, (int64_t)sp);
-            // time ~ rounds * (iterations per item + fixed cost of an item's prologue / atomic epilogue)
-            double eff = (double)tiles * a.pix_tiles / ((double)rounds * sms * (per + 4));
-            if (eff > best_eff * 1.02) {
-                best_eff = eff;
-                best = sp;
+    // Work decomposition.  An item = (tap, group of wg_nm Kout tiles, Cin tile, pixel split).  The Kout tiles of a group share
+    // the x tile of every stage, which is what keeps the kernel off the L2 -> SM bandwidth limit
+    // (profiles/r01c_conv_bisect.md); wg_nm is bounded by the 512 TMEM columns and the shared-memory ring.  The pixel range
+    // is split so that the items fill whole rounds of the persistent grid (one CTA per SM).  Both are chosen with a small
+    // cost model: time ~ rounds * (iterations * max(MMA, copy) + per-item epilogue).
+    int nm_max = std::max(1, std::min(3, std::min(mt, 512 / a.BN)));
+    if (const char* e = getenv("DOPT_B200_WG_NM")) nm_max = std::max(1, std::min(atoi(e), nm_max));
+    const int sms = sm_count();
+    const double pix = a.kmma * 16.0, nblk = (a.BN + 63) / 64;
+    double best_t = 1e300;
+    int best_nm = 1, best_sp = 1;
+    for (int nm = 1; nm <= nm_max; ++nm) {
+        a.wg_nm = nm;
+        a.stages = 2;
+        if (nm > 1 && 3 * tc_smem_layout(a).stage_bytes > 223 * 1024) break;   // keep the ring at least 3 deep
+        const int mg_ = (int)ceil_div(mt, nm);
+        const double nm_eff = (double)mt / mg_;                                  // average Kout tiles per item
+        const double mma = nm_eff * a.kmma * 115.0 * a.BN / 160.0;               // cycles per k-iteration
+        const double copy = (2.0 * nm_eff + nblk) * pix * 128.0 / 50.0;          // ~50 B/clk per SM from L2
+        const double iter = std::max(mma, copy) + 100.0;
+        const double fixed = 4000.0 + 4000.0 * nm_eff;
+        const int64_t tiles_ = (int64_t)RS * mg_ * a.n_tiles;
+        for (int sp = 1; sp <= a.pix_tiles && tiles_ * sp <= (int64_t)16 * sms; ++sp) {
+            const int64_t per = ceil_div((int64_t)a.pix_tiles, (int64_t)sp);
+            if (per < 4 && sp > 1) break;
+            const int64_t rounds = ceil_div(tiles_ * sp, (int64_t)sms);
+            const double t = (double)rounds * ((double)per * iter + fixed);
+            if (t < best_t * 0.98) {
+                best_t = t;
+                best_nm = nm;
+                best_sp = sp;
             }
         }
-        a.splits = best;
     }
+    a.wg_nm = best_nm;
+    a.splits = best_sp;
+    const int mg = (int)ceil_div(mt, a.wg_nm);
+    int tiles = RS * mg * a.n_tiles;
     if (const char* e = getenv("DOPT_B200_WG_SPLITS")) a.splits = std::max(1, std::min(a.pix_tiles, atoi(e)));
     a.stages = pick_stages(a);
-    a.m_tiles = RS * mt;
+    a.m_tiles = RS * mg;
     a.cluster = 1;
+    if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, tiles * a.splits, s);
     {
         const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);

@@ -58,6 +58,7 @@ struct TcArgs {
     int wg_tap;         // unused (tap comes from the tile index)
     int pix_tiles;      // number of pixel boxes (the reduction dimension), split over `splits`
     int kmma;           // MMAs per stage (box pixels / 16)
+    int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
 };
 
 struct TcSmemLayout {
@@ -66,7 +67,7 @@ struct TcSmemLayout {
 __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     TcSmemLayout L;
     if (a.mode == TC_MODE_WGRAD) {
-        L.a_bytes = 2u * (uint32_t)(a.kmma * 16) * 128u;                 // two 64-wide Kout blocks
+        L.a_bytes = 2u * (uint32_t)a.wg_nm * (uint32_t)(a.kmma * 16) * 128u;   // wg_nm x two 64-wide Kout blocks
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * (uint32_t)(a.kmma * 16) * 128u;
     } else if (a.mode == TC_MODE_GEMM) {
         L.a_bytes = TC_BM * 128u;
@@ -110,8 +111,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
     constexpr int csize = pair ? 2 : 1;
     const uint32_t crank = pair ? tcg::cluster_ctarank() : 0;
     constexpr uint32_t kAccStride = 256;          // TMEM columns between the two accumulators
-    const uint32_t kTmemCols = args.nacc == 2 ? 512u : 256u;
-    const uint32_t acc_mask = args.nacc == 2 ? 1u : 0u, acc_shift = args.nacc == 2 ? 1u : 0u;
+    // WGRAD: the wg_nm accumulators of an item take up to all 512 columns; its items are long, so they are not double-buffered
+    const bool two_acc = args.nacc == 2 && MODE != TC_MODE_WGRAD;
+    const uint32_t kTmemCols = (args.nacc == 2 || MODE == TC_MODE_WGRAD) ? 512u : 256u;
+    const uint32_t acc_mask = two_acc ? 1u : 0u, acc_shift = two_acc ? 1u : 0u;
 
     // work items of this CTA (cluster): cw = cluster id, cluster id + #clusters, ...
     const int m_groups = args.m_tiles / csize;
@@ -141,7 +144,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
             w.p0 = tp * args.bh;
             w.q0 = tq * args.bw;
         }
-        if (MODE == TC_MODE_WGRAD) w.wg_tap = w.m_tile / ((args.M + TC_BM - 1) / TC_BM);   // m_tile = (tap, Kout tile)
+        if (MODE == TC_MODE_WGRAD) {   // m_tile = (tap, group of wg_nm Kout tiles)
+            const int mt = (args.M + TC_BM - 1) / TC_BM;
+            const int mg = (mt + args.wg_nm - 1) / args.wg_nm;
+            w.wg_tap = w.m_tile / mg;
+            w.p0 = (w.m_tile - w.wg_tap * mg) * args.wg_nm;   // first Kout tile of the group
+            w.q0 = min(args.wg_nm, mt - w.p0);                // Kout tiles in the group
+        }
         return w;
     };
 
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         tcg::tma_prefetch_desc(&tmA);
         tcg::tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) {
-            tcg::mbar_init(&full_bar[i], MODE == TC_MODE_CONV ? 2u : 1u);   // CONV: one arrival per producer warp (A and B)
+            tcg::mbar_init(&full_bar[i], MODE == TC_MODE_GEMM ? 1u : 2u);   // CONV / WGRAD: one arrival per producer warp (A and B)
             tcg::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -174,11 +183,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
     tcg::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 || (warp == 2 + TC_EPI_WARPS && MODE == TC_MODE_CONV)) {
+    if (warp == 0 || (warp == 2 + TC_EPI_WARPS && MODE != TC_MODE_GEMM)) {
         // ===================== TMA producer(s) =====================
         // CONV mode splits the two copies of a stage over two warps (activation tile: warp 0, filter tile: warp 6): issuing a
         // 128-row 4-D box occupies the issuing thread for several hundred cycles (profiles/r01c_conv_bisect.md)
-        const bool doA = warp == 0, doB = (MODE != TC_MODE_CONV) || warp == 2 + TC_EPI_WARPS;
+        const bool doA = warp == 0, doB = (MODE == TC_MODE_GEMM) || warp == 2 + TC_EPI_WARPS;
         // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors and coordinates live in
         // uniform registers); one elected lane issues the copies.  A single-lane `if (lane == 0)` region instead makes
         // the compiler wrap every UTMALDG / UTCHMMA in a register-to-uniform waterfall (~150 cycles per MMA, measured).
@@ -202,8 +211,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     tp = t2 % args.tiles_p;
                     ng = t2 / args.tiles_p;
                 }
-                const int mt = (args.M + TC_BM - 1) / TC_BM;
-                const int m_blk = (MODE == TC_MODE_WGRAD) ? w.m_tile % mt : 0;
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     const int it = w.it_begin + i;
                     tcg::mbar_wait(&empty_bar[st], ph ^ 1u);
@@ -261,16 +268,27 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         // WGRAD: one pixel box (image group, row tile, col tile) per k-iteration
                         const int pix = args.kmma * 16;
                         const int nblk = (BN + 63) / 64;
-                        tcg::mbar_arrive_expect_tx(fb, (uint32_t)(2 + nblk) * (uint32_t)pix * 128u);
-                        // A: dy box, two 64-channel column blocks of Kout
-                        for (int b = 0; b < 2; ++b)
-                            tcg::tma_load_4d(sa + (size_t)b * pix * 128, &tmA, fb, m_blk * TC_BM + b * 64,
-                                             tq_now * args.bw, tp_now * args.bh, ng_now * args.bn);
-                        // B: x box shifted by the tap, conv stride as element stride
-                        for (int b = 0; b < nblk; ++b)
-                            tcg::tma_load_4d(sb + (size_t)b * pix * 128, &tmB, fb, w.n_tile * BN + b * 64,
-                                             tq_now * args.bw * args.a_sv + args.tap_dw[w.wg_tap],
-                                             tp_now * args.bh * args.a_su + args.tap_dh[w.wg_tap], ng_now * args.bn);
+                        if (args.dbg & 3) {   // experiments: no copies
+                            tcg::mbar_arrive(fb);
+                            continue;
+                        }
+                        if (doA) {
+                            // A: dy box, 64-channel column blocks of the group's Kout tiles; blocks that lie entirely
+                            // beyond Kout are not copied (their accumulator rows are never stored)
+                            const int ch0 = w.p0 * TC_BM;
+                            const int nb = min(2 * w.q0, (args.M - ch0 + 63) / 64);
+                            tcg::mbar_arrive_expect_tx(fb, (uint32_t)nb * (uint32_t)pix * 128u);
+                            for (int b = 0; b < nb; ++b)
+                                tcg::tma_load_4d(sa + (size_t)b * pix * 128, &tmA, fb, ch0 + b * 64,
+                                                 tq_now * args.bw, tp_now * args.bh, ng_now * args.bn);
+                        } else {
+                            // B: x box shifted by the tap, conv stride as element stride
+                            tcg::mbar_arrive_expect_tx(fb, (uint32_t)nblk * (uint32_t)pix * 128u);
+                            for (int b = 0; b < nblk; ++b)
+                                tcg::tma_load_4d(sb + (size_t)b * pix * 128, &tmB, fb, w.n_tile * BN + b * 64,
+                                                 tq_now * args.bw * args.a_sv + args.tap_dw[w.wg_tap],
+                                                 tp_now * args.bh * args.a_su + args.tap_dh[w.wg_tap], ng_now * args.bn);
+                        }
                     }
                 }
             }
@@ -302,12 +320,15 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     if (++st == stages) { st = 0; ph ^= 1u; }
                     if (!tcg::elect_one()) continue;
                     if (MODE == TC_MODE_WGRAD) {
+                        // one accumulator (BN columns) per Kout tile of the group, all fed from the same x tile
                         const uint32_t pix_bytes = (uint32_t)args.kmma * 16u * 128u;
-                        const uint64_t da = tcg::make_smem_desc(sa, pix_bytes, 1024, 2);
                         const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);
-                        for (int k = 0; k < args.kmma; ++k)
-                            tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128), idesc,
-                                           (uint32_t)((i | k) != 0));
+                        for (int j = 0; j < w.q0; ++j) {
+                            const uint64_t da = tcg::make_smem_desc(sa + (uint32_t)j * 2u * pix_bytes, pix_bytes, 1024, 2);
+                            for (int k = 0; k < args.kmma && !(args.dbg & 4); ++k)
+                                tcg::umma_bf16(tmem_d + (uint32_t)(j * BN), da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128),
+                                               idesc, (uint32_t)((i | k) != 0));
+                        }
                     } else {
                         const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
                         const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
@@ -369,27 +390,35 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 row_ok = m < args.M;
                 row_off = (long long)m * args.o_sn;
             } else {
-                const int mt = (args.M + TC_BM - 1) / TC_BM;
-                int m = (w.m_tile % mt) * TC_BM + row;
-                row_ok = m < args.M;
-                // per-tap output offset is folded into tap_bcol[] by the host (flipped filter position)
-                row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[w.wg_tap];
+                // WGRAD: set per chunk below (the item's accumulators are w.q0 Kout tiles side by side in TMEM)
+                row_ok = false;
+                row_off = 0;
             }
             const int col0 = w.n_tile * BN;
             const uint32_t t_done = t;
             const bool have = w.n_iters > 0;
+            const int ncols = (MODE == TC_MODE_WGRAD) ? w.q0 * BN : BN;   // TMEM columns to drain
             uint32_t r[16], rn[16];
-            int cb = half * 16;
-            if (have && cb < BN) tcg::tmem_ld16(taddr + (uint32_t)cb, rn);
-            for (; cb < BN; cb += kStep) {
+            int cbt = half * 16;   // TMEM column of the chunk
+            if (have && cbt < ncols) tcg::tmem_ld16(taddr + (uint32_t)cbt, rn);
+            for (; cbt < ncols; cbt += kStep) {
                 if (have) {
                     tcg::tmem_ld_wait16(rn);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] = rn[j];
-                    if (cb + kStep < BN) tcg::tmem_ld16(taddr + (uint32_t)(cb + kStep), rn);
+                    if (cbt + kStep < ncols) tcg::tmem_ld16(taddr + (uint32_t)(cbt + kStep), rn);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+                int cb = cbt;
+                if (MODE == TC_MODE_WGRAD) {
+                    const int jt = cbt / BN;
+                    cb = cbt - jt * BN;
+                    const int m = (w.p0 + jt) * TC_BM + row;
+                    row_ok = m < args.M;
+                    // the tap's plane of the output is selected through tap_bcol[] (set by the host)
+                    row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[w.wg_tap];
                 }
                 if (!row_ok || (args.dbg & 8)) continue;
                 if (args.out_kind == TC_OUT_F32_ATOMIC && !have) continue;

@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=MODEL["depth"])
     ap.add_argument("--width", type=int, default=MODEL["width"])
+    ap.add_argument("--timeline", default=None,
+                    help="diagnostics: trace 3 graph-replayed steps with CUPTI (torch.profiler) and write a per-kernel "
+                         "summary (device time, launch count, idle gaps) to this file; prints no bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -244,6 +247,32 @@ def main():
         step_e2e(i)
     barrier()
     first_loss = float(loss_out)
+
+    if args.timeline:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                step_dev(i)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type.name == "CUDA" or "cuda" in str(e.device_type).lower()),
+                     key=lambda e: e.time_range.start)
+        by, busy, gaps, last_end = {}, 0.0, 0.0, None
+        for e in evs:
+            dur = e.time_range.end - e.time_range.start
+            name = e.name.split("(")[0].replace("void ", "")
+            a = by.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += dur
+            busy += dur
+            if last_end is not None and e.time_range.start > last_end:
+                gaps += e.time_range.start - last_end
+            last_end = max(last_end or 0, e.time_range.end)
+        with open(args.timeline, "w") as f:
+            f.write("# 3 graph-replayed steps, CUPTI kernel trace (torch.profiler); times in us per step\n")
+            f.write("busy %.1f  idle-between-kernels %.1f  kernels %d\n" % (busy / 3, gaps / 3, len(evs) // 3))
+            for k, (n, us) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+                f.write("%-70s %5d %10.1f\n" % (k[:70], n // 3, us / 3))
+        return
 
     # ---- timed: device-resident inputs ----
     sampler = ClockSampler(PHYS_GPU) if RANK == 0 else None

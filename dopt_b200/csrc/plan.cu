@@ -356,10 +356,69 @@ static bool crosses_reduce(Plan& p, int id) {
     return p.nodes[id].bucket != -1;   // a copy-in bucket member is its own root
 }
 
+// does any value the nodes of region `a` read from outside `a` depend on a node of region `b`?  (A direct, whole-tensor read
+// of a node of `b` does not count: it becomes an internal edge when the two are merged.)
+static bool region_ext_depends(Plan& p, int a, int b, std::vector<int>& stamp, int& mark) {
+    auto& N = p.nodes;
+    const Region& B = p.regions[b];
+    if (B.nodes.empty()) return false;
+    for (int n : p.regions[a].nodes)
+        for (int d : effective_deps(N[n])) {
+            int64_t off = 0;
+            int rd = root_of(p, d, &off);
+            if (N[rd].region == a) continue;
+            if (N[rd].region == b) {
+                if (off != 0 || N[rd].bytes != N[n].bytes || crosses_reduce(p, d)) return true;
+                continue;
+            }
+            if (depends_on_region(p, rd, b, B.nodes.front(), stamp, mark++)) return true;
+        }
+    return false;
+}
+
 static void build_regions(Plan& p) {
     auto& N = p.nodes;
     std::vector<int> stamp(N.size(), -1);
     int mark = 0;
+    std::vector<std::vector<int>> users(N.size());
+    for (size_t i = 0; i < N.size(); ++i) {
+        if (!N[i].needed || N[i].alias_of >= 0) continue;
+        for (int d : effective_deps(N[i])) users[root_of(p, d)].push_back((int)i);
+    }
+    std::set<int> out_roots;
+    for (int o : p.outputs) out_roots.insert(root_of(p, o));
+    const bool no_merge = getenv("DOPT_B200_NO_MERGE") != nullptr;      // experiments
+    const bool no_singles = getenv("DOPT_B200_NO_SINGLES") != nullptr;
+    // would this node set still fit the interpreter (inputs, outputs, registers, program length)?
+    std::vector<int> in_set(N.size(), -1);
+    int set_mark = 0;
+    auto fits = [&](const std::vector<int>& nodes) {
+        ++set_mark;
+        for (int id : nodes) in_set[id] = set_mark;
+        std::set<std::pair<int, int64_t>> tens;
+        std::set<int> scal;
+        int outs = 0;
+        for (int id : nodes) {
+            const Node& v = N[id];
+            auto add_tensor = [&](int t) {
+                int64_t off = 0;
+                int r = root_of(p, t, &off);
+                if (in_set[r] == set_mark && off == 0) return;
+                tens.insert({r, off});
+            };
+            if (v.pw_unary) add_tensor(v.eff_in[0]);
+            else {
+                if (v.pw_mode == dbk::B_SCALAR_A) scal.insert(v.eff_in[0]); else add_tensor(v.eff_in[0]);
+                if (v.pw_mode == dbk::B_SCALAR_B) scal.insert(v.eff_in[1]); else add_tensor(v.eff_in[1]);
+            }
+            bool outside = out_roots.count(id) > 0;
+            for (int u : users[id])
+                if (in_set[u] != set_mark) outside = true;
+            if (outside) ++outs;
+        }
+        return (int)tens.size() <= FZ_MAX_TENSORS && (int)scal.size() <= FZ_MAX_SCALARS && outs <= FZ_MAX_OUTPUTS &&
+               (int)(tens.size() + scal.size() + nodes.size()) <= FZ_MAX_REGS && (int)nodes.size() <= FZ_MAX_INSTR - 2;
+    };
     for (size_t i = 0; i < N.size(); ++i) {
         Node& v = N[i];
         if (!v.needed || v.alias_of >= 0 || v.pw_op < 0 || volume(v.op.output) < 1) continue;
@@ -370,20 +429,26 @@ static void build_regions(Plan& p) {
             if (v.pw_mode != dbk::B_SCALAR_A) tens.push_back(v.eff_in[0]);
             if (v.pw_mode != dbk::B_SCALAR_B) tens.push_back(v.eff_in[1]);
         }
-        int joined = -1;
+        // Regions this node could extend: those producing one of its whole-tensor operands.  It joins the first one that is
+        // safe, and every further one that can be MERGED into it (a weight-decay product `s*W` and the optimiser chain that
+        // consumes it start out as separate regions; without merging the product stays a launch of its own).
+        std::vector<int> chosen;
+        std::vector<int> cur{(int)i};
         for (int t : tens) {
             int64_t off = 0;
             int r = root_of(p, t, &off);
             if (off != 0 || N[r].region < 0 || volume(N[r].op.output) != vol || crosses_reduce(p, t)) continue;
-            int rid = N[r].region;
+            const int rid = N[r].region;
+            if (std::find(chosen.begin(), chosen.end(), rid) != chosen.end()) continue;
+            if (!chosen.empty() && no_merge) break;
             Region& R = p.regions[rid];
-            if ((int)R.nodes.size() >= FZ_MAX_INSTR - 2) continue;
-            // every other operand must be computable before the region runs
+            // every other operand must be computable before the merged region runs
             bool safe = true;
             for (int d : effective_deps(v)) {
                 int64_t doff = 0;
                 int rd = root_of(p, d, &doff);
-                if (N[rd].region == rid) {
+                const int dreg = N[rd].region;
+                if (dreg == rid || std::find(chosen.begin(), chosen.end(), dreg) != chosen.end()) {
                     // a partial view of a value produced inside the region would have to be read from memory the same
                     // launch writes, and a reduced gradient does not exist before its bucket ran: not fusable
                     if (doff != 0 || volume(N[rd].op.output) != vol || crosses_reduce(p, d)) { safe = false; break; }
@@ -391,28 +456,34 @@ static void build_regions(Plan& p) {
                 }
                 if (depends_on_region(p, rd, rid, R.nodes.front(), stamp, mark++)) { safe = false; break; }
             }
+            for (size_t c = 0; safe && c < chosen.size(); ++c)
+                if (region_ext_depends(p, chosen[c], rid, stamp, mark) || region_ext_depends(p, rid, chosen[c], stamp, mark))
+                    safe = false;
             if (!safe) continue;
-            joined = rid;
-            break;
+            std::vector<int> merged(cur);
+            merged.insert(merged.end(), R.nodes.begin(), R.nodes.end());
+            if (!fits(merged)) continue;
+            cur.swap(merged);
+            chosen.push_back(rid);
         }
-        if (joined < 0) {
+        int joined;
+        if (chosen.empty()) {
             joined = (int)p.regions.size();
             p.regions.push_back(Region());
+        } else {
+            joined = chosen[0];
+            for (size_t c = 1; c < chosen.size(); ++c) p.regions[chosen[c]].nodes.clear();
         }
-        p.regions[joined].nodes.push_back((int)i);
-        v.region = joined;
+        std::sort(cur.begin(), cur.end());
+        p.regions[joined].nodes = cur;
+        for (int id : cur) N[id].region = joined;
     }
-    // external inputs / outputs of every region; regions that exceed the interpreter's limits fall back to single nodes
-    std::vector<std::vector<int>> users(N.size());
-    for (size_t i = 0; i < N.size(); ++i) {
-        if (!N[i].needed || N[i].alias_of >= 0) continue;
-        for (int d : effective_deps(N[i])) users[root_of(p, d)].push_back((int)i);
-    }
-    std::set<int> out_roots;
-    for (int o : p.outputs) out_roots.insert(root_of(p, o));
+    // external inputs / outputs of every region.  Single nodes stay stand-alone kernels, except small ones: as one-instruction
+    // regions they can share a multi-tensor launch with their siblings (the 28 `W*W` products of a WRN's weight decay ...).
     for (size_t rid = 0; rid < p.regions.size(); ++rid) {
         Region& R = p.regions[rid];
-        R.fused = R.nodes.size() >= 2;
+        if (R.nodes.empty()) continue;
+        R.fused = R.nodes.size() >= 2 || (!no_singles && volume(N[R.nodes[0]].op.output) <= (1 << 16));
         if (!R.fused) {
             N[R.nodes[0]].region = -1;
             continue;
@@ -442,10 +513,10 @@ static void build_regions(Plan& p) {
             if (outside || used_outside) R.out_nodes.push_back(id);
             if (used_outside) R.terminal = false;
         }
-        bool fits = (int)R.tensor_in.size() <= FZ_MAX_TENSORS && (int)R.scalar_in.size() <= FZ_MAX_SCALARS &&
-                    (int)R.out_nodes.size() <= FZ_MAX_OUTPUTS && !R.out_nodes.empty() &&
-                    (int)(R.tensor_in.size() + R.scalar_in.size() + R.nodes.size()) <= FZ_MAX_REGS;
-        if (!fits) {
+        bool ok = (int)R.tensor_in.size() <= FZ_MAX_TENSORS && (int)R.scalar_in.size() <= FZ_MAX_SCALARS &&
+                  (int)R.out_nodes.size() <= FZ_MAX_OUTPUTS && !R.out_nodes.empty() &&
+                  (int)(R.tensor_in.size() + R.scalar_in.size() + R.nodes.size()) <= FZ_MAX_REGS;
+        if (!ok) {   // cannot happen for regions grown under fits(); a dead region (no reader) ends up here
             for (int id : R.nodes) N[id].region = -1;
             R.fused = false;
             R.nodes.clear();
@@ -496,9 +567,11 @@ static FzProgram make_program(Plan& p, const Region& R) {
 // ---- pass 3: schedule ------------------------------------------------------------------------------------------------------
 static void schedule(Plan& p) {
     auto& N = p.nodes;
-    // launches: every non-terminal fused region is its own launch; terminal ones are grouped by program
+    // launches: every non-terminal fused region starts as its own launch (the ones that are ready together and share a
+    // program are merged in the scheduling loop below); terminal ones are grouped by program
     std::map<std::string, int> by_program;
     std::vector<char> launch_terminal;
+    std::vector<std::string> launch_key;
     for (size_t rid = 0; rid < p.regions.size(); ++rid) {
         Region& R = p.regions[rid];
         if (!R.fused) continue;
@@ -517,6 +590,7 @@ static void schedule(Plan& p) {
             p.launches.back().prog = g;
             p.launch_regions.push_back({});
             launch_terminal.push_back(R.terminal ? 1 : 0);
+            launch_key.push_back(std::string((const char*)&g, sizeof(g)));
         }
         R.launch = li;
         R.row = (int)p.launch_regions[li].size();
@@ -618,16 +692,51 @@ static void schedule(Plan& p) {
     }
     using QE = std::pair<int64_t, int>;
     std::priority_queue<QE, std::vector<QE>, std::greater<QE>> ready;
+    // fused launches that are ready at the same time are independent of each other; those with the same program become
+    // rows of ONE multi-tensor launch
+    std::map<std::string, std::set<int>> ready_fused;
+    std::vector<char> consumed(items.size(), 0);
+    auto make_ready = [&](int k) {
+        ready.push({item_key[k], k});
+        if (items[k].kind == ITEM_FUSED) ready_fused[launch_key[items[k].id]].insert(k);
+    };
     for (size_t k = 0; k < items.size(); ++k)
-        if (indeg[k] == 0) ready.push({item_key[k], (int)k});
+        if (indeg[k] == 0) make_ready((int)k);
     size_t done = 0;
     while (!ready.empty()) {
         int k = ready.top().second;
         ready.pop();
+        if (consumed[k]) continue;
+        std::vector<int> issued{k};
+        if (items[k].kind == ITEM_FUSED && !getenv("DOPT_B200_NO_BATCH")) {
+            auto& same = ready_fused[launch_key[items[k].id]];
+            same.erase(k);
+            const int la = items[k].id;
+            for (int o : same) {
+                const int lb = items[o].id;
+                for (int rid : p.launch_regions[lb]) {
+                    p.regions[rid].launch = la;
+                    p.regions[rid].row = (int)p.launch_regions[la].size();
+                    p.launch_regions[la].push_back(rid);
+                    FzRow blank;
+                    memset(&blank, 0, sizeof(blank));
+                    p.launches[la].rows.push_back(blank);
+                }
+                p.launch_regions[lb].clear();
+                p.launches[lb].rows.clear();
+                p.launches[lb].dirty = false;   // never launched: must not keep the plan out of CUDA-graph mode
+                items[k].join_comm = items[k].join_comm || items[o].join_comm;
+                consumed[o] = 1;
+                issued.push_back(o);
+            }
+            same.clear();
+        }
         p.order.push_back(items[k]);
-        ++done;
-        for (int s : succ[k])
-            if (--indeg[s] == 0) ready.push({item_key[s], s});
+        for (int q : issued) {
+            ++done;
+            for (int s : succ[q])
+                if (--indeg[s] == 0) make_ready(s);
+        }
     }
     DB_REQUIRE(done == items.size(), "plan scheduling failed: cyclic dependency between fused regions");
     for (size_t li = 0; li < p.launches.size(); ++li)
@@ -1105,7 +1214,7 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
         return;
     }
     bool dirty = false;
-    for (auto& L : p.launches) dirty = dirty || L.dirty;
+    for (auto& L : p.launches) dirty = dirty || (L.dirty && !L.rows.empty());
     if (p.warm_runs < 1 || dirty) {
         // eager execution: the first one sizes every workspace so that nothing allocates during capture; later ones
         // re-upload fused row tables after a pointer change (uploads cannot happen inside a capture)

@@ -44,6 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// for waits that last a whole tile (the epilogue waiting for an accumulator): back off between polls so that the polling
+// warps do not take issue slots from the single producer / MMA-issue warps of the CTAs on this SM
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
 
 // ---- TMA ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -112,40 +112,48 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
     }
 }
 
-// KCRS fp32 -> packed bf16 through a shared-memory tile, so that both the fp32 reads (runs of 32*RS contiguous floats) and
-// the bf16 writes (runs of 32 channels) are coalesced.  6 B/element.
-//   MODE 0 (fwd):   out[k][(r*S+s)*Cp + c] = w[k][c][R-1-r][S-1-s]
-//   MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]
-// grid (ceil(Kx/32), ceil(Cx/32)) over the padded extents, 256 threads, dynamic smem 32*(32*RS+1) floats.
+// KCRS fp32 -> packed bf16 through a shared-memory tile, so that both the fp32 reads (runs of TC*RS contiguous floats) and
+// the bf16 writes (128-byte rows of 64 channels) are coalesced.  6 B/element.
+//   MODE 0 (fwd):   out[k][(r*S+s)*Cp + c] = w[k][c][R-1-r][S-1-s]     tile 4 k x 64 c
+//   MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]     tile 64 k x 4 c
+// (small tiles: a 160x160x3x3 filter still gives 120 CTAs)
+// grid (ceil(Kx/TK), ceil(Cx/TCc)) over the padded extents, 256 threads, dynamic smem TK*(TCc*RS+1) floats.
 template <int MODE>
 __global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int K, int C, int RS, int Kp, int Cp) {
-    extern __shared__ float pf_tile[];   // [32 k][32 c * RS (+1)]
-    const int ld = 32 * RS + 1;
-    const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int run = min(32, C - c0) * RS;   // contiguous floats of one k row inside this tile (<= 0: padding tile)
-    for (int kk = threadIdx.x >> 5; kk < 32; kk += 8) {
+    constexpr int TK = MODE == 0 ? 4 : 64, TCc = MODE == 0 ? 64 : 4;
+    extern __shared__ float pf_tile[];   // [TK k][TCc c * RS (+1)]
+    const int ld = TCc * RS + 1;
+    const int k0 = blockIdx.x * TK, c0 = blockIdx.y * TCc;
+    const int run = min(TCc, C - c0) * RS;   // contiguous floats of one k row inside this tile (<= 0: padding tile)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int kk = wid; kk < TK; kk += 8) {
         const int k = k0 + kk;
         const float* src = w + ((int64_t)k * C + c0) * RS;
-        for (int j = threadIdx.x & 31; j < 32 * RS; j += 32) pf_tile[kk * ld + j] = (k < K && j < run) ? src[j] : 0.f;
+        for (int j = lane; j < TCc * RS; j += 32) pf_tile[kk * ld + j] = (k < K && j < run) ? src[j] : 0.f;
     }
     __syncthreads();
     if (MODE == 0) {
-        // one (k, tap) row of 32 channels per warp trip
-        for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
+        // one (k, tap) row of 64 channels = 128 bytes per warp trip, two channels per lane
+        for (int row = wid; row < TK * RS; row += 8) {
             const int kk = row / RS, t = row - kk * RS;
-            const int k = k0 + kk, c = c0 + (threadIdx.x & 31);
-            if (k < Kp && c < Cp)
-                out[((int64_t)k * RS + t) * Cp + c] =
-                    __float2bfloat16_rn(pf_tile[kk * ld + (threadIdx.x & 31) * RS + (RS - 1 - t)]);
+            const int k = k0 + kk, c = c0 + lane * 2;
+            if (k < Kp && c < Cp) {   // Cp is even
+                const float* src = pf_tile + kk * ld + (RS - 1 - t);
+                *(__nv_bfloat162*)(out + ((int64_t)k * RS + t) * Cp + c) =
+                    __floats2bfloat162_rn(src[(lane * 2) * RS], src[(lane * 2 + 1) * RS]);
+            }
         }
     } else {
-        // one (c, tap) row of 32 output channels k per warp trip
-        for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
+        // one (c, tap) row of 64 output channels k = 128 bytes per warp trip, two k per lane
+        for (int row = wid; row < TCc * RS; row += 8) {
             const int cc = row / RS, t = row - cc * RS;
-            const int c = c0 + cc, k = k0 + (threadIdx.x & 31);
-            if (c < Cp && k < Kp)
-                out[((int64_t)c * RS + t) * Kp + k] = __float2bfloat16_rn(pf_tile[(threadIdx.x & 31) * ld + cc * RS + (RS - 1 - t)]);
+            const int c = c0 + cc, k = k0 + lane * 2;
+            if (c < Cp && k < Kp) {   // Kp is even
+                const float* src = pf_tile + cc * RS + (RS - 1 - t);
+                *(__nv_bfloat162*)(out + ((int64_t)c * RS + t) * Kp + k) =
+                    __floats2bfloat162_rn(src[(lane * 2) * ld], src[(lane * 2 + 1) * ld]);
+            }
         }
     }
 }
@@ -177,15 +185,18 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 }
 
 static void pack_filters(const float* w, __nv_bfloat16* out, int K, int C, int RS, int Kp, int Cp, int mode, cudaStream_t s) {
-    const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);
+    const int TK = mode == 0 ? 4 : 64, TCc = mode == 0 ? 64 : 4;
+    const size_t smem = (size_t)TK * (TCc * RS + 1) * sizeof(float);
     DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the packing kernel");
+    DB_REQUIRE(Kp % 2 == 0 || mode == 0, "packed Kout extent must be even");
+    DB_REQUIRE(Cp % 2 == 0 || mode == 1, "packed Cin extent must be even");
     static size_t configured[2] = {48 * 1024, 48 * 1024};
     if (smem > configured[mode]) {
         if (mode == 0) DB_CUDA(cudaFuncSetAttribute(pack_filters_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         else DB_CUDA(cudaFuncSetAttribute(pack_filters_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[mode] = 200 * 1024;
     }
-    dim3 grid((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(Cp, 32));
+    dim3 grid((unsigned)ceil_div(Kp, TK), (unsigned)ceil_div(Cp, TCc));
     if (mode == 0) pack_filters_kernel<0><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
     else pack_filters_kernel<1><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
     DB_LAUNCH_CHECK();
@@ -472,7 +483,10 @@ size_t conv_tc_staged_bytes(const ConvTc* c, int input) {
 bool conv_tc_supported(const ConvGeom& g, int kind) {
     if (g.R * g.S > TC_MAX_TAPS) return false;
     if (g.u > 2 || g.v > 2) return false;
-    if (g.C < 16 || g.K < 16) return false;   // tiny-channel layers (the 3-channel stem) are bandwidth-bound: fp32 direct kernel
+    // tiny-channel layers (the 3-channel stem) are bandwidth-bound: fp32 direct kernel.  Exception: the stem's filter
+    // gradient, a 131072-pixel reduction the direct kernel spends 0.15 ms on
+    if (g.K < 16) return false;
+    if (g.C < 16 && (kind != CONV_WGRAD || (int64_t)g.N * g.P * g.Q < 16384)) return false;
     if ((int64_t)g.N * g.P * g.Q < 128) return false;
     PixelBox b;
     if (kind == CONV_FWD) return pick_box(g.N, g.P, g.Q, false, b);
@@ -527,6 +541,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.splits = 1;
     a.taps = RS;
     a.c_iters = (int)ceil_div(g.C, TC_BK);
+    a.c_valid = g.C;
     a.k_iters = RS * a.c_iters;
     for (int r = 0; r < g.R; ++r)
         for (int q = 0; q < g.S; ++q) {
@@ -548,7 +563,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
     static int trace_runs = 0;
-    if (getenv("DOPT_B200_TRACE") && trace_runs < 6) {
+    if (getenv("DOPT_B200_TRACE") && (atoi(getenv("DOPT_B200_TRACE")) <= 1 || atoi(getenv("DOPT_B200_TRACE")) == g.C) && trace_runs < 6) {
         if (!trace_dev) DB_CUDA(cudaMalloc(&trace_dev, 1024 * 8));
         DB_CUDA(cudaMemsetAsync(trace_dev, 0, 1024 * 8, s));
         a.trace = trace_dev;
@@ -606,6 +621,7 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.n_tiles = (int)ceil_div(g.C, BN);
             a.splits = 1;
             a.c_iters = (int)ceil_div(g.K, TC_BK);
+            a.c_valid = g.K;
             int nt = 0;
             for (int r = 0; r < g.R; ++r) {
                 if (pos_mod(pa + g.ph - r, g.u)) continue;

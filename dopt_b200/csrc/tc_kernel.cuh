@@ -45,6 +45,7 @@ struct TcArgs {
     int tap_dh[TC_MAX_TAPS], tap_dw[TC_MAX_TAPS];   // A coordinate offset of the tap
     int tap_bcol[TC_MAX_TAPS];                      // CONV: first B column of the tap's slab
     int c_iters;        // CONV: 64-channel blocks per tap
+    int c_valid;        // CONV: valid reduction channels per tap (the last block may be partial)
     int bn, bh, bw;     // pixel box of one tile: images x rows x cols (bn*bh*bw <= 128)
     int tiles_p, tiles_q;   // tile grid inside one image group: m_tile -> (ng, tp, tq)
     int a_su, a_sv;     // A pixel coordinate = out pixel * stride + tap offset
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 tcg::mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator
                 tcg::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                int cb = (MODE == TC_MODE_CONV) ? w.it_begin % args.c_iters : 0;   // channel block of the k-iteration
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     tcg::mbar_wait(&full_bar[st], ph);
                     tcg::tc_fence_after();
@@ -318,6 +320,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     const uint32_t sb = sa + L.a_bytes;
                     uint64_t* eb = &empty_bar[st];
                     if (++st == stages) { st = 0; ph ^= 1u; }
+                    const int cb_now = cb;
+                    if (MODE == TC_MODE_CONV && ++cb == args.c_iters) cb = 0;
                     if (!tcg::elect_one()) continue;
                     if (MODE == TC_MODE_WGRAD) {
                         // one accumulator (BN columns) per Kout tile of the group, all fed from the same x tile
@@ -333,10 +337,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
                         const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
                                                                     : tcg::make_smem_desc(sb, 16, 1024, 2);
+                        // CONV: the last channel block of a tap may hold fewer than 64 valid channels (C = 160: 32); the
+                        // k-steps that would only multiply zero padding are not issued
+                        const int ksteps = (MODE == TC_MODE_CONV) ? min(TC_BK / 16, (args.c_valid - cb_now * TC_BK + 15) / 16) : TC_BK / 16;
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
-                            if (args.dbg & 4) continue;
+                            if ((args.dbg & 4) || k >= ksteps) continue;
                             if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                             else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                         }
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 acc = t & acc_mask;
                 const uint32_t use = t >> acc_shift;
                 ++t;
-                tcg::mbar_wait(&tmem_full_bar[acc], use & 1u);
+                tcg::mbar_wait_relaxed(&tmem_full_bar[acc], use & 1u);
                 tcg::tc_fence_after();
                 if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t < 16) args.trace[512 + 2 * t] = clock64();
             }

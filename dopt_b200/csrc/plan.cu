@@ -75,6 +75,7 @@ struct Region {
     std::vector<int> nodes;     // ascending node ids (topological)
     bool fused = false;         // >= 2 nodes
     bool terminal = false;      // every value leaving the region is a plan output only
+    bool copy = false;          // pseudo region: copies a gradient into its bucket arena (one node, no instruction)
     int launch = -1;            // index into Plan::launches
     int row = -1;
     std::vector<std::pair<int, int64_t>> tensor_in;   // (root node, byte offset)
@@ -528,6 +529,12 @@ static FzProgram make_program(Plan& p, const Region& R) {
     auto& N = p.nodes;
     FzProgram g;
     memset(&g, 0, sizeof(g));
+    if (R.copy) {   // out = in
+        g.n_tensors = 1;
+        g.n_outputs = 1;
+        g.out_reg[0] = 0;
+        return g;
+    }
     g.n_tensors = (int)R.tensor_in.size();
     g.n_scalars = (int)R.scalar_in.size();
     std::map<int, int> reg_of;   // region node -> register
@@ -640,6 +647,34 @@ static void schedule(Plan& p) {
         for (int m : p.buckets[b].members) k = std::max(k, key_of(root_of(p, m)));
         item_key.push_back(k + 1);
         item_of_bucket[b] = (int)items.size() - 1;
+    }
+    // Fused launches (and arena copies) whose results are only read by a gradient bucket are held back until the bucket is
+    // about to run: by then the siblings that feed the same bucket are ready too and they all share one launch.
+    {
+        std::vector<std::vector<std::pair<int, int>>> readers(N.size());   // root -> (reader, dep)
+        for (size_t u = 0; u < N.size(); ++u) {
+            if (!N[u].needed) continue;
+            for (int d : effective_deps(N[u])) readers[root_of(p, d)].push_back({(int)u, d});
+        }
+        for (auto& kv : item_of_launch) {
+            int64_t hold = -1;
+            bool only_buckets = true;
+            for (int rid : p.launch_regions[kv.first])
+                for (int o : p.regions[rid].out_nodes) {
+                    if (N[o].bucket >= 0) {
+                        hold = std::max(hold, item_key[item_of_bucket[N[o].bucket]]);
+                        continue;
+                    }
+                    if (readers[o].empty()) only_buckets = false;
+                    for (auto& rd : readers[o]) {
+                        if (N[rd.first].bucket >= 0 && N[rd.first].alias_of >= 0)
+                            hold = std::max(hold, item_key[item_of_bucket[N[rd.first].bucket]]);
+                        else if (!crosses_reduce(p, rd.second))
+                            only_buckets = false;
+                    }
+                }
+            if (only_buckets && hold >= 0) item_key[kv.second] = std::max(item_key[kv.second], hold);
+        }
     }
     // the item that makes the value read through `d` available: the bucket when the view chain passes an in-place allreduce
     auto producer_item = [&](int d, bool* via_bucket) {
@@ -780,6 +815,24 @@ static void form_buckets(Plan& p) {
     }
     for (auto& n : N)
         if (n.bucket == -2) n.bucket = -1;   // not needed after all
+    // Members that cannot be reduced in place (their operand is a slice of a packed result, a variable ...) are copied into
+    // the arena.  With region fusion on, each copy is a one-row "region" with the identity program, so that the copies of a
+    // bucket end up as ONE multi-tensor launch right before its all-reduce instead of a memcpy per gradient.
+    if (p.flags & DOPT_B200_PLAN_FUSE)
+        for (auto& b : p.buckets)
+            for (int m : b.members) {
+                if (N[m].alias_of >= 0 || N[m].deps.size() != 1) continue;
+                Region R;
+                R.nodes = {m};
+                R.fused = true;
+                R.copy = true;
+                int64_t off = 0;
+                int r = root_of(p, N[m].deps[0], &off);
+                R.tensor_in.push_back({r, off});
+                R.out_nodes = {m};
+                N[m].region = (int)p.regions.size();
+                p.regions.push_back(R);
+            }
 }
 
 // ---- pass "absorb": relu and NHWC staging folded into the batch-norm apply pass ----------------------------------------

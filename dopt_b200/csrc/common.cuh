@@ -66,6 +66,18 @@ inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
 }
 
 // A kernel object == dopt's CUDAKernel (cuda/source/dopt/cuda/package.d:68-79).
+// one filter to pack: KCRS fp32 -> bf16, mode 0 = forward layout [K][RS][Cp], mode 1 = feature-gradient layout [C][RS][Kp]
+struct FilterPack {
+    const float* w;
+    void* out;
+    int K, C, RS, Kp, Cp, mode;
+    int tiles_x, tile0;      // filled by the launcher: tiles along the first grid dimension, first tile of this row
+};
+size_t filter_pack_bytes(const FilterPack& f);
+// packs rows[0..n) (device copy of the table in dev_rows); total_tiles and smem_bytes come from filter_pack_layout
+void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_bytes);
+void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s);
+
 struct Kernel {
     virtual ~Kernel() {}
     virtual void run(const void* const* in, int n_in, void* out, cudaStream_t s) = 0;
@@ -78,6 +90,11 @@ struct Kernel {
     // NHWC bf16 copy the tensor-core convolutions read.  `relu_out` != null: write relu(result) there instead of the
     // result itself; `staged` != null: also write the (relu'd) result as [N][HW][Cp] bf16; `skip_primary`: nobody reads
     // the fp32 result, do not write it.  Only the leading V elements of a packed result are affected.
+    // Filter staging: a tensor-core convolution reads its filter operand in a packed bf16 layout.  When the filter is a
+    // plan variable (a parameter), the plan packs ALL filters of the step in one launch at its start (FilterPack rows) and
+    // hands every kernel its packed copy instead of letting each op pack on its own.
+    virtual bool filter_pack(int /*input*/, struct FilterPack* /*desc*/) const { return false; }
+    virtual void set_packed_filter(const void* /*packed*/) {}
     virtual bool can_absorb() const { return false; }
     virtual void set_absorbed(float* /*relu_out*/, void* /*staged*/, bool /*skip_primary*/) {}
 };

@@ -83,7 +83,7 @@ struct Region {
     std::vector<int> out_nodes;                       // region nodes whose value is needed outside
 };
 
-enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5 };
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6 };
 struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
@@ -124,6 +124,13 @@ struct dopt_b200_plan_s {
     std::vector<char> direct_out;                   // per plan output: written in place by a fused region
     std::vector<db::Bucket> buckets;
     std::vector<db::Stage> stages;
+    // filters (plan variables) packed for the tensor-core convolutions by one launch at the start of the step
+    std::vector<db::FilterPack> packs;          // host rows; .w is re-resolved at bind time
+    std::vector<std::pair<int, int>> pack_users;   // (convolution node, node of its filter operand) per row
+    db::FilterPack* packs_dev = nullptr;
+    std::vector<void*> pack_bufs;
+    int pack_tiles = 0;
+    size_t pack_smem = 0;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     int64_t device_bytes = 0;
@@ -152,6 +159,8 @@ struct dopt_b200_plan_s {
             if (b.arena) cudaFree(b.arena);
         for (auto& st : stages)
             if (st.buf) cudaFree(st.buf);
+        for (void* b : pack_bufs) cudaFree(b);
+        if (packs_dev) cudaFree(packs_dev);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
         if (comm_join) cudaEventDestroy(comm_join);
@@ -725,6 +734,13 @@ static void schedule(Plan& p) {
         items[item].join_comm = via;
         for (auto& u : st.users) add_edge(item, item_of_node[u.first]);
     }
+    if (!p.packs.empty()) {
+        items.push_back({ITEM_PACK, 0, false});
+        item_key.push_back(-1);
+        succ.emplace_back();
+        indeg.push_back(0);
+        for (auto& u : p.pack_users) add_edge((int)items.size() - 1, item_of_node[u.first]);
+    }
     using QE = std::pair<int64_t, int>;
     std::priority_queue<QE, std::vector<QE>, std::greater<QE>> ready;
     // fused launches that are ready at the same time are independent of each other; those with the same program become
@@ -995,6 +1011,31 @@ static void build(Plan& p) {
                 p.stages[it->second].users.push_back({(int)i, k});
             }
         }
+        if (!getenv("DOPT_B200_NO_FILTER_STAGE"))
+            for (size_t i = 0; i < N.size(); ++i) {
+                Node& n = N[i];
+                if (!n.kernel) continue;
+                for (int k = 0; k < (int)n.deps.size() && k < 2; ++k) {
+                    FilterPack f;
+                    if (!n.kernel->filter_pack(k, &f)) continue;
+                    int64_t off = 0;
+                    int r = root_of(p, n.deps[k], &off);
+                    if (N[r].type != "variable") continue;   // only parameters: they hold still for the whole step
+                    void* buf = nullptr;
+                    size_t bytes = filter_pack_bytes(f);
+                    DB_CUDA(cudaMalloc(&buf, bytes));
+                    p.device_bytes += (int64_t)bytes;
+                    p.pack_bufs.push_back(buf);
+                    f.out = buf;
+                    p.packs.push_back(f);
+                    p.pack_users.push_back({(int)i, n.deps[k]});
+                    n.kernel->set_packed_filter(buf);
+                }
+            }
+        if (!p.packs.empty()) {
+            filter_pack_layout(p.packs.data(), (int)p.packs.size(), &p.pack_tiles, &p.pack_smem);
+            DB_CUDA(cudaMalloc(&p.packs_dev, p.packs.size() * sizeof(FilterPack)));
+        }
         if (!getenv("DOPT_B200_NO_ABSORB")) absorb(p);
         for (auto& st : p.stages) {
             if (st.users.size() < 2 && st.producer < 0) {
@@ -1011,7 +1052,7 @@ static void build(Plan& p) {
     p.direct_out.assign(p.outputs.size(), 0);
     if (getenv("DOPT_B200_PLAN_DUMP")) {
         // one line per scheduled item: kind, op type, output volume, the op types of its operands
-        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage"};
+        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack"};
         for (const Item& it : p.order) {
             if (it.kind == ITEM_KERNEL || it.kind == ITEM_PW_SCALAR || it.kind == ITEM_COPY) {
                 const Node& n = N[it.id];
@@ -1136,6 +1177,9 @@ static void run_items(Plan& p, cudaStream_t s) {
                 comm_pending = false;
             }
             label = "allreduceBucket";
+        } else if (it.kind == ITEM_PACK) {
+            filter_pack_launch(p.packs_dev, (int)p.packs.size(), p.pack_tiles, p.pack_smem, s);
+            label = "packFilters";
         } else if (it.kind == ITEM_STAGE) {
             const Stage& st = p.stages[it.id];
             stage_nchw_to_nhwc_bf16((const float*)N[st.src_dep].ptr, st.buf, st.n, st.c, st.hw, s);
@@ -1241,6 +1285,10 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             n.ptr = (char*)N[r].ptr + off;
         }
         bind_fused(p, rets);
+        if (!p.packs.empty()) {
+            for (size_t i = 0; i < p.packs.size(); ++i) p.packs[i].w = (const float*)N[p.pack_users[i].second].ptr;
+            DB_CUDA(cudaMemcpy(p.packs_dev, p.packs.data(), p.packs.size() * sizeof(FilterPack), cudaMemcpyHostToDevice));
+        }
         p.bound_key = key;
     }
     auto body = [&](cudaStream_t st) {

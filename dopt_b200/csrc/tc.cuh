@@ -22,5 +22,7 @@ void conv_tc_run(ConvTc* c, const float* a, const float* b, float* out, cudaStre
 void conv_tc_destroy(ConvTc* c);
 void conv_tc_set_staged(ConvTc* c, int input, const void* nhwc_bf16);
 size_t conv_tc_staged_bytes(const ConvTc* c, int input);
+bool conv_tc_filter_pack(const ConvTc* c, int input, FilterPack* desc);
+void conv_tc_set_packed_filter(ConvTc* c, const void* packed);
 
 }  // namespace db

@@ -10,6 +10,7 @@
 //                wgrad      : fp32 atomics into KCRS (split over the pixel dimension)
 #include "common.cuh"
 #include "tc.cuh"
+#include <type_traits>
 #include "tc_kernel.cuh"
 #include <mutex>
 
@@ -119,19 +120,38 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
 // (small tiles: a 160x160x3x3 filter still gives 120 CTAs)
 // grid (ceil(Kx/TK), ceil(Cx/TCc)) over the padded extents, 256 threads, dynamic smem TK*(TCc*RS+1) floats.
 template <int MODE>
-__global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                           int K, int C, int RS, int Kp, int Cp) {
+__device__ __forceinline__ void pack_filters_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int C,
+                                                  int RS, int Kp, int Cp, int bx, int by, float* pf_tile) {
     constexpr int TK = MODE == 0 ? 4 : 64, TCc = MODE == 0 ? 64 : 4;
-    extern __shared__ float pf_tile[];   // [TK k][TCc c * RS (+1)]
-    const int ld = TCc * RS + 1;
-    const int k0 = blockIdx.x * TK, c0 = blockIdx.y * TCc;
+    const int ld = TCc * RS + 1;   // pf_tile: [TK k][TCc c * RS (+1)]
+    const int k0 = bx * TK, c0 = by * TCc;
     const int run = min(TCc, C - c0) * RS;   // contiguous floats of one k row inside this tile (<= 0: padding tile)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int kk = wid; kk < TK; kk += 8) {
-        const int k = k0 + kk;
-        const float* src = w + ((int64_t)k * C + c0) * RS;
-        for (int j = lane; j < TCc * RS; j += 32) pf_tile[kk * ld + j] = (k < K && j < run) ? src[j] : 0.f;
-    }
+    // TK * TCc == 256 == blockDim: the tile has exactly RS elements per thread.  All loads of a thread are issued before the
+    // first shared-memory store (registers), otherwise each block pays RS dependent global-memory round trips.
+    const int row_len = TCc * RS;
+    auto load_tile = [&](auto rs_tag) {
+        constexpr int U = decltype(rs_tag)::value;   // elements per thread handled per trip
+        for (int i0 = 0; i0 < RS; i0 += U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = (i0 + u) * 256 + (int)threadIdx.x;
+                const int kk = e / row_len, j = e - kk * row_len;
+                const int k = k0 + kk;
+                v[u] = (i0 + u < RS && k < K && j < run) ? w[((int64_t)k * C + c0) * RS + j] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = (i0 + u) * 256 + (int)threadIdx.x;
+                const int kk = e / row_len, j = e - kk * row_len;
+                if (i0 + u < RS) pf_tile[kk * ld + j] = v[u];
+            }
+        }
+    };
+    if (RS % 9 == 0) load_tile(std::integral_constant<int, 9>());
+    else if (RS % 5 == 0) load_tile(std::integral_constant<int, 5>());
+    else load_tile(std::integral_constant<int, 1>());
     __syncthreads();
     if (MODE == 0) {
         // one (k, tap) row of 64 channels = 128 bytes per warp trip, two channels per lane
@@ -157,6 +177,27 @@ __global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restri
         }
     }
 }
+template <int MODE>
+__global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                           int K, int C, int RS, int Kp, int Cp) {
+    extern __shared__ float pf_tile[];
+    pack_filters_tile<MODE>(w, out, K, C, RS, Kp, Cp, blockIdx.x, blockIdx.y, pf_tile);
+}
+// every filter of a plan in one launch: block -> (row, tile) through the rows' tile prefix
+__global__ void __launch_bounds__(256) pack_filters_multi_kernel(const FilterPack* __restrict__ rows, int n_rows) {
+    extern __shared__ float pf_tile[];
+    int lo = 0, hi = n_rows - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (rows[mid].tile0 <= (int)blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const FilterPack r = rows[lo];
+    const int t = (int)blockIdx.x - r.tile0;
+    const int bx = t % r.tiles_x, by = t / r.tiles_x;
+    if (r.mode == 0) pack_filters_tile<0>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
+    else pack_filters_tile<1>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
+}
 
 // convolutionFiltersGrad: the tensor-core kernel accumulates into a scratch laid out [tap][C][K] (K contiguous = the
 // accumulator's lane dimension, so a warp's 32 atomic adds fall into one 128-byte line); this turns it into dopt's KCRS
@@ -167,12 +208,22 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
     const int ld = 32 * RS + 1;
     const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int kk = threadIdx.x & 31, k = k0 + kk;
-    for (int row = threadIdx.x >> 5; row < 32 * RS; row += 8) {
-        const int t = row / 32, cc = row - t * 32;
-        const int c = c0 + cc;
-        float v = 0.f;
-        if (k < K && c < C) v = scratch[((int64_t)t * C + c) * K + k];
-        pf_tile[kk * ld + cc * RS + (RS - 1 - t)] = v;
+    // rows (tap, c) of 32 consecutive k; 4 * RS rows per warp, loaded four at a time into registers before they are stored
+    for (int row0 = threadIdx.x >> 5; row0 < 32 * RS; row0 += 32) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = row0 + u * 8;
+            const int t = row / 32, cc = row - t * 32;
+            const int c = c0 + cc;
+            v[u] = (row < 32 * RS && k < K && c < C) ? scratch[((int64_t)t * C + c) * K + k] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = row0 + u * 8;
+            const int t = row / 32, cc = row - t * 32;
+            if (row < 32 * RS) pf_tile[kk * ld + cc * RS + (RS - 1 - t)] = v[u];
+        }
     }
     __syncthreads();
     const int run = min(32, C - c0) * RS;
@@ -199,6 +250,35 @@ static void pack_filters(const float* w, __nv_bfloat16* out, int K, int C, int R
     dim3 grid((unsigned)ceil_div(Kp, TK), (unsigned)ceil_div(Cp, TCc));
     if (mode == 0) pack_filters_kernel<0><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
     else pack_filters_kernel<1><<<grid, 256, smem, s>>>(w, out, K, C, RS, Kp, Cp);
+    DB_LAUNCH_CHECK();
+}
+
+size_t filter_pack_bytes(const FilterPack& f) {
+    return ((size_t)(f.mode == 0 ? f.K : f.C) * f.RS * (f.mode == 0 ? f.Cp : f.Kp) * 2 + 1023) / 1024 * 1024;
+}
+void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_bytes) {
+    int tiles = 0;
+    size_t smem = 0;
+    for (int i = 0; i < n; ++i) {
+        FilterPack& f = rows[i];
+        const int TK = f.mode == 0 ? 4 : 64, TCc = f.mode == 0 ? 64 : 4;
+        f.tiles_x = (int)ceil_div(f.Kp, TK);
+        f.tile0 = tiles;
+        tiles += f.tiles_x * (int)ceil_div(f.Cp, TCc);
+        smem = std::max(smem, (size_t)TK * (TCc * f.RS + 1) * sizeof(float));
+    }
+    *total_tiles = tiles;
+    *smem_bytes = smem;
+}
+void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s) {
+    if (n <= 0 || total_tiles <= 0) return;
+    DB_REQUIRE(smem_bytes <= 200 * 1024, "filter window too large for the packing kernel");
+    static size_t configured = 48 * 1024;
+    if (smem_bytes > configured) {
+        DB_CUDA(cudaFuncSetAttribute(pack_filters_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    pack_filters_multi_kernel<<<(unsigned)total_tiles, 256, smem_bytes, s>>>(dev_rows, n);
     DB_LAUNCH_CHECK();
 }
 
@@ -462,12 +542,28 @@ struct ConvTc {
     int Cp, Kp;
     PixelBox box;
     const void* pre[2] = {nullptr, nullptr};   // operands already staged as NHWC bf16 by the plan
+    const void* pre_w = nullptr;               // filter already packed by the plan (fwd / dgrad)
 };
 
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
     nchw_to_nhwc_bf16(in, (__nv_bfloat16*)out, N, C, (int)HW, (int)align_up(C, 8), s);
 }
 size_t staged_nhwc_bytes(int N, int C, int64_t HW) { return align_up((size_t)N * HW * align_up(C, 8) * 2, 1024); }
+bool conv_tc_filter_pack(const ConvTc* c, int input, FilterPack* d) {
+    if (!c || input != 1 || c->kind == CONV_WGRAD) return false;
+    const ConvGeom& g = c->g;
+    d->w = nullptr;
+    d->out = nullptr;
+    d->K = g.K; d->C = g.C; d->RS = g.R * g.S;
+    d->mode = c->kind == CONV_FWD ? 0 : 1;
+    d->Kp = c->kind == CONV_FWD ? g.K : c->Kp;
+    d->Cp = c->kind == CONV_FWD ? c->Cp : g.C;
+    d->tiles_x = d->tile0 = 0;
+    return true;
+}
+void conv_tc_set_packed_filter(ConvTc* c, const void* packed) {
+    if (c) c->pre_w = packed;
+}
 void conv_tc_set_staged(ConvTc* c, int input, const void* p) {
     if (c && input >= 0 && input < 2) c->pre[input] = p;
 }
@@ -524,7 +620,8 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     auto* wp = (__nv_bfloat16*)(st + xb);
     if (c->pre[0]) xh = (__nv_bfloat16*)c->pre[0];
     else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
-    pack_filters(w, wp, g.K, g.C, RS, g.K, Cp, 0, s);
+    if (c->pre_w) wp = (__nv_bfloat16*)c->pre_w;
+    else pack_filters(w, wp, g.K, g.C, RS, g.K, Cp, 0, s);
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, xh, g.N, g.H, g.W, Cp, g.C, b.bn, b.bh, b.bw, g.u, g.v, "convolution x");
@@ -597,7 +694,8 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
     auto* wp = (__nv_bfloat16*)(st + yb);
     if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
     else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
-    pack_filters(w, wp, g.K, g.C, RS, Kp, g.C, 1, s);
+    if (c->pre_w) wp = (__nv_bfloat16*)c->pre_w;
+    else pack_filters(w, wp, g.K, g.C, RS, Kp, g.C, 1, s);
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, b.bh, b.bw, 1, 1, "convolutionFeaturesGrad dy");

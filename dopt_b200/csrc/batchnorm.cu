@@ -26,10 +26,20 @@ struct BnGeom {
 
 // ---- statistics ----------------------------------------------------------------------------------------------------
 // part layout: [split][C][NS] floats.  NS = 2 (train: sum(x-K), sum((x-K)^2)) or 4 (grad: + sum dy, sum dy*(x-K)).
-template <bool GRAD>
+// MASK (grad only): dy is the gradient w.r.t. relu(y); it is gated by [y > 0] with y recomputed from x and the FORWARD
+// pass's per-channel coefficients (fcoef = [mean | a | b], the very values and operation the forward apply used, so the
+// gate is bit-identical to testing the stored relu output)
+template <bool GRAD, bool MASK = false>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                       float* __restrict__ part, BnGeom g, int splits) {
+                                                       float* __restrict__ part, BnGeom g, int splits,
+                                                       const float* __restrict__ fcoef = nullptr) {
     constexpr int NS = GRAD ? 4 : 2;
+    float fm = 0.f, fa = 0.f, fb = 0.f;
+    if (MASK) {
+        fm = fcoef[blockIdx.x];
+        fa = fcoef[g.C + blockIdx.x];
+        fb = fcoef[2 * g.C + blockIdx.x];
+    }
     __shared__ float sm[NS][8];
     const int c = blockIdx.x, sp = blockIdx.y;
     const float K = x[(int64_t)c * g.HW];   // pivot: first sample of the channel
@@ -48,6 +58,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
             s2 += (a * a + b * b) + (cc * cc + d * d);
             if (GRAD) {
                 float4 q = *(const float4*)(dy + off);
+                if (MASK) {
+                    q.x = fmaf(v.x - fm, fa, fb) > 0.f ? q.x : 0.f;
+                    q.y = fmaf(v.y - fm, fa, fb) > 0.f ? q.y : 0.f;
+                    q.z = fmaf(v.z - fm, fa, fb) > 0.f ? q.z : 0.f;
+                    q.w = fmaf(v.w - fm, fa, fb) > 0.f ? q.w : 0.f;
+                }
                 sd += (q.x + q.y) + (q.z + q.w);
                 sdx += (q.x * a + q.y * b) + (q.z * cc + q.w * d);
             }
@@ -62,6 +78,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
             s2 += a * a;
             if (GRAD) {
                 float q = dy[off];
+                if (MASK) q = fmaf(x[off] - fm, fa, fb) > 0.f ? q : 0.f;
                 sd += q;
                 sdx += q * a;
             }
@@ -156,10 +173,11 @@ __global__ void bn_infer_coef(const float* __restrict__ scale, const float* __re
 }
 
 // ---- apply: y = (x-mean[c])*a[c] + b[c]  (MODE 0)   /   dx = dy*A[c] + (x-mean[c])*B[c] + Cc[c]  (MODE 1) ---------------------------------
+// RELU: MODE 0 -> relu on the result; MODE 1 -> dy is gated by the forward relu, recomputed from x and fcoef (see bn_stats_kernel)
 template <int MODE, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                        const float* __restrict__ coef, float* __restrict__ out,
-                                                       BnGeom g) {
+                                                       BnGeom g, const float* __restrict__ fcoef = nullptr) {
     const int64_t V = g.N * g.C * g.HW;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if ((g.HW & 3) == 0 && (((uintptr_t)out | (uintptr_t)x | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0) {
@@ -168,6 +186,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
             int c = (int)((i / hw4) % g.C);
             float4 v = dbk::ld_stream((const float4*)x + i), r;
             const float mu = coef[c];
+            bool m0 = true, m1 = true, m2 = true, m3 = true;
+            if (MODE == 1 && RELU) {
+                const float fm = fcoef[c], fa = fcoef[g.C + c], fb = fcoef[2 * g.C + c];
+                m0 = fmaf(v.x - fm, fa, fb) > 0.f; m1 = fmaf(v.y - fm, fa, fb) > 0.f;
+                m2 = fmaf(v.z - fm, fa, fb) > 0.f; m3 = fmaf(v.w - fm, fa, fb) > 0.f;
+            }
             v.x -= mu; v.y -= mu; v.z -= mu; v.w -= mu;
             if (MODE == 0) {
                 float a = coef[g.C + c], b = coef[2 * g.C + c];
@@ -176,6 +200,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
             } else {
                 float A = coef[g.C + c], B = coef[2 * g.C + c], Cc = coef[3 * g.C + c];
                 float4 q = dbk::ld_stream((const float4*)dy + i);
+                if (RELU) { q.x = m0 ? q.x : 0.f; q.y = m1 ? q.y : 0.f; q.z = m2 ? q.z : 0.f; q.w = m3 ? q.w : 0.f; }
                 r.x = fmaf(q.x, A, fmaf(v.x, B, Cc)); r.y = fmaf(q.y, A, fmaf(v.y, B, Cc));
                 r.z = fmaf(q.z, A, fmaf(v.z, B, Cc)); r.w = fmaf(q.w, A, fmaf(v.w, B, Cc));
             }
@@ -189,7 +214,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                 r = fmaf(v, coef[g.C + c], coef[2 * g.C + c]);
                 if (RELU) r = fmaxf(r, 0.f);
             } else {
-                r = fmaf(dy[i], coef[g.C + c], fmaf(v, coef[2 * g.C + c], coef[3 * g.C + c]));
+                float q = dy[i];
+                if (RELU) q = fmaf(x[i] - fcoef[c], fcoef[g.C + c], fcoef[2 * g.C + c]) > 0.f ? q : 0.f;
+                r = fmaf(q, coef[g.C + c], fmaf(v, coef[2 * g.C + c], coef[3 * g.C + c]));
             }
             out[i] = r;
         }
@@ -205,7 +232,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 template <int MODE, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ coef, float* __restrict__ out,
-                                                             __nv_bfloat16* __restrict__ staged, BnGeom g, int Cp) {
+                                                             __nv_bfloat16* __restrict__ staged, BnGeom g, int Cp,
+                                                             const float* __restrict__ fcoef = nullptr) {
     __shared__ float tile[64][33];
     const int n = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
@@ -218,12 +246,15 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
         float r = 0.f;
         if (c < C && hw < HW) {
             const int64_t i = img + (int64_t)c * HW + hw;
-            const float v = x[i] - coef[c];
+            const float xv = x[i];
+            const float v = xv - coef[c];
             if (MODE == 0) {
                 r = fmaf(v, coef[C + c], coef[2 * C + c]);
                 if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
             } else {
-                r = fmaf(dy[i], coef[C + c], fmaf(v, coef[2 * C + c], coef[3 * C + c]));
+                float q = dy[i];
+                if (RELU) q = fmaf(xv - fcoef[c], fcoef[C + c], fcoef[2 * C + c]) > 0.f ? q : 0.f;
+                r = fmaf(q, coef[C + c], fmaf(v, coef[2 * C + c], coef[3 * C + c]));
             }
             if (out) out[i] = r;
         }
@@ -245,18 +276,14 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
 
 namespace {
 
+// relu: forward -> relu on the result; backward -> gate dy by the forward relu (fcoef).  fp32 == nullptr: no fp32 result.
 template <int MODE>
-static void bn_apply_absorbed(const float* x, const float* dy, const float* coef, float* primary, float* relu_out,
-                              void* staged, bool skip_primary, const BnGeom& g, cudaStream_t s) {
+static void bn_apply_tiled(const float* x, const float* dy, const float* coef, float* fp32, void* staged, bool relu,
+                           const float* fcoef, const BnGeom& g, cudaStream_t s) {
     const int Cp = (int)((g.C + 7) / 8 * 8);
     dim3 grid((unsigned)ceil_div(g.HW, 32), (unsigned)ceil_div(Cp, 64), (unsigned)g.N);
-    if (relu_out) {
-        DB_REQUIRE(MODE == 0, "relu can only be absorbed by the forward pass");
-        bn_apply_stage_kernel<0, true><<<grid, 256, 0, s>>>(x, nullptr, coef, relu_out, (__nv_bfloat16*)staged, g, Cp);
-    } else {
-        bn_apply_stage_kernel<MODE, false><<<grid, 256, 0, s>>>(x, dy, coef, skip_primary ? nullptr : primary,
-                                                                (__nv_bfloat16*)staged, g, Cp);
-    }
+    if (relu) bn_apply_stage_kernel<MODE, true><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+    else bn_apply_stage_kernel<MODE, false><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
     DB_LAUNCH_CHECK();
 }
 
@@ -285,15 +312,11 @@ struct BnTrainKernel : Kernel {
     double factor;
     int splits;
     Scratch ws;
-    float* relu_out = nullptr;
-    void* staged = nullptr;
-    bool skip_primary = false;
+    Absorb ab;
+    float* coef_dev = nullptr;   // [mean | a | b] of the last run: the backward pass recomputes the relu gate from it
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
-    void set_absorbed(float* r, void* st, bool skip) override {
-        relu_out = r;
-        staged = st;
-        skip_primary = skip;
-    }
+    void set_absorbed(const Absorb& a) override { ab = a; }
+    const void* aux_ptr() const override { return coef_dev; }
     BnTrainKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 5, "batchNormTrain: deps are [x, scale, bias, mean, var]");
         g = geom_of(d.inputs[0]);
@@ -315,8 +338,10 @@ struct BnTrainKernel : Kernel {
                                                                        (const float*)in[3], (const float*)in[4], coef,
                                                                        y + V, y + V + g.C, g, splits, factor);
         DB_LAUNCH_CHECK();
-        if (relu_out || staged || skip_primary) {
-            bn_apply_absorbed<0>(x, nullptr, coef, y, relu_out, staged, skip_primary, g, s);
+        coef_dev = coef;
+        if (ab.relu || ab.staged || ab.skip_fp32 || ab.redirect) {
+            float* fp32 = ab.skip_fp32 ? nullptr : (ab.redirect ? ab.redirect : y);
+            bn_apply_tiled<0>(x, nullptr, coef, fp32, ab.staged, ab.relu, nullptr, g, s);
             return;
         }
         bn_apply_kernel<0, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, nullptr, coef, y, g);
@@ -328,14 +353,14 @@ struct BnGradKernel : Kernel {
     BnGeom g;
     int splits;
     Scratch ws;
-    void* staged = nullptr;
-    bool skip_primary = false;
+    Absorb ab;
+    const Kernel* fwd = nullptr;   // batchNormTrain kernel whose relu gates dy (plan pass "absorb")
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
-    void set_absorbed(float* r, void* st, bool skip) override {
-        DB_REQUIRE(r == nullptr, "batchNormGrad cannot absorb a relu");
-        staged = st;
-        skip_primary = skip;
+    void set_absorbed(const Absorb& a) override {
+        DB_REQUIRE(!a.relu && !a.redirect, "batchNormGrad cannot absorb a relu");
+        ab = a;
     }
+    void set_gate_source(const Kernel* forward) override { fwd = forward; }
     BnGradKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 3, "batchNormGrad: deps are [parentGrad, x, scale]");
         g = geom_of(d.inputs[1]);
@@ -353,16 +378,20 @@ struct BnGradKernel : Kernel {
         float* dx = (float*)out;
         float* part = (float*)ws.get(((size_t)splits * g.C * 4 + 4 * g.C) * sizeof(float));
         float* coef = part + (size_t)splits * g.C * 4;
-        bn_stats_kernel<true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits);
+        const float* fcoef = fwd ? (const float*)fwd->aux_ptr() : nullptr;
+        DB_REQUIRE(!fwd || fcoef, "batchNormGrad: the forward pass it takes its relu gate from has not run");
+        if (fcoef) bn_stats_kernel<true, true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fcoef);
+        else bn_stats_kernel<true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits);
         DB_LAUNCH_CHECK();
         bn_grad_finalize<<<(unsigned)ceil_div(g.C, 128), 128, 0, s>>>(part, x, (const float*)in[2], coef, dx + V,
                                                                       dx + V + g.C, g, splits);
         DB_LAUNCH_CHECK();
-        if (staged || skip_primary) {
-            bn_apply_absorbed<1>(x, dy, coef, dx, nullptr, staged, skip_primary, g, s);
+        if (ab.staged || ab.skip_fp32) {
+            bn_apply_tiled<1>(x, dy, coef, ab.skip_fp32 ? nullptr : dx, ab.staged, fcoef != nullptr, fcoef, g, s);
             return;
         }
-        bn_apply_kernel<1, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g);
+        if (fcoef) bn_apply_kernel<1, true><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g, fcoef);
+        else bn_apply_kernel<1, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g);
         DB_LAUNCH_CHECK();
     }
 };

@@ -78,6 +78,13 @@ size_t filter_pack_bytes(const FilterPack& f);
 void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_bytes);
 void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s);
 
+struct Absorb {
+    bool relu = false;          // apply relu to the result
+    float* redirect = nullptr;  // write the fp32 result here instead of the kernel's own output (the relu node's buffer)
+    bool skip_fp32 = false;     // nobody reads the fp32 result: do not write it
+    void* staged = nullptr;     // also write the result as [N][HW][Cp] bf16 here
+};
+
 struct Kernel {
     virtual ~Kernel() {}
     virtual void run(const void* const* in, int n_in, void* out, cudaStream_t s) = 0;
@@ -87,16 +94,20 @@ struct Kernel {
     virtual size_t staged_bytes(int /*input*/) const { return 0; }
     virtual void set_staged_input(int /*input*/, const void* /*nhwc_bf16*/) {}
     // Producer-side fusion (plan.cu, pass "absorb"): a kernel that can apply relu to its result and / or also emit the
-    // NHWC bf16 copy the tensor-core convolutions read.  `relu_out` != null: write relu(result) there instead of the
-    // result itself; `staged` != null: also write the (relu'd) result as [N][HW][Cp] bf16; `skip_primary`: nobody reads
-    // the fp32 result, do not write it.  Only the leading V elements of a packed result are affected.
+    // NHWC bf16 copy the tensor-core convolutions read (see struct Absorb).  Only the leading V elements of a packed
+    // result are affected.
+    virtual bool can_absorb() const { return false; }
+    virtual void set_absorbed(const struct Absorb&) {}
     // Filter staging: a tensor-core convolution reads its filter operand in a packed bf16 layout.  When the filter is a
     // plan variable (a parameter), the plan packs ALL filters of the step in one launch at its start (FilterPack rows) and
     // hands every kernel its packed copy instead of letting each op pack on its own.
     virtual bool filter_pack(int /*input*/, struct FilterPack* /*desc*/) const { return false; }
     virtual void set_packed_filter(const void* /*packed*/) {}
-    virtual bool can_absorb() const { return false; }
-    virtual void set_absorbed(float* /*relu_out*/, void* /*staged*/, bool /*skip_primary*/) {}
+    // batchNormGrad whose incoming gradient is gated by the relu that followed `forward` (a batchNormTrain kernel): the gate
+    // is recomputed from x and forward->aux_ptr() (its per-channel coefficients), so neither reluGrad nor the stored relu
+    // output is needed
+    virtual void set_gate_source(const Kernel* /*forward*/) {}
+    virtual const void* aux_ptr() const { return nullptr; }
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s);

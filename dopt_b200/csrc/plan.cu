@@ -63,7 +63,8 @@ struct Node {
     int absorbed_by = -1;       // relu: node whose kernel produces this value
     int absorb_relu = -1;       // producer: relu node whose buffer receives relu(result)
     int absorb_stage = -1;      // producer: stage whose NHWC bf16 buffer it also writes
-    bool absorb_skip = false;   // producer: its own fp32 result has no reader left
+    bool absorb_skip = false;   // producer: its fp32 result (or the relu output it writes instead) has no reader left
+    int gate_from = -1;         // batchNormGrad: batchNormTrain node whose relu gates the incoming gradient (reluGrad absorbed)
     int in_override[DOPT_B200_MAX_INPUTS] = {-1, -1, -1, -1, -1, -1, -1, -1};   // read this node instead of deps[k]
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
@@ -714,6 +715,13 @@ static void schedule(Plan& p) {
             add_edge(producer_item(d, &via), item);
             if (via) items[item].join_comm = true;
         }
+        for (int k = 0; k < DOPT_B200_MAX_INPUTS; ++k)
+            if (N[i].in_override[k] >= 0) {
+                bool via = false;
+                add_edge(producer_item(N[i].in_override[k], &via), item);
+                if (via) items[item].join_comm = true;
+            }
+        if (N[i].gate_from >= 0) add_edge(item_of_node[N[i].gate_from], item);
     }
     for (size_t b = 0; b < p.buckets.size(); ++b)
         for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
@@ -935,6 +943,52 @@ static void absorb(Plan& p) {
             if (std::find(st.users.begin(), st.users.end(), rd) == st.users.end()) all_staged = false;
         B.absorb_skip = all_staged;
     }
+    // reluGrad folded into batchNormGrad: dz = reluGrad(dy, relu(y), y) feeding batchNormGrad(dz, x, scale) of the SAME
+    // batch norm whose relu was absorbed above.  The gate [y > 0] is recomputed from x and the forward coefficients, so the
+    // reluGrad pass disappears, and when the relu output then has only staged readers left, its fp32 copy does too.
+    if (!getenv("DOPT_B200_NO_GATE"))
+        for (size_t i = 0; i < N.size(); ++i) {
+            Node& G = N[i];
+            if (!G.needed || G.alias_of >= 0 || G.type != "batchNormGrad" || !G.kernel || G.deps.size() != 3) continue;
+            int64_t off = 0;
+            const int rg = root_of(p, G.deps[0], &off);
+            Node& RG = N[rg];
+            if (off != 0 || RG.type != "reluGrad" || RG.alias_of >= 0 || RG.deps.size() != 3) continue;
+            if (N[G.deps[0]].bytes != RG.bytes || head_is_output(rg, RG.bytes)) continue;
+            auto rd = readers_of_head(rg, RG.bytes);
+            if (rd.size() != 1 || rd[0].first != (int)i || rd[0].second != 0) continue;
+            int64_t o1 = 0, ox = 0, oxb = 0;
+            const int r = root_of(p, RG.deps[1], &o1);
+            if (o1 != 0 || N[r].absorbed_by < 0) continue;
+            const int b = N[r].absorbed_by;
+            if (N[b].type != "batchNormTrain") continue;
+            if (root_of(p, G.deps[1], &ox) != root_of(p, N[b].deps[0], &oxb) || ox != oxb) continue;   // same x
+            G.in_override[0] = RG.deps[0];
+            G.gate_from = b;
+            G.kernel->set_gate_source(N[b].kernel);
+            RG.needed = false;   // never computed
+            if (RG.buf) {
+                cudaFree(RG.buf);
+                RG.buf = nullptr;
+                p.device_bytes -= RG.bytes;
+            }
+            // does anybody still read the fp32 relu output?
+            bool fp32_read = head_is_output(r, N[r].bytes);
+            const int si = N[b].absorb_stage;
+            for (auto& u : readers_of_head(r, N[r].bytes)) {
+                bool staged_user = si >= 0 && std::find(p.stages[si].users.begin(), p.stages[si].users.end(), u) !=
+                                                  p.stages[si].users.end();
+                if (!staged_user) fp32_read = true;
+            }
+            if (!fp32_read && si >= 0) {
+                N[b].absorb_skip = true;
+                if (N[r].buf) {   // the relu output only exists as the staged bf16 copy
+                    cudaFree(N[r].buf);
+                    N[r].buf = nullptr;
+                    p.device_bytes -= N[r].bytes;
+                }
+            }
+        }
 }
 
 static void build(Plan& p) {
@@ -1193,9 +1247,14 @@ static void run_items(Plan& p, cudaStream_t s) {
             Node& n = N[it.id];
             const void* in[DOPT_B200_MAX_INPUTS];
             for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.in_override[k] >= 0 ? n.in_override[k] : n.deps[k]].ptr;
-            if (n.absorb_relu >= 0 || n.absorb_stage >= 0)
-                n.kernel->set_absorbed(n.absorb_relu >= 0 ? (float*)N[n.absorb_relu].ptr : nullptr,
-                                       n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr, n.absorb_skip);
+            if (n.absorb_relu >= 0 || n.absorb_stage >= 0) {
+                Absorb ab;
+                ab.relu = n.absorb_relu >= 0;
+                ab.redirect = ab.relu ? (float*)N[n.absorb_relu].ptr : nullptr;
+                ab.skip_fp32 = n.absorb_skip;
+                ab.staged = n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr;
+                n.kernel->set_absorbed(ab);
+            }
             n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
             label = n.type.c_str();
         } else if (it.kind == ITEM_PW_SCALAR) {

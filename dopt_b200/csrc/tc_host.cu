@@ -72,6 +72,16 @@ static void make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W,
              what);
 }
 
+// NCHW fp32 output [N][C][H][W] for the TMA-store epilogue; box = (bw, bh, 16 channels, bn), no swizzle
+static bool make_map_out(CUtensorMap* m, void* base, int N, int C, int H, int W, int bn, int bh, int bw) {
+    if ((bw * 4) % 16 != 0 || ((uintptr_t)base & 15) != 0 || (W * 4) % 16 != 0) return false;
+    uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+    uint64_t st[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)C * H * W * 4};
+    uint32_t box[4] = {(uint32_t)bw, (uint32_t)bh, 16u, (uint32_t)bn};
+    return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, st, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE) ==
+           CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // staging kernels (HBM-bound)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -383,6 +393,15 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_ev[g_tc_ev_used++].second, s));
 }
 
+static int g_kbox() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DOPT_B200_KBOX");
+        v = e ? std::max(1, std::min(2, atoi(e))) : 2;
+    }
+    return v;
+}
+
 // Persistent CTAs come in two shapes (measured on the WRN layers, profiles/r01c_conv_bisect.md):
 //  * one per SM, two TMEM accumulators, the whole shared memory as operand ring: the epilogue of tile i overlaps the main
 //    loop of tile i+1 inside the CTA.  Best when an SM gets many tiles (C=160 layer: 6.9 tiles per SM) and for wgrad.
@@ -401,12 +420,13 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
     a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
-    int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - 2048) / L.stage_bytes);
+    const int fixed = 2048 + (int)(L.bar_off - L.epi_off);   // barriers + the TMA-store epilogue's slabs
+    int st = ((per_sm == 1 ? 225 : 110) * 1024 - fixed) / (int)L.stage_bytes;
     if (st > 8) st = 8;
     if (st < 2) {
         // the tile does not fit twice: fall back to one CTA per SM
         a.nacc = 2;
-        st = (int)((225 * 1024 - 2048) / L.stage_bytes);
+        st = (225 * 1024 - fixed) / (int)L.stage_bytes;
         if (st > 8) st = 8;
         if (st < 2) st = 2;
     }
@@ -656,6 +676,8 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_off = 0;
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
+    a.kbox = g_kbox();
+    a.tma_store = (!getenv("DOPT_B200_NO_TMA_STORE") && make_map_out(&a.tmC, y, g.N, g.K, g.P, g.Q, b.bn, b.bh, b.bw)) ? 1 : 0;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
@@ -748,6 +770,9 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sn = (long long)g.C * g.H * g.W; a.o_sc = (long long)g.H * g.W;
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
+            a.kbox = g_kbox();
+            a.tma_store = (g.u == 1 && g.v == 1 && !getenv("DOPT_B200_NO_TMA_STORE") &&
+                           make_map_out(&a.tmC, dx, g.N, g.C, g.H, g.W, b.bn, b.bh, b.bw)) ? 1 : 0;
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }

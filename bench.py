@@ -272,6 +272,12 @@ def main():
             f.write("busy %.1f  idle-between-kernels %.1f  kernels %d\n" % (busy / 3, gaps / 3, len(evs) // 3))
             for k, (n, us) in sorted(by.items(), key=lambda kv: -kv[1][1]):
                 f.write("%-70s %5d %10.1f\n" % (k[:70], n // 3, us / 3))
+            # the tensor-core launches of the last traced step, in launch order (us)
+            tc = [(e.name.split("(")[0].replace("void ", "").replace("db::", ""), e.time_range.end - e.time_range.start)
+                  for e in evs if "tc_kernel" in e.name]
+            tc = tc[2 * len(tc) // 3:]
+            f.write("tc_kernel launches of one step, in order:\n")
+            f.write(" ".join("%s:%.0f" % (n.replace("tc_kernel", ""), d) for n, d in tc) + "\n")
         return
 
     # ---- timed: device-resident inputs ----

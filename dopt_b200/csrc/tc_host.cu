@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <type_traits>
+#include <algorithm>
 #include "tc_kernel.cuh"
 #include <mutex>
 
@@ -631,6 +632,56 @@ void conv_tc_destroy(ConvTc* c) { delete c; }
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int pos_mod(int a, int b) { return ((a % b) + b) % b; }
 
+// Halo mode (see TcArgs): possible when the taps form full columns of consecutive vertical offsets, the tile is a stack of
+// whole image rows of one image whose width is a multiple of the 8-row swizzle atom, the convolution has unit stride and
+// the tile is computed by a CTA pair (otherwise the three filter boxes of a stage do not fit next to the activation box).
+static bool setup_halo(TcArgs& a, const PixelBox& b, int n_taps, int row_limit) {
+    static int enabled = -1;
+    if (enabled < 0) enabled = getenv("DOPT_B200_NO_HALO") ? 0 : 1;
+    if (!enabled || !a.pair || b.bn != 1 || (b.bw % 8) != 0 || a.a_su != 1 || a.a_sv != 1) return false;
+    int count = 0;
+    for (int t = 0; t < n_taps; ++t) {
+        int g = -1;
+        for (int k = 0; k < count; ++k)
+            if (a.grp_dw[k] == a.tap_dw[t]) g = k;
+        if (g < 0) {
+            if (count == 8) return false;
+            g = count++;
+            a.grp_dw[g] = a.tap_dw[t];
+            a.grp_n[g] = 0;
+            a.grp_dh0[g] = a.tap_dh[t];
+        }
+        if (a.grp_n[g] == 8) return false;
+        // taps of a group must arrive with consecutive vertical offsets (either direction is sorted below)
+        a.grp_bcol[g][a.grp_n[g]] = a.tap_bcol[t];
+        // remember dh in a scratch slot: reuse grp_dh0 after sorting
+        a.grp_n[g]++;
+        a.grp_dh0[g] = std::min(a.grp_dh0[g], a.tap_dh[t]);
+    }
+    // order each group's taps by dh and check they are consecutive
+    int nmax = 1;
+    for (int g = 0; g < count; ++g) {
+        std::vector<std::pair<int, int>> taps;   // (dh, bcol)
+        for (int t = 0; t < n_taps; ++t)
+            if (a.tap_dw[t] == a.grp_dw[g]) taps.push_back({a.tap_dh[t], a.tap_bcol[t]});
+        std::sort(taps.begin(), taps.end());
+        for (size_t j = 0; j < taps.size(); ++j) {
+            if (taps[j].first != taps[0].first + (int)j) return false;
+            a.grp_bcol[g][j] = taps[j].second;
+        }
+        a.grp_dh0[g] = taps[0].first;
+        a.grp_n[g] = (int)taps.size();
+        nmax = std::max(nmax, a.grp_n[g]);
+    }
+    if (nmax < 2) return false;   // nothing to share
+    if (b.bh + nmax - 1 > row_limit) return false;
+    a.grp_count = count;
+    a.halo_rows = b.bh + nmax - 1;
+    a.halo = 1;
+    a.k_iters = a.c_iters * count;   // pipeline stages per tile
+    return true;
+}
+
 static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStream_t s) {
     const ConvGeom& g = c->g;
     const int RS = g.R * g.S, Cp = c->Cp;
@@ -677,7 +728,11 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
     a.kbox = g_kbox();
-    a.tma_store = (!getenv("DOPT_B200_NO_TMA_STORE") && make_map_out(&a.tmC, y, g.N, g.K, g.P, g.Q, b.bn, b.bh, b.bw)) ? 1 : 0;
+    if (setup_halo(a, b, RS, 256))
+        make_map_nhwc(&tmA, xh, g.N, g.H, g.W, Cp, g.C, b.bn, a.halo_rows, b.bw, 1, 1, "convolution x (halo)");
+    // TMA-store epilogue: costs 32 KB of the operand ring; pays off where the epilogue is the longer phase (halo tiles)
+    a.tma_store = (a.halo && !getenv("DOPT_B200_NO_TMA_STORE") &&
+                   make_map_out(&a.tmC, y, g.N, g.K, g.P, g.Q, b.bn, b.bh, b.bw)) ? 1 : 0;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
@@ -771,7 +826,10 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
             a.kbox = g_kbox();
-            a.tma_store = (g.u == 1 && g.v == 1 && !getenv("DOPT_B200_NO_TMA_STORE") &&
+            if (g.u == 1 && g.v == 1 && setup_halo(a, b, nt, 256))
+                make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, a.halo_rows, b.bw, 1, 1,
+                              "convolutionFeaturesGrad dy (halo)");
+            a.tma_store = (a.halo && !getenv("DOPT_B200_NO_TMA_STORE") &&
                            make_map_out(&a.tmC, dx, g.N, g.C, g.H, g.W, b.bn, b.bh, b.bw)) ? 1 : 0;
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);

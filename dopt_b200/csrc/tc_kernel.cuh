@@ -61,6 +61,14 @@ struct TcArgs {
     int kmma;           // MMAs per stage (box pixels / 16)
     int kbox;           // CONV: (tap, channel block) boxes per pipeline stage (1 or 2): the per-stage barrier round trip and the
                         // issue-loop overhead are paid once for 2 x 4 MMAs, which keeps the tensor pipe fed by one issuing thread
+    // CONV halo mode: the taps are grouped by horizontal offset; the taps of a group (vertical offsets dh0 .. dh0+n-1) read
+    // ONE activation box with n-1 extra rows, each through a descriptor that starts (dh-dh0)*bw rows further down.  A
+    // pipeline stage = one (channel block, group): 1 activation copy + n filter copies + 4n MMAs.
+    int halo;                        // 0 = off
+    int grp_count;                   // groups (= filter width)
+    int grp_n[8], grp_dw[8], grp_dh0[8];
+    int grp_bcol[8][8];              // first B column of each tap of the group
+    int halo_rows;                   // rows of the activation box = bh + max(n) - 1
     int tma_store;      // CONV: the epilogue stages 16-channel slabs in shared memory and writes them with TMA (tmC)
     alignas(64) CUtensorMap tmC;   // NCHW fp32 output, box = (bw, bh, 16 channels, bn)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
@@ -79,9 +87,17 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
         L.a_bytes = TC_BM * 128u;
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * 64u * 128u;           // [n-block][64 k rows][64 n]
     } else {
-        const uint32_t kb = (uint32_t)(a.kbox > 1 ? a.kbox : 1);
-        L.a_bytes = kb * TC_BM * 128u;
-        L.b_bytes = kb * (((uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u + 1023u) & ~1023u);   // per box, 1024-aligned
+        const uint32_t b_box = ((uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u + 1023u) & ~1023u;   // per tap, 1024-aligned
+        if (a.halo) {
+            int nmax = 1;
+            for (int g = 0; g < a.grp_count; ++g) nmax = a.grp_n[g] > nmax ? a.grp_n[g] : nmax;
+            L.a_bytes = ((uint32_t)(a.halo_rows * a.bw) * 128u + 1023u) & ~1023u;
+            L.b_bytes = (uint32_t)nmax * b_box;
+        } else {
+            const uint32_t kb = (uint32_t)(a.kbox > 1 ? a.kbox : 1);
+            L.a_bytes = kb * TC_BM * 128u;
+            L.b_bytes = kb * b_box;
+        }
     }
     L.b_bytes = (L.b_bytes + 1023u) & ~1023u;
     L.stage_bytes = L.a_bytes + L.b_bytes;
@@ -139,8 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         w.split = rest % args.splits;
         w.n_tile = rest / args.splits;
         w.m_tile = cm * csize + (int)crank;
-        const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1) ? args.kbox : 1;
-        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + kbox - 1) / kbox;
+        const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
+        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + kbox - 1) / kbox;   // halo: k_iters = stages
         int per = (total + args.splits - 1) / args.splits;
         w.it_begin = w.split * per;
         w.n_iters = max(0, min(total, w.it_begin + per) - w.it_begin);
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 const Work w = decode(cw);
                 // CONV: it -> (tap t, channel block cb); WGRAD: it -> pixel box (ng, tp, tq)
                 int t = 0, cb = 0, tq = 0, tp = 0, ng = 0;
-                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1) ? args.kbox : 1;
+                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
                 int box = w.it_begin * kbox;   // CONV: first (tap, channel block) box of the next stage
                 if (MODE == TC_MODE_CONV) {
                     t = box / args.c_iters;
@@ -245,6 +261,32 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         }
                     }
                     if (!tcg::elect_one()) continue;
+                    if (MODE == TC_MODE_CONV && args.halo) {
+                        // stage `it` = (channel block, tap group)
+                        const int cbh = it / args.grp_count, gh = it - cbh * args.grp_count;
+                        const int n = args.grp_n[gh];
+                        const int rows = pair ? BN / 2 : BN;
+                        const uint32_t b_box = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+                        const uint32_t mult = pair ? 2u : 1u;   // the leader arms the barrier for both CTAs of a pair
+                        if (doA) {
+                            if (!pair || crank == 0)
+                                tcg::mbar_arrive_expect_tx(fb, mult * (uint32_t)(args.halo_rows * args.bw) * 128u);
+                            if constexpr (pair)
+                                tcg::tma_load_4d_2sm(sa, &tmA, fb, cbh * TC_BK, w.q0 + args.grp_dw[gh], w.p0 + args.grp_dh0[gh], w.img0);
+                            else
+                                tcg::tma_load_4d(sa, &tmA, fb, cbh * TC_BK, w.q0 + args.grp_dw[gh], w.p0 + args.grp_dh0[gh], w.img0);
+                        } else {
+                            if (!pair || crank == 0) tcg::mbar_arrive_expect_tx(fb, mult * (uint32_t)n * (uint32_t)rows * 128u);
+                            for (int j = 0; j < n; ++j) {
+                                if constexpr (pair)
+                                    tcg::tma_load_2d_2sm(sb + (size_t)j * b_box, &tmB, fb, args.grp_bcol[gh][j] + cbh * TC_BK,
+                                                         w.n_tile * BN + (int)crank * rows);
+                                else
+                                    tcg::tma_load_2d(sb + (size_t)j * b_box, &tmB, fb, args.grp_bcol[gh][j] + cbh * TC_BK, w.n_tile * BN);
+                            }
+                        }
+                        continue;
+                    }
                     if (MODE == TC_MODE_GEMM) {
                         const int nblk = (BN + 63) / 64;
                         tcg::mbar_arrive_expect_tx(fb, TC_BM * 128u + (uint32_t)nblk * 8192u);
@@ -340,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 tcg::mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator
                 tcg::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
-                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1) ? args.kbox : 1;
+                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
                 int box = w.it_begin * kbox;                                        // CONV: first box of the next stage
                 int cb = (MODE == TC_MODE_CONV) ? box % args.c_iters : 0;          // and its channel block
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
@@ -360,7 +402,24 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                             if (++cb == args.c_iters) cb = 0;
                     }
                     if (!tcg::elect_one()) continue;
-                    if (MODE == TC_MODE_WGRAD) {
+                    if (MODE == TC_MODE_CONV && args.halo) {
+                        const int it = w.it_begin + i;
+                        const int cbh = it / args.grp_count, gh = it - cbh * args.grp_count;
+                        const int n = args.grp_n[gh];
+                        const uint32_t b_box = ((uint32_t)(pair ? BN / 2 : BN) * 128u + 1023u) & ~1023u;
+                        const int ksteps = min(TC_BK / 16, (args.c_valid - cbh * TC_BK + 15) / 16);
+                        for (int j = 0; j < n; ++j) {
+                            // tap j of the group: same box, j image rows (bw pixels each, a multiple of the 8-row swizzle atom) down
+                            const uint64_t da = tcg::make_smem_desc(sa + (uint32_t)(j * args.bw) * 128u, 16, 1024, 2);
+                            const uint64_t dbb = tcg::make_smem_desc(sb + (uint32_t)j * b_box, 16, 1024, 2);
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                if ((args.dbg & 4) || k >= ksteps) continue;
+                                if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc, (uint32_t)((i | j | k) != 0));
+                                else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc, (uint32_t)((i | j | k) != 0));
+                            }
+                        }
+                    } else if (MODE == TC_MODE_WGRAD) {
                         // one accumulator (BN columns) per Kout tile of the group, all fed from the same x tile
                         const uint32_t pix_bytes = (uint32_t)args.kmma * 16u * 128u;
                         const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);

@@ -11,7 +11,6 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <type_traits>
-#include <algorithm>
 #include "tc_kernel.cuh"
 #include <mutex>
 
@@ -71,16 +70,6 @@ static void make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W,
     uint32_t es[4] = {1, (uint32_t)sv, (uint32_t)su, 1};
     check_cu(encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, st, box, es, CU_TENSOR_MAP_SWIZZLE_128B),
              what);
-}
-
-// NCHW fp32 output [N][C][H][W] for the TMA-store epilogue; box = (bw, bh, 16 channels, bn), no swizzle
-static bool make_map_out(CUtensorMap* m, void* base, int N, int C, int H, int W, int bn, int bh, int bw) {
-    if ((bw * 4) % 16 != 0 || ((uintptr_t)base & 15) != 0 || (W * 4) % 16 != 0) return false;
-    uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
-    uint64_t st[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)C * H * W * 4};
-    uint32_t box[4] = {(uint32_t)bw, (uint32_t)bh, 16u, (uint32_t)bn};
-    return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, st, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE) ==
-           CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -394,15 +383,6 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_ev[g_tc_ev_used++].second, s));
 }
 
-static int g_kbox() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DOPT_B200_KBOX");
-        v = e ? std::max(1, std::min(2, atoi(e))) : 2;
-    }
-    return v;
-}
-
 // Persistent CTAs come in two shapes (measured on the WRN layers, profiles/r01c_conv_bisect.md):
 //  * one per SM, two TMEM accumulators, the whole shared memory as operand ring: the epilogue of tile i overlaps the main
 //    loop of tile i+1 inside the CTA.  Best when an SM gets many tiles (C=160 layer: 6.9 tiles per SM) and for wgrad.
@@ -421,13 +401,12 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
     a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
-    const int fixed = 2048 + (int)(L.bar_off - L.epi_off);   // barriers + the TMA-store epilogue's slabs
-    int st = ((per_sm == 1 ? 225 : 110) * 1024 - fixed) / (int)L.stage_bytes;
+    int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - 2048) / L.stage_bytes);
     if (st > 8) st = 8;
     if (st < 2) {
         // the tile does not fit twice: fall back to one CTA per SM
         a.nacc = 2;
-        st = (225 * 1024 - fixed) / (int)L.stage_bytes;
+        st = (int)((225 * 1024 - 2048) / L.stage_bytes);
         if (st > 8) st = 8;
         if (st < 2) st = 2;
     }
@@ -632,56 +611,6 @@ void conv_tc_destroy(ConvTc* c) { delete c; }
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int pos_mod(int a, int b) { return ((a % b) + b) % b; }
 
-// Halo mode (see TcArgs): possible when the taps form full columns of consecutive vertical offsets, the tile is a stack of
-// whole image rows of one image whose width is a multiple of the 8-row swizzle atom, the convolution has unit stride and
-// the tile is computed by a CTA pair (otherwise the three filter boxes of a stage do not fit next to the activation box).
-static bool setup_halo(TcArgs& a, const PixelBox& b, int n_taps, int row_limit) {
-    static int enabled = -1;
-    if (enabled < 0) enabled = getenv("DOPT_B200_NO_HALO") ? 0 : 1;
-    if (!enabled || !a.pair || b.bn != 1 || (b.bw % 8) != 0 || a.a_su != 1 || a.a_sv != 1) return false;
-    int count = 0;
-    for (int t = 0; t < n_taps; ++t) {
-        int g = -1;
-        for (int k = 0; k < count; ++k)
-            if (a.grp_dw[k] == a.tap_dw[t]) g = k;
-        if (g < 0) {
-            if (count == 8) return false;
-            g = count++;
-            a.grp_dw[g] = a.tap_dw[t];
-            a.grp_n[g] = 0;
-            a.grp_dh0[g] = a.tap_dh[t];
-        }
-        if (a.grp_n[g] == 8) return false;
-        // taps of a group must arrive with consecutive vertical offsets (either direction is sorted below)
-        a.grp_bcol[g][a.grp_n[g]] = a.tap_bcol[t];
-        // remember dh in a scratch slot: reuse grp_dh0 after sorting
-        a.grp_n[g]++;
-        a.grp_dh0[g] = std::min(a.grp_dh0[g], a.tap_dh[t]);
-    }
-    // order each group's taps by dh and check they are consecutive
-    int nmax = 1;
-    for (int g = 0; g < count; ++g) {
-        std::vector<std::pair<int, int>> taps;   // (dh, bcol)
-        for (int t = 0; t < n_taps; ++t)
-            if (a.tap_dw[t] == a.grp_dw[g]) taps.push_back({a.tap_dh[t], a.tap_bcol[t]});
-        std::sort(taps.begin(), taps.end());
-        for (size_t j = 0; j < taps.size(); ++j) {
-            if (taps[j].first != taps[0].first + (int)j) return false;
-            a.grp_bcol[g][j] = taps[j].second;
-        }
-        a.grp_dh0[g] = taps[0].first;
-        a.grp_n[g] = (int)taps.size();
-        nmax = std::max(nmax, a.grp_n[g]);
-    }
-    if (nmax < 2) return false;   // nothing to share
-    if (b.bh + nmax - 1 > row_limit) return false;
-    a.grp_count = count;
-    a.halo_rows = b.bh + nmax - 1;
-    a.halo = 1;
-    a.k_iters = a.c_iters * count;   // pipeline stages per tile
-    return true;
-}
-
 static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStream_t s) {
     const ConvGeom& g = c->g;
     const int RS = g.R * g.S, Cp = c->Cp;
@@ -727,12 +656,6 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_off = 0;
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
-    a.kbox = g_kbox();
-    if (setup_halo(a, b, RS, 256))
-        make_map_nhwc(&tmA, xh, g.N, g.H, g.W, Cp, g.C, b.bn, a.halo_rows, b.bw, 1, 1, "convolution x (halo)");
-    // TMA-store epilogue: costs 32 KB of the operand ring; pays off where the epilogue is the longer phase (halo tiles)
-    a.tma_store = (a.halo && !getenv("DOPT_B200_NO_TMA_STORE") &&
-                   make_map_out(&a.tmC, y, g.N, g.K, g.P, g.Q, b.bn, b.bh, b.bw)) ? 1 : 0;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
@@ -825,12 +748,6 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sn = (long long)g.C * g.H * g.W; a.o_sc = (long long)g.H * g.W;
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
-            a.kbox = g_kbox();
-            if (g.u == 1 && g.v == 1 && setup_halo(a, b, nt, 256))
-                make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, a.halo_rows, b.bw, 1, 1,
-                              "convolutionFeaturesGrad dy (halo)");
-            a.tma_store = (a.halo && !getenv("DOPT_B200_NO_TMA_STORE") &&
-                           make_map_out(&a.tmC, dx, g.N, g.C, g.H, g.W, b.bn, b.bh, b.bw)) ? 1 : 0;
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }

@@ -59,25 +59,12 @@ struct TcArgs {
     int wg_tap;         // unused (tap comes from the tile index)
     int pix_tiles;      // number of pixel boxes (the reduction dimension), split over `splits`
     int kmma;           // MMAs per stage (box pixels / 16)
-    int kbox;           // CONV: (tap, channel block) boxes per pipeline stage (1 or 2): the per-stage barrier round trip and the
-                        // issue-loop overhead are paid once for 2 x 4 MMAs, which keeps the tensor pipe fed by one issuing thread
-    // CONV halo mode: the taps are grouped by horizontal offset; the taps of a group (vertical offsets dh0 .. dh0+n-1) read
-    // ONE activation box with n-1 extra rows, each through a descriptor that starts (dh-dh0)*bw rows further down.  A
-    // pipeline stage = one (channel block, group): 1 activation copy + n filter copies + 4n MMAs.
-    int halo;                        // 0 = off
-    int grp_count;                   // groups (= filter width)
-    int grp_n[8], grp_dw[8], grp_dh0[8];
-    int grp_bcol[8][8];              // first B column of each tap of the group
-    int halo_rows;                   // rows of the activation box = bh + max(n) - 1
-    int tma_store;      // CONV: the epilogue stages 16-channel slabs in shared memory and writes them with TMA (tmC)
-    alignas(64) CUtensorMap tmC;   // NCHW fp32 output, box = (bw, bh, 16 channels, bn)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
 };
 
 struct TcSmemLayout {
-    uint32_t a_bytes, b_bytes, stage_bytes, epi_off, bar_off, total;
+    uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total;
 };
-static constexpr uint32_t TC_EPI_SLAB = 16u * 128u * 4u;   // 16 channels x 128 pixels fp32
 __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     TcSmemLayout L;
     if (a.mode == TC_MODE_WGRAD) {
@@ -87,23 +74,12 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
         L.a_bytes = TC_BM * 128u;
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * 64u * 128u;           // [n-block][64 k rows][64 n]
     } else {
-        const uint32_t b_box = ((uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u + 1023u) & ~1023u;   // per tap, 1024-aligned
-        if (a.halo) {
-            int nmax = 1;
-            for (int g = 0; g < a.grp_count; ++g) nmax = a.grp_n[g] > nmax ? a.grp_n[g] : nmax;
-            L.a_bytes = ((uint32_t)(a.halo_rows * a.bw) * 128u + 1023u) & ~1023u;
-            L.b_bytes = (uint32_t)nmax * b_box;
-        } else {
-            const uint32_t kb = (uint32_t)(a.kbox > 1 ? a.kbox : 1);
-            L.a_bytes = kb * TC_BM * 128u;
-            L.b_bytes = kb * b_box;
-        }
+        L.a_bytes = TC_BM * 128u;
+        L.b_bytes = (uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u;
     }
     L.b_bytes = (L.b_bytes + 1023u) & ~1023u;
     L.stage_bytes = L.a_bytes + L.b_bytes;
-    L.epi_off = L.stage_bytes * (uint32_t)a.stages;
-    // TMA-store epilogue: two warp groups (TC_EPI_WARPS / 4), two slabs each
-    L.bar_off = L.epi_off + ((a.mode == TC_MODE_CONV && a.tma_store) ? 4u * TC_EPI_SLAB : 0u);
+    L.bar_off = L.stage_bytes * (uint32_t)a.stages;
     L.total = L.bar_off + 1024u /* barriers + tmem slot */ + 1024u /* alignment slack */;
     return L;
 }
@@ -155,8 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         w.split = rest % args.splits;
         w.n_tile = rest / args.splits;
         w.m_tile = cm * csize + (int)crank;
-        const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
-        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + kbox - 1) / kbox;   // halo: k_iters = stages
+        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : args.k_iters;
         int per = (total + args.splits - 1) / args.splits;
         w.it_begin = w.split * per;
         w.n_iters = max(0, min(total, w.it_begin + per) - w.it_begin);
@@ -228,11 +203,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 const Work w = decode(cw);
                 // CONV: it -> (tap t, channel block cb); WGRAD: it -> pixel box (ng, tp, tq)
                 int t = 0, cb = 0, tq = 0, tp = 0, ng = 0;
-                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
-                int box = w.it_begin * kbox;   // CONV: first (tap, channel block) box of the next stage
                 if (MODE == TC_MODE_CONV) {
-                    t = box / args.c_iters;
-                    cb = box - t * args.c_iters;
+                    t = w.it_begin / args.c_iters;
+                    cb = w.it_begin - t * args.c_iters;
                 } else if (MODE == TC_MODE_WGRAD) {
                     tq = w.it_begin % args.tiles_q;
                     int t2 = w.it_begin / args.tiles_q;
@@ -248,12 +221,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     uint64_t* fb = &full_bar[st];
                     const int t_now = t, cb_now = cb, tq_now = tq, tp_now = tp, ng_now = ng;
                     if (++st == stages) { st = 0; ph ^= 1u; }
-                    int nb = 1;
                     if (MODE == TC_MODE_CONV) {
-                        nb = min(kbox, args.k_iters - box);
-                        box += nb;
-                        for (int j = 0; j < nb; ++j)
-                            if (++cb == args.c_iters) { cb = 0; ++t; }
+                        if (++cb == args.c_iters) { cb = 0; ++t; }
                     } else if (MODE == TC_MODE_WGRAD) {
                         if (++tq == args.tiles_q) {
                             tq = 0;
@@ -261,32 +230,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         }
                     }
                     if (!tcg::elect_one()) continue;
-                    if (MODE == TC_MODE_CONV && args.halo) {
-                        // stage `it` = (channel block, tap group)
-                        const int cbh = it / args.grp_count, gh = it - cbh * args.grp_count;
-                        const int n = args.grp_n[gh];
-                        const int rows = pair ? BN / 2 : BN;
-                        const uint32_t b_box = ((uint32_t)rows * 128u + 1023u) & ~1023u;
-                        const uint32_t mult = pair ? 2u : 1u;   // the leader arms the barrier for both CTAs of a pair
-                        if (doA) {
-                            if (!pair || crank == 0)
-                                tcg::mbar_arrive_expect_tx(fb, mult * (uint32_t)(args.halo_rows * args.bw) * 128u);
-                            if constexpr (pair)
-                                tcg::tma_load_4d_2sm(sa, &tmA, fb, cbh * TC_BK, w.q0 + args.grp_dw[gh], w.p0 + args.grp_dh0[gh], w.img0);
-                            else
-                                tcg::tma_load_4d(sa, &tmA, fb, cbh * TC_BK, w.q0 + args.grp_dw[gh], w.p0 + args.grp_dh0[gh], w.img0);
-                        } else {
-                            if (!pair || crank == 0) tcg::mbar_arrive_expect_tx(fb, mult * (uint32_t)n * (uint32_t)rows * 128u);
-                            for (int j = 0; j < n; ++j) {
-                                if constexpr (pair)
-                                    tcg::tma_load_2d_2sm(sb + (size_t)j * b_box, &tmB, fb, args.grp_bcol[gh][j] + cbh * TC_BK,
-                                                         w.n_tile * BN + (int)crank * rows);
-                                else
-                                    tcg::tma_load_2d(sb + (size_t)j * b_box, &tmB, fb, args.grp_bcol[gh][j] + cbh * TC_BK, w.n_tile * BN);
-                            }
-                        }
-                        continue;
-                    }
                     if (MODE == TC_MODE_GEMM) {
                         const int nblk = (BN + 63) / 64;
                         tcg::mbar_arrive_expect_tx(fb, TC_BM * 128u + (uint32_t)nblk * 8192u);
@@ -298,43 +241,29 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         // are credited to the leader's barrier, which the leader arms for the pair
                         const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
                         const int rows = BN / 2;
-                        const uint32_t b_box = ((uint32_t)rows * 128u + 1023u) & ~1023u;
-                        int tt = t_now, cc = cb_now;
                         if (doA) {
-                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * (uint32_t)nb * a_bytes);
-                            for (int j = 0; j < nb; ++j) {
-                                tcg::tma_load_4d_2sm(sa + (size_t)j * (TC_BM * 128), &tmA, fb, cc * TC_BK,
-                                                     w.q0 * args.a_sv + args.tap_dw[tt], w.p0 * args.a_su + args.tap_dh[tt], w.img0);
-                                if (++cc == args.c_iters) { cc = 0; ++tt; }
-                            }
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * a_bytes);
+                            tcg::tma_load_4d_2sm(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
+                                                 w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
                         } else {
-                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * (uint32_t)nb * (uint32_t)rows * 128u);
-                            for (int j = 0; j < nb; ++j) {
-                                tcg::tma_load_2d_2sm(sb + (size_t)j * b_box, &tmB, fb, args.tap_bcol[tt] + cc * TC_BK,
-                                                     w.n_tile * BN + (int)crank * rows);
-                                if (++cc == args.c_iters) { cc = 0; ++tt; }
-                            }
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * (uint32_t)rows * 128u);
+                            tcg::tma_load_2d_2sm(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK,
+                                                 w.n_tile * BN + (int)crank * rows);
                         }
                     } else if (MODE == TC_MODE_CONV) {
                         const uint32_t a_bytes = (args.dbg & 1) ? 0u : (uint32_t)(args.bn * args.bh * args.bw) * 128u;
                         const uint32_t b_bytes = (args.dbg & 2) ? 0u : (uint32_t)BN * 128u;
-                        const uint32_t b_box = ((uint32_t)BN * 128u + 1023u) & ~1023u;
-                        int tt = t_now, cc = cb_now;
                         if (doA) {
-                            if (a_bytes) tcg::mbar_arrive_expect_tx(fb, (uint32_t)nb * a_bytes);
+                            if (a_bytes) tcg::mbar_arrive_expect_tx(fb, a_bytes);
                             else tcg::mbar_arrive(fb);
-                            for (int j = 0; j < nb && !(args.dbg & 1); ++j) {
-                                tcg::tma_load_4d(sa + (size_t)j * (TC_BM * 128), &tmA, fb, cc * TC_BK,
-                                                 w.q0 * args.a_sv + args.tap_dw[tt], w.p0 * args.a_su + args.tap_dh[tt], w.img0);
-                                if (++cc == args.c_iters) { cc = 0; ++tt; }
-                            }
+                            if (!(args.dbg & 1))
+                                tcg::tma_load_4d(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
+                                                 w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
                         } else {
-                            if (b_bytes) tcg::mbar_arrive_expect_tx(fb, (uint32_t)nb * b_bytes);
+                            if (b_bytes) tcg::mbar_arrive_expect_tx(fb, b_bytes);
                             else tcg::mbar_arrive(fb);
-                            for (int j = 0; j < nb && !(args.dbg & 2); ++j) {
-                                tcg::tma_load_2d(sb + (size_t)j * b_box, &tmB, fb, args.tap_bcol[tt] + cc * TC_BK, w.n_tile * BN);
-                                if (++cc == args.c_iters) { cc = 0; ++tt; }
-                            }
+                            if (!(args.dbg & 2))
+                                tcg::tma_load_2d(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK, w.n_tile * BN);
                         }
                     } else {
                         // WGRAD: one pixel box (image group, row tile, col tile) per k-iteration
@@ -382,9 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 tcg::mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator
                 tcg::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
-                const int kbox = (MODE == TC_MODE_CONV && args.kbox > 1 && !args.halo) ? args.kbox : 1;
-                int box = w.it_begin * kbox;                                        // CONV: first box of the next stage
-                int cb = (MODE == TC_MODE_CONV) ? box % args.c_iters : 0;          // and its channel block
+                int cb = (MODE == TC_MODE_CONV) ? w.it_begin % args.c_iters : 0;   // channel block of the k-iteration
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     tcg::mbar_wait(&full_bar[st], ph);
                     tcg::tc_fence_after();
@@ -394,32 +321,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     uint64_t* eb = &empty_bar[st];
                     if (++st == stages) { st = 0; ph ^= 1u; }
                     const int cb_now = cb;
-                    int nb = 1;
-                    if (MODE == TC_MODE_CONV) {
-                        nb = min(kbox, args.k_iters - box);
-                        box += nb;
-                        for (int j = 0; j < nb; ++j)
-                            if (++cb == args.c_iters) cb = 0;
-                    }
+                    if (MODE == TC_MODE_CONV && ++cb == args.c_iters) cb = 0;
                     if (!tcg::elect_one()) continue;
-                    if (MODE == TC_MODE_CONV && args.halo) {
-                        const int it = w.it_begin + i;
-                        const int cbh = it / args.grp_count, gh = it - cbh * args.grp_count;
-                        const int n = args.grp_n[gh];
-                        const uint32_t b_box = ((uint32_t)(pair ? BN / 2 : BN) * 128u + 1023u) & ~1023u;
-                        const int ksteps = min(TC_BK / 16, (args.c_valid - cbh * TC_BK + 15) / 16);
-                        for (int j = 0; j < n; ++j) {
-                            // tap j of the group: same box, j image rows (bw pixels each, a multiple of the 8-row swizzle atom) down
-                            const uint64_t da = tcg::make_smem_desc(sa + (uint32_t)(j * args.bw) * 128u, 16, 1024, 2);
-                            const uint64_t dbb = tcg::make_smem_desc(sb + (uint32_t)j * b_box, 16, 1024, 2);
-#pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {
-                                if ((args.dbg & 4) || k >= ksteps) continue;
-                                if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc, (uint32_t)((i | j | k) != 0));
-                                else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + (uint64_t)(k * 2), idesc, (uint32_t)((i | j | k) != 0));
-                            }
-                        }
-                    } else if (MODE == TC_MODE_WGRAD) {
+                    if (MODE == TC_MODE_WGRAD) {
                         // one accumulator (BN columns) per Kout tile of the group, all fed from the same x tile
                         const uint32_t pix_bytes = (uint32_t)args.kmma * 16u * 128u;
                         const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);
@@ -430,25 +334,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                                                idesc, (uint32_t)((i | k) != 0));
                         }
                     } else {
-                        const uint32_t b_box = (MODE == TC_MODE_CONV)
-                                                   ? (((uint32_t)(pair ? BN / 2 : BN) * 128u + 1023u) & ~1023u) : 0u;
-                        int cc = cb_now;
-                        for (int j = 0; j < nb; ++j) {
-                            const uint64_t da = tcg::make_smem_desc(sa + (uint32_t)j * (TC_BM * 128u), 16, 1024, 2);
-                            const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
-                                                                        : tcg::make_smem_desc(sb + (uint32_t)j * b_box, 16, 1024, 2);
-                            // CONV: the last channel block of a tap may hold fewer than 64 valid channels (C = 160: 32);
-                            // the k-steps that would only multiply zero padding are not issued
-                            const int ksteps = (MODE == TC_MODE_CONV) ? min(TC_BK / 16, (args.c_valid - cc * TC_BK + 15) / 16)
-                                                                      : TC_BK / 16;
-                            if (++cc == args.c_iters) cc = 0;
+                        const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
+                        const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
+                                                                    : tcg::make_smem_desc(sb, 16, 1024, 2);
+                        // CONV: the last channel block of a tap may hold fewer than 64 valid channels (C = 160: 32); the
+                        // k-steps that would only multiply zero padding are not issued
+                        const int ksteps = (MODE == TC_MODE_CONV) ? min(TC_BK / 16, (args.c_valid - cb_now * TC_BK + 15) / 16) : TC_BK / 16;
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {
-                                const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
-                                if ((args.dbg & 4) || k >= ksteps) continue;
-                                if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | j | k) != 0));
-                                else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | j | k) != 0));
-                            }
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
+                            if ((args.dbg & 4) || k >= ksteps) continue;
+                            if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
+                            else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                         }
                     }
                     // frees the stage once these MMAs have read it (in both CTAs of a pair)
@@ -507,49 +404,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
             const int col0 = w.n_tile * BN;
             const uint32_t t_done = t;
             const bool have = w.n_iters > 0;
-            if (MODE == TC_MODE_CONV && args.tma_store && have) {
-                // ---- TMA-store epilogue.  The four warps that share a `half` (one per TMEM lane quarter) fill a slab of
-                // 16 channels x 128 pixels in shared memory, laid out exactly like the (bw, bh, 16, bn) box of the NCHW
-                // output; one of their threads hands it to the TMA.  Plain st.global from the epilogue warps was the
-                // bottleneck of the whole kernel once the main loop ran at full speed (13K cycles per tile next to the
-                // streaming TMA loads, 3K without them -- profiles/r01c_conv_bisect.md).
-                float* slab0 = (float*)(smem + L.epi_off) + (size_t)half * 2u * (TC_EPI_SLAB / 4u);
-                const bool issuer = quarter == 0 && lane == 0;
-                const int bwh = args.bw * args.bh;
-                const int in_ = row / bwh;
-                const int rem = row - in_ * bwh;
-                const bool row_in_box = row < args.bn * bwh;
-                uint32_t rr[16], rrn[16];
-                int cb2 = half * 16;
-                uint32_t buf = 0;
-                if (cb2 < BN) tcg::tmem_ld16(taddr + (uint32_t)cb2, rrn);
-                for (; cb2 < BN; cb2 += kStep, buf ^= 1u) {
-                    tcg::tmem_ld_wait16(rrn);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) rr[j] = rrn[j];
-                    if (cb2 + kStep < BN) tcg::tmem_ld16(taddr + (uint32_t)(cb2 + kStep), rrn);
-                    // the store that last read this slab (two chunks ago) must be done with it
-                    if (issuer) tcg::bulk_wait_read<1>();
-                    tcg::named_bar_sync(1 + half, 128);
-                    float* slab = slab0 + (size_t)buf * (TC_EPI_SLAB / 4u);
-                    if (row_in_box) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) slab[(in_ * 16 + j) * bwh + rem] = __uint_as_float(rr[j]);
-                    }
-                    tcg::fence_proxy_async();
-                    tcg::named_bar_sync(1 + half, 128);
-                    if (issuer && !(args.dbg & 8)) {
-                        tcg::tma_store_4d(&args.tmC, slab, w.q0, w.p0, col0 + cb2, w.img0);
-                        tcg::bulk_commit();
-                    }
-                }
-                tcg::tc_fence_before();
-                if constexpr (pair) tcg::mbar_arrive_cluster(tcg::smem_u32(&tmem_empty_bar[acc]) & 0xFEFFFFFFu);
-                else tcg::mbar_arrive(&tmem_empty_bar[acc]);
-                if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t_done <= 16 && t_done > 0)
-                    args.trace[512 + 2 * (t_done - 1) + 1] = clock64();
-                continue;
-            }
             const int ncols = (MODE == TC_MODE_WGRAD) ? w.q0 * BN : BN;   // TMEM columns to drain
             uint32_t r[16], rn[16];
             int cbt = half * 16;   // TMEM column of the chunk
@@ -591,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         if (c < args.Nout) {
                             long long o = row_off + (long long)c * args.o_sc;
                             float val = __uint_as_float(r[j]);
-                            if (args.out_kind == TC_OUT_F32) __stcs((float*)args.out + o, val);
+                            if (args.out_kind == TC_OUT_F32) ((float*)args.out)[o] = val;
                             else if (args.out_kind == TC_OUT_BF16) ((__nv_bfloat16*)args.out)[o] = __float2bfloat16_rn(val);
                             else atomicAdd((float*)args.out + o, val);
                         }
@@ -610,7 +464,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         }
     }
 
-    if (MODE == TC_MODE_CONV && args.tma_store) tcg::bulk_wait_all();   // shared memory must outlive the TMA stores reading it
     __syncwarp();   // the single-lane producer / issuer loops diverged their warps; the cluster barrier is warp-aligned
     tcg::tc_fence_before();
     if constexpr (pair) tcg::cluster_sync();   // nobody leaves while the peer may still arrive on this CTA's barriers

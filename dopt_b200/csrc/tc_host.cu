@@ -366,7 +366,23 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
             DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             pair_configured = true;
         }
-        DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
+        if (a.trace || a.dbg) {
+            static bool instr_configured = false;
+            if (!instr_configured) {
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                instr_configured = true;
+            }
+            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, true>, tmA, tmB, a));
+        } else {
+            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
+        }
+    } else if (a.trace || a.dbg) {
+        static bool instr_configured = false;
+        if (!instr_configured) {
+            DB_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            instr_configured = true;
+        }
+        tc_kernel<MODE, false, true><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     } else {
         tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     }

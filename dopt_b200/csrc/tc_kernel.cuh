@@ -92,10 +92,16 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
 // epilogue of item i (TMEM -> registers -> global) overlaps the main loop of item i+1, and barrier set-up, TMEM allocation
 // and tensor-map prefetch are paid once per SM instead of once per tile (profiles/r01c_conv_bisect.md: in the
 // one-tile-per-CTA version those fixed costs and the exposed epilogue were 60 % of the kernel time).
-template <int MODE, bool PAIR = false>
+// INSTR: the experiment hooks (TcArgs::trace / dbg) are compiled in; the production instantiations leave them out -- the
+// single-warp issue loops are sensitive to every extra instruction.
+template <int MODE, bool PAIR = false, bool INSTR = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
-                                                        const __grid_constant__ TcArgs args) {
+                                                        const __grid_constant__ TcArgs args_) {
+    const TcArgs& args = args_;
+    const unsigned long long* const trace_on = INSTR ? args_.trace : nullptr;   // compile-time null in the production build
+    const int dbg = INSTR ? args_.dbg : 0;
+    (void)trace_on;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcSmemLayout L = tc_smem_layout(args);
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     const int it = w.it_begin + i;
                     tcg::mbar_wait(&empty_bar[st], ph ^ 1u);
-                    if (args.trace && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[(warp == 0 ? 0 : 768) + (g < 255 ? g : 255)] = clock64();
+                    if (trace_on && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[(warp == 0 ? 0 : 768) + (g < 255 ? g : 255)] = clock64();
                     uint8_t* sa = smem + (size_t)st * L.stage_bytes;
                     uint8_t* sb = sa + L.a_bytes;
                     uint64_t* fb = &full_bar[st];
@@ -251,25 +257,25 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                                                  w.n_tile * BN + (int)crank * rows);
                         }
                     } else if (MODE == TC_MODE_CONV) {
-                        const uint32_t a_bytes = (args.dbg & 1) ? 0u : (uint32_t)(args.bn * args.bh * args.bw) * 128u;
-                        const uint32_t b_bytes = (args.dbg & 2) ? 0u : (uint32_t)BN * 128u;
+                        const uint32_t a_bytes = (dbg & 1) ? 0u : (uint32_t)(args.bn * args.bh * args.bw) * 128u;
+                        const uint32_t b_bytes = (dbg & 2) ? 0u : (uint32_t)BN * 128u;
                         if (doA) {
                             if (a_bytes) tcg::mbar_arrive_expect_tx(fb, a_bytes);
                             else tcg::mbar_arrive(fb);
-                            if (!(args.dbg & 1))
+                            if (!(dbg & 1))
                                 tcg::tma_load_4d(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
                                                  w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
                         } else {
                             if (b_bytes) tcg::mbar_arrive_expect_tx(fb, b_bytes);
                             else tcg::mbar_arrive(fb);
-                            if (!(args.dbg & 2))
+                            if (!(dbg & 2))
                                 tcg::tma_load_2d(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK, w.n_tile * BN);
                         }
                     } else {
                         // WGRAD: one pixel box (image group, row tile, col tile) per k-iteration
                         const int pix = args.kmma * 16;
                         const int nblk = (BN + 63) / 64;
-                        if (args.dbg & 3) {   // experiments: no copies
+                        if (dbg & 3) {   // experiments: no copies
                             tcg::mbar_arrive(fb);
                             continue;
                         }
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     tcg::mbar_wait(&full_bar[st], ph);
                     tcg::tc_fence_after();
-                    if (args.trace && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[256 + g] = clock64();
+                    if (trace_on && blockIdx.x == 0 && g < 256 && lane == 0) args.trace[256 + g] = clock64();
                     const uint32_t sa = tcg::smem_u32(smem + (size_t)st * L.stage_bytes);
                     const uint32_t sb = sa + L.a_bytes;
                     uint64_t* eb = &empty_bar[st];
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         const uint64_t dbb = tcg::make_smem_desc(sb, pix_bytes, 1024, 2);
                         for (int j = 0; j < w.q0; ++j) {
                             const uint64_t da = tcg::make_smem_desc(sa + (uint32_t)j * 2u * pix_bytes, pix_bytes, 1024, 2);
-                            for (int k = 0; k < args.kmma && !(args.dbg & 4); ++k)
+                            for (int k = 0; k < args.kmma && !(dbg & 4); ++k)
                                 tcg::umma_bf16(tmem_d + (uint32_t)(j * BN), da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128),
                                                idesc, (uint32_t)((i | k) != 0));
                         }
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t bk = (MODE == TC_MODE_GEMM) ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
-                            if ((args.dbg & 4) || k >= ksteps) continue;
+                            if ((dbg & 4) || k >= ksteps) continue;
                             if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                             else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                         }
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 ++t;
                 tcg::mbar_wait_relaxed(&tmem_full_bar[acc], use & 1u);
                 tcg::tc_fence_after();
-                if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t < 16) args.trace[512 + 2 * t] = clock64();
+                if (trace_on && blockIdx.x == 0 && threadIdx.x == 64 && t < 16) args.trace[512 + 2 * t] = clock64();
             }
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
             // row -> output coordinates
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     // the tap's plane of the output is selected through tap_bcol[] (set by the host)
                     row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[w.wg_tap];
                 }
-                if (!row_ok || (args.dbg & 8)) continue;
+                if (!row_ok || (dbg & 8)) continue;
                 if (args.out_kind == TC_OUT_F32_ATOMIC && !have) continue;
                 if (args.out_kind == TC_OUT_BF16 && args.o_sc == 1 && col0 + cb + 16 <= args.Nout) {
                     // NHWC bf16: 16 consecutive channels of one pixel = 32 contiguous bytes
@@ -459,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 if constexpr (pair) tcg::mbar_arrive_cluster(tcg::smem_u32(&tmem_empty_bar[acc]) & 0xFEFFFFFFu);
                 else tcg::mbar_arrive(&tmem_empty_bar[acc]);
             }
-            if (args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t_done <= 16 && t_done > 0)
+            if (trace_on && blockIdx.x == 0 && threadIdx.x == 64 && t_done <= 16 && t_done > 0)
                 args.trace[512 + 2 * (t_done - 1) + 1] = clock64();
         }
     }

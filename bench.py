@@ -49,6 +49,10 @@ MODEL = dict(depth=28, width=10, batch=128, hw=32, classes=100, lr=0.1, momentum
 TRAIN_GFLOP_PER_IMAGE = 31.459
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, round 1 final)
+TC_DRAM_BYTES_PER_STEP = 3107299328 + 559083264
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     try:
@@ -326,7 +330,10 @@ def main():
             achieved = conv_flops / (tc_us * 1e-6) / 1e12
             roof = {"bound": "tensor", "kernel": "tc_kernel<CONV|WGRAD> (tcgen05 implicit GEMM)", "achieved": achieved,
                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                    "traffic": TC_DRAM_BYTES_PER_STEP if (args.depth, args.width) == (28, 10) else None,
+                    "traffic_source": "ncu dram__bytes_read+write summed over the step's tc_kernel launches "
+                                      "(profiles/r01_final_tc_dram.csv), per step like `achieved`",
+                    "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                     "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3}
     barrier()
 

@@ -49,15 +49,15 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     if ((g.HW & 3) == 0 && (((uintptr_t)x | (GRAD ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0) {
         const int64_t hw4 = g.HW >> 2;
         const int64_t total = (n1 - n0) * hw4;
-        for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-            int64_t n = n0 + i / hw4, j = i % hw4;
-            int64_t off = ((n * g.C + c) * g.HW) + (j << 2);
-            float4 v = *(const float4*)(x + off);
+        // four independent 128-bit loads (per operand) in flight per thread: the one-load-per-trip version ran at half the
+        // HBM bandwidth (profiles/r01_final_timeline.txt)
+        constexpr int U = 4;
+        auto accumulate = [&](const float4& v, const float4& q0) {
+            float4 q = q0;
             float a = v.x - K, b = v.y - K, cc = v.z - K, d = v.w - K;
             s1 += (a + b) + (cc + d);
             s2 += (a * a + b * b) + (cc * cc + d * d);
             if (GRAD) {
-                float4 q = *(const float4*)(dy + off);
                 if (MASK) {
                     q.x = fmaf(v.x - fm, fa, fb) > 0.f ? q.x : 0.f;
                     q.y = fmaf(v.y - fm, fa, fb) > 0.f ? q.y : 0.f;
@@ -67,6 +67,27 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
                 sd += (q.x + q.y) + (q.z + q.w);
                 sdx += (q.x * a + q.y * b) + (q.z * cc + q.w * d);
             }
+        };
+        int64_t i = threadIdx.x;
+        for (; i + (U - 1) * (int64_t)blockDim.x < total; i += U * (int64_t)blockDim.x) {
+            float4 v[U], q[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t iu = i + u * (int64_t)blockDim.x;
+                const int64_t n = n0 + iu / hw4, j = iu % hw4;
+                const int64_t off = ((n * g.C + c) * g.HW) + (j << 2);
+                v[u] = *(const float4*)(x + off);
+                q[u] = GRAD ? *(const float4*)(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) accumulate(v[u], q[u]);
+        }
+        for (; i < total; i += blockDim.x) {
+            const int64_t n = n0 + i / hw4, j = i % hw4;
+            const int64_t off = ((n * g.C + c) * g.HW) + (j << 2);
+            const float4 v = *(const float4*)(x + off);
+            const float4 q = GRAD ? *(const float4*)(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            accumulate(v, q);
         }
     } else {
         const int64_t total = (n1 - n0) * g.HW;
@@ -228,7 +249,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 // tensor-core convolutions) into the apply pass: x is read once, and per element 4 B (fp32 result, when anybody reads it)
 // + 2 B (bf16 copy) are written, instead of 22 B for apply + relu + staging as three kernels.  The arithmetic is the
 // same as bn_apply_kernel / relu_kernel / nchw_to_nhwc_bf16_kernel, so results are bit-identical.
-// Tile: 64 channels x 32 pixels of one image; grid (ceil(HW/32), ceil(Cp/64), N), 256 threads.
+// Tile: 64 channels x 32 pixels of one image; a block walks BN_SUBS consecutive pixel tiles and has the loads of the next one
+// in flight while it transposes and stores the current one.  grid (ceil(HW/(32*BN_SUBS)), ceil(Cp/64), N), 256 threads.
+static constexpr int BN_SUBS = 1;   // (4 was measured: no gain forward, slower backward)
 template <int MODE, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ coef, float* __restrict__ out,
@@ -236,40 +259,73 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
                                                              const float* __restrict__ fcoef = nullptr) {
     __shared__ float tile[64][33];
     const int n = blockIdx.z;
-    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int c0 = blockIdx.y * 64;
     const int HW = (int)g.HW, C = (int)g.C;
     const int64_t img = (int64_t)n * C * HW;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    // per-channel coefficients of this thread's 8 channels
+    float cm[8], ca[8], cb[8], cc[8], fm[8], fa[8], fb[8];
 #pragma unroll
-    for (int j = 0; j < 64; j += 8) {
-        const int c = c0 + ty + j, hw = hw0 + tx;
-        float r = 0.f;
-        if (c < C && hw < HW) {
-            const int64_t i = img + (int64_t)c * HW + hw;
-            const float xv = x[i];
-            const float v = xv - coef[c];
-            if (MODE == 0) {
-                r = fmaf(v, coef[C + c], coef[2 * C + c]);
-                if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
-            } else {
-                float q = dy[i];
-                if (RELU) q = fmaf(xv - fcoef[c], fcoef[C + c], fcoef[2 * C + c]) > 0.f ? q : 0.f;
-                r = fmaf(q, coef[C + c], fmaf(v, coef[2 * C + c], coef[3 * C + c]));
-            }
-            if (out) out[i] = r;
-        }
-        tile[ty + j][tx] = r;
+    for (int j = 0; j < 8; ++j) {
+        const int c = min(c0 + ty + j * 8, C - 1);
+        cm[j] = coef[c]; ca[j] = coef[C + c]; cb[j] = coef[2 * C + c];
+        cc[j] = MODE == 1 ? coef[3 * C + c] : 0.f;
+        if (MODE == 1 && RELU) { fm[j] = fcoef[c]; fa[j] = fcoef[C + c]; fb[j] = fcoef[2 * C + c]; }
+        else { fm[j] = fa[j] = fb[j] = 0.f; }
     }
-    if (!staged) return;
-    __syncthreads();
-    __nv_bfloat16* dst = staged + (int64_t)n * HW * Cp;
+    float xv[8], qv[8], xn[8], qn[8];
+    auto load = [&](int hw0, float (&xr)[8], float (&qr)[8]) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        const int hw = hw0 + ty + j;
-        const int c = c0 + tx * 2;
-        if (hw < HW && c < Cp) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(tile[tx * 2][ty + j], tile[tx * 2 + 1][ty + j]);
-            *(__nv_bfloat162*)(dst + (int64_t)hw * Cp + c) = v;
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + ty + j * 8, hw = hw0 + tx;
+            const bool ok = c < C && hw < HW;
+            const int64_t i = img + (int64_t)c * HW + hw;
+            xr[j] = ok ? x[i] : 0.f;
+            qr[j] = (MODE == 1 && ok) ? dy[i] : 0.f;
+        }
+    };
+    const int first = blockIdx.x * BN_SUBS;
+    load(first * 32, xv, qv);
+    __nv_bfloat16* dst = staged ? staged + (int64_t)n * HW * Cp : nullptr;
+    for (int sub = 0; sub < BN_SUBS; ++sub) {
+        const int hw0 = (first + sub) * 32;
+        if (hw0 >= HW) break;
+        const bool more = sub + 1 < BN_SUBS && hw0 + 32 < HW;
+        if (more) load(hw0 + 32, xn, qn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + ty + j * 8, hw = hw0 + tx;
+            float r = 0.f;
+            if (c < C && hw < HW) {
+                const float v = xv[j] - cm[j];
+                if (MODE == 0) {
+                    r = fmaf(v, ca[j], cb[j]);
+                    if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
+                } else {
+                    float q = qv[j];
+                    if (RELU) q = fmaf(xv[j] - fm[j], fa[j], fb[j]) > 0.f ? q : 0.f;
+                    r = fmaf(q, ca[j], fmaf(v, cb[j], cc[j]));
+                }
+                if (out) out[img + (int64_t)c * HW + hw] = r;
+            }
+            tile[ty + j * 8][tx] = r;
+        }
+        if (staged) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const int hw = hw0 + ty + j;
+                const int c = c0 + tx * 2;
+                if (hw < HW && c < Cp) {
+                    __nv_bfloat162 v = __floats2bfloat162_rn(tile[tx * 2][ty + j], tile[tx * 2 + 1][ty + j]);
+                    *(__nv_bfloat162*)(dst + (int64_t)hw * Cp + c) = v;
+                }
+            }
+            __syncthreads();   // the tile is rewritten by the next pixel tile
+        }
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { xv[j] = xn[j]; qv[j] = qn[j]; }
         }
     }
 }
@@ -281,7 +337,7 @@ template <int MODE>
 static void bn_apply_tiled(const float* x, const float* dy, const float* coef, float* fp32, void* staged, bool relu,
                            const float* fcoef, const BnGeom& g, cudaStream_t s) {
     const int Cp = (int)((g.C + 7) / 8 * 8);
-    dim3 grid((unsigned)ceil_div(g.HW, 32), (unsigned)ceil_div(Cp, 64), (unsigned)g.N);
+    dim3 grid((unsigned)ceil_div(g.HW, 32 * BN_SUBS), (unsigned)ceil_div(Cp, 64), (unsigned)g.N);
     if (relu) bn_apply_stage_kernel<MODE, true><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
     else bn_apply_stage_kernel<MODE, false><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
     DB_LAUNCH_CHECK();

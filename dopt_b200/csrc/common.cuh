@@ -78,6 +78,17 @@ size_t filter_pack_bytes(const FilterPack& f);
 void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_bytes);
 void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s);
 
+// one row of a batched full reduction (msum.cu): *out = sum_i a[i] * b[i]  (b == nullptr: sum_i a[i])
+struct MsumRow {
+    const float* a;
+    const float* b;
+    float* out;
+    int64_t n;
+    int64_t chunk0;   // filled by msum_layout
+};
+int64_t msum_layout(MsumRow* rows, int n);   // returns the number of partials (floats of scratch)
+void msum_launch(const MsumRow* dev_rows, int n, int64_t chunks, float* partial, cudaStream_t s);
+
 struct Absorb {
     bool relu = false;          // apply relu to the result
     float* redirect = nullptr;  // write the fp32 result here instead of the kernel's own output (the relu node's buffer)

@@ -64,6 +64,8 @@ struct Node {
     int absorb_relu = -1;       // producer: relu node whose buffer receives relu(result)
     int absorb_stage = -1;      // producer: stage whose NHWC bf16 buffer it also writes
     bool absorb_skip = false;   // producer: its fp32 result (or the relu output it writes instead) has no reader left
+    bool msum = false;          // full `sum` run as a row of a batched reduction (msum.cu)
+    int msum_a = -1, msum_b = -1;   // operands: sum_i a[i]*b[i] (b = -1: plain sum)
     int gate_from = -1;         // batchNormGrad: batchNormTrain node whose relu gates the incoming gradient (reluGrad absorbed)
     int in_override[DOPT_B200_MAX_INPUTS] = {-1, -1, -1, -1, -1, -1, -1, -1};   // read this node instead of deps[k]
     // runtime
@@ -84,7 +86,7 @@ struct Region {
     std::vector<int> out_nodes;                       // region nodes whose value is needed outside
 };
 
-enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6 };
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6, ITEM_MSUM = 7 };
 struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
@@ -132,6 +134,15 @@ struct dopt_b200_plan_s {
     std::vector<void*> pack_bufs;
     int pack_tiles = 0;
     size_t pack_smem = 0;
+    // batched full reductions: one (partial, finish) launch pair per group of `sum` nodes that were ready together
+    struct MsumGroup {
+        std::vector<int> nodes;
+        std::vector<db::MsumRow> rows;
+        db::MsumRow* dev = nullptr;
+        float* partial = nullptr;
+        int64_t chunks = 0;
+    };
+    std::vector<MsumGroup> msums;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     int64_t device_bytes = 0;
@@ -161,6 +172,10 @@ struct dopt_b200_plan_s {
         for (auto& st : stages)
             if (st.buf) cudaFree(st.buf);
         for (void* b : pack_bufs) cudaFree(b);
+        for (auto& m : msums) {
+            if (m.dev) cudaFree(m.dev);
+            if (m.partial) cudaFree(m.partial);
+        }
         if (packs_dev) cudaFree(packs_dev);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
@@ -646,7 +661,7 @@ static void schedule(Plan& p) {
             continue;
         }
         bool scalar_pw = n.pw_op >= 0 && (n.pw_mode != dbk::B_TENSOR);
-        int kind = n.bucket >= 0 ? ITEM_COPY : (scalar_pw ? ITEM_PW_SCALAR : ITEM_KERNEL);
+        int kind = n.bucket >= 0 ? ITEM_COPY : (n.msum ? ITEM_MSUM : (scalar_pw ? ITEM_PW_SCALAR : ITEM_KERNEL));
         items.push_back({kind, (int)i, false});
         item_key.push_back(key_of((int)i));
         item_of_node[i] = (int)items.size() - 1;
@@ -722,6 +737,13 @@ static void schedule(Plan& p) {
                 if (via) items[item].join_comm = true;
             }
         if (N[i].gate_from >= 0) add_edge(item_of_node[N[i].gate_from], item);
+        if (N[i].msum)
+            for (int d : {N[i].msum_a, N[i].msum_b})
+                if (d >= 0) {
+                    bool via = false;
+                    add_edge(producer_item(d, &via), item);
+                    if (via) items[item].join_comm = true;
+                }
     }
     for (size_t b = 0; b < p.buckets.size(); ++b)
         for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
@@ -755,9 +777,11 @@ static void schedule(Plan& p) {
     // rows of ONE multi-tensor launch
     std::map<std::string, std::set<int>> ready_fused;
     std::vector<char> consumed(items.size(), 0);
+    std::set<int> ready_msum;
     auto make_ready = [&](int k) {
         ready.push({item_key[k], k});
         if (items[k].kind == ITEM_FUSED) ready_fused[launch_key[items[k].id]].insert(k);
+        if (items[k].kind == ITEM_MSUM) ready_msum.insert(k);
     };
     for (size_t k = 0; k < items.size(); ++k)
         if (indeg[k] == 0) make_ready((int)k);
@@ -789,6 +813,21 @@ static void schedule(Plan& p) {
                 issued.push_back(o);
             }
             same.clear();
+        }
+        if (items[k].kind == ITEM_MSUM) {
+            // every full reduction that is ready now goes into the same pair of launches
+            Plan::MsumGroup grp;
+            ready_msum.erase(k);
+            grp.nodes.push_back(items[k].id);
+            for (int o : ready_msum) {
+                grp.nodes.push_back(items[o].id);
+                items[k].join_comm = items[k].join_comm || items[o].join_comm;
+                consumed[o] = 1;
+                issued.push_back(o);
+            }
+            ready_msum.clear();
+            items[k].id = (int)p.msums.size();
+            p.msums.push_back(std::move(grp));
         }
         p.order.push_back(items[k]);
         for (int q : issued) {
@@ -857,6 +896,43 @@ static void form_buckets(Plan& p) {
                 N[m].region = (int)p.regions.size();
                 p.regions.push_back(R);
             }
+}
+
+// ---- batched full reductions ---------------------------------------------------------------------------------------------
+// Every float32 `sum` over all axes becomes a row of a batched reduction; when its operand is a stand-alone product `a*b`
+// that nothing else reads, the product is folded in (the weight-decay terms sum(W*W)).
+static void mark_msums(Plan& p) {
+    auto& N = p.nodes;
+    std::vector<int> n_readers(N.size(), 0);
+    for (size_t u = 0; u < N.size(); ++u) {
+        if (!N[u].needed) continue;
+        for (int d : effective_deps(N[u])) ++n_readers[root_of(p, d)];
+    }
+    std::set<int> out_roots;
+    for (int o : p.outputs) out_roots.insert(root_of(p, o));
+    for (size_t i = 0; i < N.size(); ++i) {
+        Node& S = N[i];
+        if (!S.needed || S.alias_of >= 0 || S.type != "sum" || !S.kernel || S.deps.size() != 1) continue;
+        if (S.op.output.dtype != DOPT_B200_FLOAT32 || volume(S.op.output) != 1) continue;
+        const dopt_b200_tensor& in = S.op.inputs[0];
+        if (in.dtype != DOPT_B200_FLOAT32 || S.op.n_axes != in.rank || volume(in) < 1) continue;
+        S.msum = true;
+        S.msum_a = S.deps[0];
+        int64_t off = 0;
+        const int m = root_of(p, S.deps[0], &off);
+        Node& M = N[m];
+        if (off == 0 && M.type == "mul" && M.pw_op >= 0 && M.pw_mode == dbk::B_TENSOR && !M.pw_unary && M.region < 0 &&
+            M.alias_of < 0 && n_readers[m] == 1 && !out_roots.count(m) && M.bytes == N[S.deps[0]].bytes) {
+            S.msum_a = M.eff_in[0];
+            S.msum_b = M.eff_in[1];
+            M.needed = false;   // never materialised
+            if (M.buf) {
+                cudaFree(M.buf);
+                M.buf = nullptr;
+                p.device_bytes -= M.bytes;
+            }
+        }
+    }
 }
 
 // ---- pass "absorb": relu and NHWC staging folded into the batch-norm apply pass ----------------------------------------
@@ -1065,6 +1141,7 @@ static void build(Plan& p) {
                 p.stages[it->second].users.push_back({(int)i, k});
             }
         }
+        if (!getenv("DOPT_B200_NO_MSUM")) mark_msums(p);
         if (!getenv("DOPT_B200_NO_FILTER_STAGE"))
             for (size_t i = 0; i < N.size(); ++i) {
                 Node& n = N[i];
@@ -1106,7 +1183,7 @@ static void build(Plan& p) {
     p.direct_out.assign(p.outputs.size(), 0);
     if (getenv("DOPT_B200_PLAN_DUMP")) {
         // one line per scheduled item: kind, op type, output volume, the op types of its operands
-        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack"};
+        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack", "msum"};
         for (const Item& it : p.order) {
             if (it.kind == ITEM_KERNEL || it.kind == ITEM_PW_SCALAR || it.kind == ITEM_COPY) {
                 const Node& n = N[it.id];
@@ -1231,6 +1308,10 @@ static void run_items(Plan& p, cudaStream_t s) {
                 comm_pending = false;
             }
             label = "allreduceBucket";
+        } else if (it.kind == ITEM_MSUM) {
+            auto& m = p.msums[it.id];
+            msum_launch(m.dev, (int)m.rows.size(), m.chunks, m.partial, s);
+            label = "sum";
         } else if (it.kind == ITEM_PACK) {
             filter_pack_launch(p.packs_dev, (int)p.packs.size(), p.pack_tiles, p.pack_smem, s);
             label = "packFilters";
@@ -1344,6 +1425,23 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             n.ptr = (char*)N[r].ptr + off;
         }
         bind_fused(p, rets);
+        for (auto& m : p.msums) {
+            m.rows.resize(m.nodes.size());
+            for (size_t i = 0; i < m.nodes.size(); ++i) {
+                const Node& S = N[m.nodes[i]];
+                MsumRow& r = m.rows[i];
+                r.a = (const float*)N[S.msum_a].ptr;
+                r.b = S.msum_b >= 0 ? (const float*)N[S.msum_b].ptr : nullptr;
+                r.out = (float*)S.ptr;
+                r.n = volume(S.op.inputs[0]);
+            }
+            m.chunks = msum_layout(m.rows.data(), (int)m.rows.size());
+            if (!m.dev) {
+                DB_CUDA(cudaMalloc(&m.dev, m.rows.size() * sizeof(MsumRow)));
+                DB_CUDA(cudaMalloc(&m.partial, (size_t)m.chunks * sizeof(float)));
+            }
+            DB_CUDA(cudaMemcpy(m.dev, m.rows.data(), m.rows.size() * sizeof(MsumRow), cudaMemcpyHostToDevice));
+        }
         if (!p.packs.empty()) {
             for (size_t i = 0; i < p.packs.size(); ++i) p.packs[i].w = (const float*)N[p.pack_users[i].second].ptr;
             DB_CUDA(cudaMemcpy(p.packs_dev, p.packs.data(), p.packs.size() * sizeof(FilterPack), cudaMemcpyHostToDevice));

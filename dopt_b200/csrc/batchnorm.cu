@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 // per-channel coefficients: y = x*a + b (train), and the running-statistics update written straight into the packed tail
 __global__ void bn_train_finalize(const float* __restrict__ part, const float* __restrict__ x,
                                   const float* __restrict__ scale, const float* __restrict__ bias,
-                                  const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                  const float* rmean, const float* rvar,   /* may alias mean_out2 / var_out2 */
                                   float* __restrict__ coef, float* __restrict__ new_mean, float* __restrict__ new_var,
-                                  BnGeom g, int splits, double factor) {
+                                  BnGeom g, int splits, double factor, float* mean_out2, float* var_out2) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.C) return;
     double s1 = 0, s2 = 0;
@@ -144,8 +144,13 @@ __global__ void bn_train_finalize(const float* __restrict__ part, const float* _
     coef[g.C + c] = (float)((double)scale[c] * istd);
     coef[2 * g.C + c] = bias[c];
     double unbiased = M > 1 ? var * M / (M - 1) : var;
-    new_mean[c] = (float)((double)rmean[c] * (1.0 - factor) + mean * factor);
-    new_var[c] = (float)((double)rvar[c] * (1.0 - factor) + unbiased * factor);
+    const float nm = (float)((double)rmean[c] * (1.0 - factor) + mean * factor);
+    const float nv = (float)((double)rvar[c] * (1.0 - factor) + unbiased * factor);
+    new_mean[c] = nm;
+    new_var[c] = nv;
+    // second copy for the caller's buffers (may be the very rmean / rvar this thread just read: read-before-write per channel)
+    if (mean_out2) mean_out2[c] = nm;
+    if (var_out2) var_out2[c] = nv;
 }
 
 // grad: dx = dy*a + x*b + k  with  a = scale*istd, b = -scale*istd^3*dsx_c/M ... expressed through xhat below
@@ -373,6 +378,13 @@ struct BnTrainKernel : Kernel {
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
     void set_absorbed(const Absorb& a) override { ab = a; }
     const void* aux_ptr() const override { return coef_dev; }
+    float* mean_out2 = nullptr;
+    float* var_out2 = nullptr;
+    bool set_stat_outputs(float* m, float* v) override {
+        mean_out2 = m;
+        var_out2 = v;
+        return true;
+    }
     BnTrainKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 5, "batchNormTrain: deps are [x, scale, bias, mean, var]");
         g = geom_of(d.inputs[0]);
@@ -392,7 +404,8 @@ struct BnTrainKernel : Kernel {
         DB_LAUNCH_CHECK();
         bn_train_finalize<<<(unsigned)ceil_div(g.C, 128), 128, 0, s>>>(part, x, (const float*)in[1], (const float*)in[2],
                                                                        (const float*)in[3], (const float*)in[4], coef,
-                                                                       y + V, y + V + g.C, g, splits, factor);
+                                                                       y + V, y + V + g.C, g, splits, factor, mean_out2,
+                                                                       var_out2);
         DB_LAUNCH_CHECK();
         coef_dev = coef;
         if (ab.relu || ab.staged || ab.skip_fp32 || ab.redirect) {

@@ -118,6 +118,9 @@ struct Kernel {
     // is recomputed from x and forward->aux_ptr() (its per-channel coefficients), so neither reluGrad nor the stored relu
     // output is needed
     virtual void set_gate_source(const Kernel* /*forward*/) {}
+    // batchNormTrain: also write the running statistics (packed tail of the result) straight to these buffers -- the plan
+    // passes the caller's return buffers (dopt.online feeds them back as the new `mean` / `var`) and skips the copies
+    virtual bool set_stat_outputs(float* /*new_mean*/, float* /*new_var*/) { return false; }
     virtual const void* aux_ptr() const { return nullptr; }
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use

@@ -1266,6 +1266,58 @@ static void bind_fused(Plan& p, void* const* rets) {
     }
 }
 
+// batchNormTrain's running statistics (the packed tail [newMean | newVar] of its result) are plan outputs that dopt.online
+// feeds back into the `mean` / `var` variables (nnet/layers/batchnorm.d:140-154): 2 x 25 tiny device copies per WRN step.
+// Where it is safe the kernel writes them to the return buffers itself and the copy is dropped.
+static void bind_bn_stats(Plan& p, void* const* rets) {
+    auto& N = p.nodes;
+    if (!(p.flags & DOPT_B200_PLAN_FUSE) || getenv("DOPT_B200_NO_BN_DIRECT")) return;
+    std::map<int, std::pair<float*, float*>> want;   // batchNormTrain node -> (mean buffer, var buffer)
+    std::vector<int> which(p.outputs.size(), -1);
+    for (size_t i = 0; i < p.outputs.size(); ++i) {
+        const Node& o = N[p.outputs[i]];
+        if (!rets[i] || o.alias_of < 0 || p.direct_out[i]) continue;
+        int64_t off = 0;
+        const int b = root_of(p, p.outputs[i], &off);
+        const Node& B = N[b];
+        if (B.type != "batchNormTrain" || !B.kernel || B.deps.size() != 5) continue;
+        const int64_t C = volume(B.op.inputs[1]), V = volume(B.op.inputs[0]);
+        if (o.bytes != C * 4) continue;
+        int slot = off == V * 4 ? 0 : (off == (V + C) * 4 ? 1 : -1);
+        if (slot < 0) continue;
+        // the return buffer must not be something another node of the plan reads (it may be this kernel's own running
+        // mean / var operand: the finalize kernel reads a channel before it writes it)
+        bool safe = true;
+        int dup = 0;
+        for (size_t k = 0; k < p.outputs.size(); ++k)
+            if (rets[k] == rets[i]) ++dup;
+        if (dup != 1) safe = false;
+        for (size_t u = 0; safe && u < N.size(); ++u) {
+            if (!N[u].needed || N[u].type != "variable") continue;
+            const char* vp = (const char*)N[u].ptr;
+            if (!vp || (const char*)rets[i] + o.bytes <= vp || vp + N[u].bytes <= (const char*)rets[i]) continue;
+            // an overlapping variable: every reader must be B itself
+            for (size_t r = 0; safe && r < N.size(); ++r) {
+                if (!N[r].needed || (int)r == b) continue;
+                for (int d : effective_deps(N[r]))
+                    if (root_of(p, d) == (int)u) safe = false;
+            }
+        }
+        if (!safe) continue;
+        auto& w = want[b];
+        (slot == 0 ? w.first : w.second) = (float*)rets[i];
+        which[i] = b;
+    }
+    for (size_t i = 0; i < N.size(); ++i)
+        if (N[i].type == "batchNormTrain" && N[i].kernel) {
+            auto it = want.find((int)i);
+            N[i].kernel->set_stat_outputs(it == want.end() ? nullptr : it->second.first,
+                                          it == want.end() ? nullptr : it->second.second);
+        }
+    for (size_t i = 0; i < p.outputs.size(); ++i)
+        if (which[i] >= 0) p.direct_out[i] = 1;
+}
+
 static void run_items(Plan& p, cudaStream_t s) {
     auto& N = p.nodes;
     bool comm_pending = false;
@@ -1425,6 +1477,7 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             n.ptr = (char*)N[r].ptr + off;
         }
         bind_fused(p, rets);
+        bind_bn_stats(p, rets);
         for (auto& m : p.msums) {
             m.rows.resize(m.nodes.size());
             for (size_t i = 0; i < m.nodes.size(); ++i) {

@@ -24,6 +24,76 @@ struct BnGeom {
     int64_t N, C, HW;
 };
 
+// ---- finalize (per channel), run by the LAST statistics block of a channel ----------------------------------------------
+// Separate finalize launches were 50 tiny kernels per WRN step.  Each statistics block publishes its partial sums, then
+// bumps a per-channel counter; the block that sees splits-1 combines the partials in split order (deterministic) and
+// resets the counter for the next execution.
+struct BnFin {
+    unsigned* counters;                       // [C], zero between launches
+    const float* scale; const float* bias;    // train
+    const float* rmean; const float* rvar;    // train; may alias mean2 / var2
+    float* coef;                              // train [mean | a | b], grad [mean | A | B | C]
+    float* out0; float* out1;                 // train: new mean / var (packed tail); grad: dscale / dbias
+    float* mean2; float* var2;                // train: optional second copy (the caller's return buffers)
+    double factor;
+};
+
+__device__ __forceinline__ void bn_train_finalize_channel(const float* part, const float* x, const BnFin& f, const BnGeom& g,
+                                                          int splits, int c) {
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < splits; ++s) {
+        s1 += __ldcg(part + ((int64_t)s * g.C + c) * 2 + 0);
+        s2 += __ldcg(part + ((int64_t)s * g.C + c) * 2 + 1);
+    }
+    double M = (double)g.N * (double)g.HW;
+    double K = x[(int64_t)c * g.HW];
+    double d = s1 / M;
+    double mean = K + d;
+    double var = s2 / M - d * d;
+    if (var < 0) var = 0;
+    double istd = 1.0 / sqrt(var + kBnEps);
+    f.coef[c] = (float)mean;
+    f.coef[g.C + c] = (float)((double)f.scale[c] * istd);
+    f.coef[2 * g.C + c] = f.bias[c];
+    double unbiased = M > 1 ? var * M / (M - 1) : var;
+    const float nm = (float)((double)f.rmean[c] * (1.0 - f.factor) + mean * f.factor);
+    const float nv = (float)((double)f.rvar[c] * (1.0 - f.factor) + unbiased * f.factor);
+    f.out0[c] = nm;
+    f.out1[c] = nv;
+    // second copy for the caller's buffers (may be the very rmean / rvar just read: read-before-write per channel)
+    if (f.mean2) f.mean2[c] = nm;
+    if (f.var2) f.var2[c] = nv;
+}
+
+// grad: dx = dy*A + (x-mean)*B + Cc
+__device__ __forceinline__ void bn_grad_finalize_channel(const float* part, const float* x, const BnFin& f, const BnGeom& g,
+                                                         int splits, int c) {
+    double s1 = 0, s2 = 0, sd = 0, sdx = 0;
+    for (int s = 0; s < splits; ++s) {
+        const float* p = part + ((int64_t)s * g.C + c) * 4;
+        s1 += __ldcg(p + 0); s2 += __ldcg(p + 1); sd += __ldcg(p + 2); sdx += __ldcg(p + 3);
+    }
+    double M = (double)g.N * (double)g.HW;
+    double K = x[(int64_t)c * g.HW];
+    double d = s1 / M;
+    double mean = K + d;
+    double var = s2 / M - d * d;
+    if (var < 0) var = 0;
+    double istd = 1.0 / sqrt(var + kBnEps);
+    double dbeta = sd;
+    double dgamma = (sdx - d * sd) * istd;   // sum dy*(x-mean)*istd
+    f.out0[c] = (float)dgamma;
+    f.out1[c] = (float)dbeta;
+    // dx = scale*istd * (dy - dbeta/M - xhat*dgamma/M),  xhat = (x-mean)*istd
+    double A = (double)f.scale[c] * istd;
+    double B = -A * istd * dgamma / M;
+    double Cc = -A * dbeta / M;
+    f.coef[c] = (float)mean;
+    f.coef[g.C + c] = (float)A;
+    f.coef[2 * g.C + c] = (float)B;
+    f.coef[3 * g.C + c] = (float)Cc;
+}
+
 // ---- statistics ----------------------------------------------------------------------------------------------------
 // part layout: [split][C][NS] floats.  NS = 2 (train: sum(x-K), sum((x-K)^2)) or 4 (grad: + sum dy, sum dy*(x-K)).
 // MASK (grad only): dy is the gradient w.r.t. relu(y); it is gated by [y > 0] with y recomputed from x and the FORWARD
@@ -32,6 +102,7 @@ struct BnGeom {
 template <bool GRAD, bool MASK = false>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                        float* __restrict__ part, BnGeom g, int splits,
+                                                       const __grid_constant__ BnFin fin,
                                                        const float* __restrict__ fcoef = nullptr) {
     constexpr int NS = GRAD ? 4 : 2;
     float fm = 0.f, fa = 0.f, fb = 0.f;
@@ -113,78 +184,21 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
         if (lane == 0) sm[k][w] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NS) {
-        float v = 0.f;
-        for (int i = 0; i < 8; ++i) v += sm[threadIdx.x][i];
-        part[((int64_t)sp * g.C + c) * NS + threadIdx.x] = v;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < NS; ++k) {
+            float v = 0.f;
+            for (int i = 0; i < 8; ++i) v += sm[k][i];
+            part[((int64_t)sp * g.C + c) * NS + k] = v;
+        }
+        __threadfence();   // the partials are visible before the counter moves
+        const unsigned seen = atomicAdd(&fin.counters[c], 1u);
+        if (seen == (unsigned)splits - 1u) {
+            fin.counters[c] = 0u;
+            __threadfence();
+            if (GRAD) bn_grad_finalize_channel(part, x, fin, g, splits, c);
+            else bn_train_finalize_channel(part, x, fin, g, splits, c);
+        }
     }
-}
-
-// per-channel coefficients: y = x*a + b (train), and the running-statistics update written straight into the packed tail
-__global__ void bn_train_finalize(const float* __restrict__ part, const float* __restrict__ x,
-                                  const float* __restrict__ scale, const float* __restrict__ bias,
-                                  const float* rmean, const float* rvar,   /* may alias mean_out2 / var_out2 */
-                                  float* __restrict__ coef, float* __restrict__ new_mean, float* __restrict__ new_var,
-                                  BnGeom g, int splits, double factor, float* mean_out2, float* var_out2) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.C) return;
-    double s1 = 0, s2 = 0;
-    for (int s = 0; s < splits; ++s) {
-        s1 += part[((int64_t)s * g.C + c) * 2 + 0];
-        s2 += part[((int64_t)s * g.C + c) * 2 + 1];
-    }
-    double M = (double)g.N * (double)g.HW;
-    double K = x[(int64_t)c * g.HW];
-    double d = s1 / M;
-    double mean = K + d;
-    double var = s2 / M - d * d;
-    if (var < 0) var = 0;
-    double istd = 1.0 / sqrt(var + kBnEps);
-    coef[c] = (float)mean;
-    coef[g.C + c] = (float)((double)scale[c] * istd);
-    coef[2 * g.C + c] = bias[c];
-    double unbiased = M > 1 ? var * M / (M - 1) : var;
-    const float nm = (float)((double)rmean[c] * (1.0 - factor) + mean * factor);
-    const float nv = (float)((double)rvar[c] * (1.0 - factor) + unbiased * factor);
-    new_mean[c] = nm;
-    new_var[c] = nv;
-    // second copy for the caller's buffers (may be the very rmean / rvar this thread just read: read-before-write per channel)
-    if (mean_out2) mean_out2[c] = nm;
-    if (var_out2) var_out2[c] = nv;
-}
-
-// grad: dx = dy*a + x*b + k  with  a = scale*istd, b = -scale*istd^3*dsx_c/M ... expressed through xhat below
-__global__ void bn_grad_finalize(const float* __restrict__ part, const float* __restrict__ x,
-                                 const float* __restrict__ scale, float* __restrict__ coef, float* __restrict__ dscale,
-                                 float* __restrict__ dbias, BnGeom g, int splits) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.C) return;
-    double s1 = 0, s2 = 0, sd = 0, sdx = 0;
-    for (int s = 0; s < splits; ++s) {
-        const float* p = part + ((int64_t)s * g.C + c) * 4;
-        s1 += p[0]; s2 += p[1]; sd += p[2]; sdx += p[3];
-    }
-    double M = (double)g.N * (double)g.HW;
-    double K = x[(int64_t)c * g.HW];
-    double d = s1 / M;
-    double mean = K + d;
-    double var = s2 / M - d * d;
-    if (var < 0) var = 0;
-    double istd = 1.0 / sqrt(var + kBnEps);
-    double dbeta = sd;
-    double dgamma = (sdx - d * sd) * istd;   // sum dy*(x-mean)*istd
-    dscale[c] = (float)dgamma;
-    dbias[c] = (float)dbeta;
-    // dx = scale*istd * (dy - dbeta/M - xhat*dgamma/M),  xhat = (x-mean)*istd
-    //    = dy*A + x*B + Cc
-    //    = dy*A + (x-mean)*B + Cc
-    double A = (double)scale[c] * istd;
-    double B = -A * istd * dgamma / M;
-    double Cc = -A * dbeta / M;
-    coef[c] = (float)mean;
-    coef[g.C + c] = (float)A;
-    coef[2 * g.C + c] = (float)B;
-    coef[3 * g.C + c] = (float)Cc;
 }
 
 __global__ void bn_infer_coef(const float* __restrict__ scale, const float* __restrict__ bias,
@@ -380,6 +394,7 @@ struct BnTrainKernel : Kernel {
     const void* aux_ptr() const override { return coef_dev; }
     float* mean_out2 = nullptr;
     float* var_out2 = nullptr;
+    const void* counters_for = nullptr;
     bool set_stat_outputs(float* m, float* v) override {
         mean_out2 = m;
         var_out2 = v;
@@ -398,14 +413,22 @@ struct BnTrainKernel : Kernel {
         const float* x = (const float*)in[0];
         int64_t V = g.N * g.C * g.HW;
         float* y = (float*)out;
-        float* part = (float*)ws.get(((size_t)splits * g.C * 2 + 3 * g.C) * sizeof(float));
+        float* part = (float*)ws.get(((size_t)splits * g.C * 2 + 4 * g.C) * sizeof(float));
         float* coef = part + (size_t)splits * g.C * 2;
-        bn_stats_kernel<false><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, nullptr, part, g, splits);
-        DB_LAUNCH_CHECK();
-        bn_train_finalize<<<(unsigned)ceil_div(g.C, 128), 128, 0, s>>>(part, x, (const float*)in[1], (const float*)in[2],
-                                                                       (const float*)in[3], (const float*)in[4], coef,
-                                                                       y + V, y + V + g.C, g, splits, factor, mean_out2,
-                                                                       var_out2);
+        unsigned* counters = (unsigned*)(coef + 3 * g.C);
+        if (ws.ptr != counters_for) {   // new workspace: counters start at zero and return to zero after every launch
+            DB_CUDA(cudaMemsetAsync(counters, 0, (size_t)g.C * sizeof(unsigned), s));
+            counters_for = ws.ptr;
+        }
+        BnFin fin{};
+        fin.counters = counters;
+        fin.scale = (const float*)in[1]; fin.bias = (const float*)in[2];
+        fin.rmean = (const float*)in[3]; fin.rvar = (const float*)in[4];
+        fin.coef = coef;
+        fin.out0 = y + V; fin.out1 = y + V + g.C;
+        fin.mean2 = mean_out2; fin.var2 = var_out2;
+        fin.factor = factor;
+        bn_stats_kernel<false><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, nullptr, part, g, splits, fin);
         DB_LAUNCH_CHECK();
         coef_dev = coef;
         if (ab.relu || ab.staged || ab.skip_fp32 || ab.redirect) {
@@ -424,6 +447,7 @@ struct BnGradKernel : Kernel {
     Scratch ws;
     Absorb ab;
     const Kernel* fwd = nullptr;   // batchNormTrain kernel whose relu gates dy (plan pass "absorb")
+    const void* counters_for = nullptr;
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
     void set_absorbed(const Absorb& a) override {
         DB_REQUIRE(!a.relu && !a.redirect, "batchNormGrad cannot absorb a relu");
@@ -445,15 +469,22 @@ struct BnGradKernel : Kernel {
         const float* x = (const float*)in[1];
         int64_t V = g.N * g.C * g.HW;
         float* dx = (float*)out;
-        float* part = (float*)ws.get(((size_t)splits * g.C * 4 + 4 * g.C) * sizeof(float));
+        float* part = (float*)ws.get(((size_t)splits * g.C * 4 + 5 * g.C) * sizeof(float));
         float* coef = part + (size_t)splits * g.C * 4;
+        unsigned* counters = (unsigned*)(coef + 4 * g.C);
+        if (ws.ptr != counters_for) {
+            DB_CUDA(cudaMemsetAsync(counters, 0, (size_t)g.C * sizeof(unsigned), s));
+            counters_for = ws.ptr;
+        }
+        BnFin fin{};
+        fin.counters = counters;
+        fin.scale = (const float*)in[2];
+        fin.coef = coef;
+        fin.out0 = dx + V; fin.out1 = dx + V + g.C;
         const float* fcoef = fwd ? (const float*)fwd->aux_ptr() : nullptr;
         DB_REQUIRE(!fwd || fcoef, "batchNormGrad: the forward pass it takes its relu gate from has not run");
-        if (fcoef) bn_stats_kernel<true, true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fcoef);
-        else bn_stats_kernel<true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits);
-        DB_LAUNCH_CHECK();
-        bn_grad_finalize<<<(unsigned)ceil_div(g.C, 128), 128, 0, s>>>(part, x, (const float*)in[2], coef, dx + V,
-                                                                      dx + V + g.C, g, splits);
+        if (fcoef) bn_stats_kernel<true, true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fin, fcoef);
+        else bn_stats_kernel<true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fin);
         DB_LAUNCH_CHECK();
         if (ab.staged || ab.skip_fp32) {
             bn_apply_tiled<1>(x, dy, coef, ab.skip_fp32 ? nullptr : dx, ab.staged, fcoef != nullptr, fcoef, g, s);

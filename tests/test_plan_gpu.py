@@ -250,6 +250,34 @@ def test_bn_relu_staging_absorption_is_bit_exact(monkeypatch):
         assert float(np.abs(a - b).max()) <= 1e-5 * max(float(np.abs(a).max()), 1e-3)
 
 
+@pytest.mark.parametrize("knob", ["DOPT_B200_NO_MSUM", "DOPT_B200_NO_FILTER_STAGE", "DOPT_B200_NO_BN_DIRECT", "DOPT_B200_NO_GATE",
+                                  "DOPT_B200_NO_MERGE", "DOPT_B200_NO_SINGLES", "DOPT_B200_NO_BATCH"])
+def test_plan_passes_do_not_change_results(monkeypatch, knob):
+    # every lowering pass of the plan compiler can be switched off with an environment knob (read when the plan is built):
+    # batched reductions, filter staging, direct BN statistics, the relu gate in batchNormGrad, region merging, single-node
+    # regions, launch batching.  Forward results must be identical bit for bit with and without each of them; the loss
+    # (whose weight-decay sums change summation order under NO_MSUM) and the parameters within fp32 rounding.
+    def run(off):
+        if off:
+            monkeypatch.setenv(knob, "1")
+        else:
+            monkeypatch.delenv(knob, raising=False)
+        H.reset()
+        H.set_math(db.MATH_BF16)
+        H.set_plan_flags(FUSE | GRAPH)
+        loss, extra, net, feed = _wrn(10, 4, 8, 16, 10)()
+        upd = H.Updater(H.SGD, [loss] + extra, network=net, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+        outs = [upd.step(feed(s)) for s in range(2)]
+        return outs, [p.get().copy() for p in net.params]
+    o0, p0 = run(True)
+    o1, p1 = run(False)
+    assert np.array_equal(o0[0][1], o1[0][1])                                  # step-0 predictions
+    assert abs(float(o0[0][0]) - float(o1[0][0])) <= 2e-6 * abs(float(o0[0][0]))
+    assert abs(float(o0[1][0]) - float(o1[1][0])) <= 1e-5 * abs(float(o0[1][0]))
+    for a, b in zip(p0, p1):
+        assert float(np.abs(a - b).max()) <= 1e-5 * max(float(np.abs(a).max()), 1e-3)
+
+
 def test_wrn_strided_stem_sins_like_amsgrad():
     # sins10.d uses strides [2,2,2]; BASELINE configs[4] trains it with AMSGrad
     _train_compare(_wrn(10, 2, 4, 24, 10, strides=(2, 2, 2)), 2, db.MATH_FP32, 5e-4, 1e-2, kind=H.AMSGRAD,

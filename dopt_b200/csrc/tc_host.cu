@@ -373,6 +373,13 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
                 instr_configured = true;
             }
             DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, true>, tmA, tmB, a));
+        } else if (a.kbox == 2) {
+            static bool k2_configured = false;
+            if (!k2_configured) {
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                k2_configured = true;
+            }
+            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 2>, tmA, tmB, a));
         } else {
             DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
         }
@@ -397,6 +404,15 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         count_launch();
     }
     if (g_tc_prof) DB_CUDA(cudaEventRecord(g_tc_ev[g_tc_ev_used++].second, s));
+}
+
+static int conv_kbox() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DOPT_B200_KBOX");
+        v = e ? (atoi(e) == 2 ? 2 : 1) : 2;
+    }
+    return v;
 }
 
 // Persistent CTAs come in two shapes (measured on the WRN layers, profiles/r01c_conv_bisect.md):
@@ -672,6 +688,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_off = 0;
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
+    a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
@@ -764,6 +781,7 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sn = (long long)g.C * g.H * g.W; a.o_sc = (long long)g.H * g.W;
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
+            a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }

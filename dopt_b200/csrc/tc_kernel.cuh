@@ -59,6 +59,7 @@ struct TcArgs {
     int wg_tap;         // unused (tap comes from the tile index)
     int pix_tiles;      // number of pixel boxes (the reduction dimension), split over `splits`
     int kmma;           // MMAs per stage (box pixels / 16)
+    int kbox;           // CONV pair tiles: (tap, channel block) boxes per pipeline stage (1, or 2 = tc_kernel<.., KBOX = 2>)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
 };
 
@@ -74,8 +75,9 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
         L.a_bytes = TC_BM * 128u;
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * 64u * 128u;           // [n-block][64 k rows][64 n]
     } else {
-        L.a_bytes = TC_BM * 128u;
-        L.b_bytes = (uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u;
+        const uint32_t kb = a.kbox == 2 ? 2u : 1u;
+        L.a_bytes = kb * TC_BM * 128u;
+        L.b_bytes = kb * (((uint32_t)(a.pair ? a.BN / 2 : a.BN) * 128u + 1023u) & ~1023u);
     }
     L.b_bytes = (L.b_bytes + 1023u) & ~1023u;
     L.stage_bytes = L.a_bytes + L.b_bytes;
@@ -94,7 +96,9 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
 // one-tile-per-CTA version those fixed costs and the exposed epilogue were 60 % of the kernel time).
 // INSTR: the experiment hooks (TcArgs::trace / dbg) are compiled in; the production instantiations leave them out -- the
 // single-warp issue loops are sensitive to every extra instruction.
-template <int MODE, bool PAIR = false, bool INSTR = false>
+// KBOX = 2 (CONV pair tiles only): a pipeline stage holds two consecutive (tap, channel block) boxes, so the barrier round
+// trip and the fixed part of the issue loops are paid once per 8 MMAs.
+template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1>
 __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args_) {
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
         w.split = rest % args.splits;
         w.n_tile = rest / args.splits;
         w.m_tile = cm * csize + (int)crank;
-        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : args.k_iters;
+        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + KBOX - 1) / KBOX;
         int per = (total + args.splits - 1) / args.splits;
         w.it_begin = w.split * per;
         w.n_iters = max(0, min(total, w.it_begin + per) - w.it_begin);
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 // CONV: it -> (tap t, channel block cb); WGRAD: it -> pixel box (ng, tp, tq)
                 int t = 0, cb = 0, tq = 0, tp = 0, ng = 0;
                 if (MODE == TC_MODE_CONV) {
-                    t = w.it_begin / args.c_iters;
-                    cb = w.it_begin - t * args.c_iters;
+                    t = (w.it_begin * KBOX) / args.c_iters;
+                    cb = w.it_begin * KBOX - t * args.c_iters;
                 } else if (MODE == TC_MODE_WGRAD) {
                     tq = w.it_begin % args.tiles_q;
                     int t2 = w.it_begin / args.tiles_q;
@@ -227,8 +231,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     uint64_t* fb = &full_bar[st];
                     const int t_now = t, cb_now = cb, tq_now = tq, tp_now = tp, ng_now = ng;
                     if (++st == stages) { st = 0; ph ^= 1u; }
+                    int t1 = t_now, cb1 = cb_now;   // KBOX == 2: second box of the stage
                     if (MODE == TC_MODE_CONV) {
                         if (++cb == args.c_iters) { cb = 0; ++t; }
+                        if (KBOX == 2) {
+                            t1 = t; cb1 = cb;
+                            if (++cb == args.c_iters) { cb = 0; ++t; }
+                        }
                     } else if (MODE == TC_MODE_WGRAD) {
                         if (++tq == args.tiles_q) {
                             tq = 0;
@@ -247,14 +256,21 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                         // are credited to the leader's barrier, which the leader arms for the pair
                         const uint32_t a_bytes = (uint32_t)(args.bn * args.bh * args.bw) * 128u;
                         const int rows = BN / 2;
+                        const bool two = KBOX == 2 && it * 2 + 1 < args.k_iters;   // the last stage of an odd count holds one box
                         if (doA) {
-                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * a_bytes);
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, (two ? 4u : 2u) * a_bytes);
                             tcg::tma_load_4d_2sm(sa, &tmA, fb, cb_now * TC_BK, w.q0 * args.a_sv + args.tap_dw[t_now],
                                                  w.p0 * args.a_su + args.tap_dh[t_now], w.img0);
+                            if (two)
+                                tcg::tma_load_4d_2sm(sa + TC_BM * 128, &tmA, fb, cb1 * TC_BK, w.q0 * args.a_sv + args.tap_dw[t1],
+                                                     w.p0 * args.a_su + args.tap_dh[t1], w.img0);
                         } else {
-                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * (uint32_t)rows * 128u);
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, (two ? 4u : 2u) * (uint32_t)rows * 128u);
                             tcg::tma_load_2d_2sm(sb, &tmB, fb, args.tap_bcol[t_now] + cb_now * TC_BK,
                                                  w.n_tile * BN + (int)crank * rows);
+                            if (two)
+                                tcg::tma_load_2d_2sm(sb + (((uint32_t)rows * 128u + 1023u) & ~1023u), &tmB, fb,
+                                                     args.tap_bcol[t1] + cb1 * TC_BK, w.n_tile * BN + (int)crank * rows);
                         }
                     } else if (MODE == TC_MODE_CONV) {
                         const uint32_t a_bytes = (dbg & 1) ? 0u : (uint32_t)(args.bn * args.bh * args.bw) * 128u;
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                 tcg::mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator
                 tcg::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
-                int cb = (MODE == TC_MODE_CONV) ? w.it_begin % args.c_iters : 0;   // channel block of the k-iteration
+                int cb = (MODE == TC_MODE_CONV) ? (w.it_begin * KBOX) % args.c_iters : 0;   // channel block of the next box
                 for (int i = 0; i < w.n_iters; ++i, ++g) {
                     tcg::mbar_wait(&full_bar[st], ph);
                     tcg::tc_fence_after();
@@ -328,6 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                     if (++st == stages) { st = 0; ph ^= 1u; }
                     const int cb_now = cb;
                     if (MODE == TC_MODE_CONV && ++cb == args.c_iters) cb = 0;
+                    const int cb1 = cb;
+                    if (MODE == TC_MODE_CONV && KBOX == 2 && ++cb == args.c_iters) cb = 0;
                     if (!tcg::elect_one()) continue;
                     if (MODE == TC_MODE_WGRAD) {
                         // one accumulator (BN columns) per Kout tile of the group, all fed from the same x tile
@@ -352,6 +370,19 @@ __global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ 
                             if ((dbg & 4) || k >= ksteps) continue;
                             if constexpr (pair) tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
                             else tcg::umma_bf16(tmem_d, da + (uint64_t)(k * 2), dbb + bk, idesc, (uint32_t)((i | k) != 0));
+                        }
+                    }
+                    if constexpr (KBOX == 2 && pair) {
+                        if ((w.it_begin + i) * 2 + 1 < args.k_iters) {   // second box of the stage
+                            const uint32_t b_box = ((uint32_t)(BN / 2) * 128u + 1023u) & ~1023u;
+                            const uint64_t da1 = tcg::make_smem_desc(sa + TC_BM * 128u, 16, 1024, 2);
+                            const uint64_t db1 = tcg::make_smem_desc(sb + b_box, 16, 1024, 2);
+                            const int ks1 = min(TC_BK / 16, (args.c_valid - cb1 * TC_BK + 15) / 16);
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                if ((dbg & 4) || k >= ks1) continue;
+                                tcg::umma_bf16_2sm(tmem_d, da1 + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc, 1u);
+                            }
                         }
                     }
                     // frees the stage once these MMAs have read it (in both CTAs of a pair)

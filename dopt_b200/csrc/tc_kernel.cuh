@@ -99,7 +99,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
 // KBOX = 2 (CONV pair tiles only): a pipeline stage holds two consecutive (tap, channel block) boxes, so the barrier round
 // trip and the fixed part of the issue loops are paid once per 8 MMAs.
 template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1>
-__global__ void __launch_bounds__(TC_THREADS) tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args_) {
     const TcArgs& args = args_;

@@ -268,83 +268,95 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 // tensor-core convolutions) into the apply pass: x is read once, and per element 4 B (fp32 result, when anybody reads it)
 // + 2 B (bf16 copy) are written, instead of 22 B for apply + relu + staging as three kernels.  The arithmetic is the
 // same as bn_apply_kernel / relu_kernel / nchw_to_nhwc_bf16_kernel, so results are bit-identical.
-// Tile: 64 channels x 32 pixels of one image; a block walks BN_SUBS consecutive pixel tiles and has the loads of the next one
-// in flight while it transposes and stores the current one.  grid (ceil(HW/(32*BN_SUBS)), ceil(Cp/64), N), 256 threads.
-static constexpr int BN_SUBS = 1;   // (4 was measured: no gain forward, slower backward)
-template <int MODE, bool RELU>
+// Tile: 16 channels x PX pixels of one image (PX = 256, or 64 for small maps).  Reads are PX*4-byte contiguous runs per channel
+// (128-bit loads; the earlier 64-channel x 32-pixel tile read 128-byte pieces 4 KB apart and ran at half the HBM
+// bandwidth), fp32 results go back the same way, the bf16 copy is written as one full 32-byte sector per pixel
+// (16 channels) -- neighbouring channel groups fill the rest of the line in L2.
+// grid (ceil(HW/PX), ceil(Cp/16), N), 256 threads.
+template <int MODE, bool RELU, int PX>
 __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ coef, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ staged, BnGeom g, int Cp,
                                                              const float* __restrict__ fcoef = nullptr) {
-    __shared__ float tile[64][33];
+    constexpr int PITCH = PX + 4;            // floats; keeps 128-bit shared stores aligned
+    constexpr int V4 = PX / 4;               // float4 per channel row
+    constexpr int PER_CH = V4 / 32 > 0 ? V4 / 32 : 1;   // float4 per lane per channel (PX=256: 2, PX=64: 1 for 16 lanes)
+    __shared__ __align__(16) float tile[16][PITCH];
     const int n = blockIdx.z;
-    const int c0 = blockIdx.y * 64;
+    const int hw0 = blockIdx.x * PX, c0 = blockIdx.y * 16;
     const int HW = (int)g.HW, C = (int)g.C;
     const int64_t img = (int64_t)n * C * HW;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    // per-channel coefficients of this thread's 8 channels
-    float cm[8], ca[8], cb[8], cc[8], fm[8], fa[8], fb[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool vec = (HW & 3) == 0 && ((((uintptr_t)x | (uintptr_t)out | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0);
+    // warp w handles channels c0 + w and c0 + w + 8
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = min(c0 + ty + j * 8, C - 1);
-        cm[j] = coef[c]; ca[j] = coef[C + c]; cb[j] = coef[2 * C + c];
-        cc[j] = MODE == 1 ? coef[3 * C + c] : 0.f;
-        if (MODE == 1 && RELU) { fm[j] = fcoef[c]; fa[j] = fcoef[C + c]; fb[j] = fcoef[2 * C + c]; }
-        else { fm[j] = fa[j] = fb[j] = 0.f; }
+    for (int half = 0; half < 2; ++half) {
+        const int cl = w + half * 8, c = c0 + cl;
+        float cm = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, fm = 0.f, fa = 0.f, fb = 0.f;
+        if (c < C) {
+            cm = coef[c]; ca = coef[C + c]; cb = coef[2 * C + c];
+            if (MODE == 1) cc = coef[3 * C + c];
+            if (MODE == 1 && RELU) { fm = fcoef[c]; fa = fcoef[C + c]; fb = fcoef[2 * C + c]; }
+        }
+        auto apply = [&](float xv, float q) {
+            const float v = xv - cm;
+            if (MODE == 0) {
+                float r = fmaf(v, ca, cb);
+                if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
+                return r;
+            }
+            if (RELU) q = fmaf(xv - fm, fa, fb) > 0.f ? q : 0.f;
+            return fmaf(q, ca, fmaf(v, cb, cc));
+        };
+        if (vec) {
+            float4 xv[PER_CH], qv[PER_CH];
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;                  // float4 index inside the tile row
+                const int hw = hw0 + p4 * 4;
+                const bool ok = c < C && p4 < V4 && hw < HW;   // HW % 4 == 0: a float4 is inside or outside as a whole
+                const int64_t i = img + (int64_t)c * HW + hw;
+                xv[u] = ok ? *(const float4*)(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                qv[u] = (MODE == 1 && ok) ? *(const float4*)(dy + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;
+                const int hw = hw0 + p4 * 4;
+                const bool ok = c < C && p4 < V4 && hw < HW;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    r.x = apply(xv[u].x, qv[u].x); r.y = apply(xv[u].y, qv[u].y);
+                    r.z = apply(xv[u].z, qv[u].z); r.w = apply(xv[u].w, qv[u].w);
+                    if (out) *(float4*)(out + img + (int64_t)c * HW + hw) = r;
+                }
+                if (p4 < V4) *(float4*)&tile[cl][p4 * 4] = r;
+            }
+        } else {
+            for (int p = lane; p < PX; p += 32) {
+                const int hw = hw0 + p;
+                float r = 0.f;
+                if (c < C && hw < HW) {
+                    const int64_t i = img + (int64_t)c * HW + hw;
+                    r = apply(x[i], MODE == 1 ? dy[i] : 0.f);
+                    if (out) out[i] = r;
+                }
+                tile[cl][p] = r;
+            }
+        }
     }
-    float xv[8], qv[8], xn[8], qn[8];
-    auto load = [&](int hw0, float (&xr)[8], float (&qr)[8]) {
+    if (!staged) return;
+    __syncthreads();
+    // one 16-byte store (8 channels) per thread trip: lanes 2p, 2p+1 write the two halves of pixel p's 32-byte sector
+    __nv_bfloat16* dst = staged + (int64_t)n * HW * Cp;
+    for (int idx = threadIdx.x; idx < PX * 2; idx += 256) {
+        const int p = idx >> 1, h = idx & 1;
+        const int hw = hw0 + p, c = c0 + h * 8;
+        if (hw < HW && c < Cp) {   // Cp is a multiple of 8
+            __nv_bfloat162 v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + ty + j * 8, hw = hw0 + tx;
-            const bool ok = c < C && hw < HW;
-            const int64_t i = img + (int64_t)c * HW + hw;
-            xr[j] = ok ? x[i] : 0.f;
-            qr[j] = (MODE == 1 && ok) ? dy[i] : 0.f;
-        }
-    };
-    const int first = blockIdx.x * BN_SUBS;
-    load(first * 32, xv, qv);
-    __nv_bfloat16* dst = staged ? staged + (int64_t)n * HW * Cp : nullptr;
-    for (int sub = 0; sub < BN_SUBS; ++sub) {
-        const int hw0 = (first + sub) * 32;
-        if (hw0 >= HW) break;
-        const bool more = sub + 1 < BN_SUBS && hw0 + 32 < HW;
-        if (more) load(hw0 + 32, xn, qn);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + ty + j * 8, hw = hw0 + tx;
-            float r = 0.f;
-            if (c < C && hw < HW) {
-                const float v = xv[j] - cm[j];
-                if (MODE == 0) {
-                    r = fmaf(v, ca[j], cb[j]);
-                    if (RELU) r = (r > 0.f || r != r) ? r : 0.f;
-                } else {
-                    float q = qv[j];
-                    if (RELU) q = fmaf(xv[j] - fm[j], fa[j], fb[j]) > 0.f ? q : 0.f;
-                    r = fmaf(q, ca[j], fmaf(v, cb[j], cc[j]));
-                }
-                if (out) out[img + (int64_t)c * HW + hw] = r;
-            }
-            tile[ty + j * 8][tx] = r;
-        }
-        if (staged) {
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                const int hw = hw0 + ty + j;
-                const int c = c0 + tx * 2;
-                if (hw < HW && c < Cp) {
-                    __nv_bfloat162 v = __floats2bfloat162_rn(tile[tx * 2][ty + j], tile[tx * 2 + 1][ty + j]);
-                    *(__nv_bfloat162*)(dst + (int64_t)hw * Cp + c) = v;
-                }
-            }
-            __syncthreads();   // the tile is rewritten by the next pixel tile
-        }
-        if (more) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { xv[j] = xn[j]; qv[j] = qn[j]; }
+            for (int k = 0; k < 4; ++k) v[k] = __floats2bfloat162_rn(tile[h * 8 + 2 * k][p], tile[h * 8 + 2 * k + 1][p]);
+            *(uint4*)(dst + (int64_t)hw * Cp + c) = *(uint4*)v;
         }
     }
 }
@@ -356,9 +368,15 @@ template <int MODE>
 static void bn_apply_tiled(const float* x, const float* dy, const float* coef, float* fp32, void* staged, bool relu,
                            const float* fcoef, const BnGeom& g, cudaStream_t s) {
     const int Cp = (int)((g.C + 7) / 8 * 8);
-    dim3 grid((unsigned)ceil_div(g.HW, 32 * BN_SUBS), (unsigned)ceil_div(Cp, 64), (unsigned)g.N);
-    if (relu) bn_apply_stage_kernel<MODE, true><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
-    else bn_apply_stage_kernel<MODE, false><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+    if (g.HW > 64) {
+        dim3 grid((unsigned)ceil_div(g.HW, 256), (unsigned)ceil_div(Cp, 16), (unsigned)g.N);
+        if (relu) bn_apply_stage_kernel<MODE, true, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+        else bn_apply_stage_kernel<MODE, false, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+    } else {
+        dim3 grid((unsigned)ceil_div(g.HW, 64), (unsigned)ceil_div(Cp, 16), (unsigned)g.N);
+        if (relu) bn_apply_stage_kernel<MODE, true, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+        else bn_apply_stage_kernel<MODE, false, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+    }
     DB_LAUNCH_CHECK();
 }
 

@@ -86,29 +86,54 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
 }
 
 // NCHW fp32 -> NHWC bf16 with channel padding: per image a [C][HW] -> [HW][Cp] transpose through shared memory.
-// grid (ceil(HW/32), ceil(Cp/64), N), 256 threads.  4 B read + 2 B written per element.
+// Tile = 16 channels x PX pixels (PX = 256, or 64 for small maps): the reads are PX*4-byte contiguous runs (DRAM pages like
+// long runs: the earlier 64-channel x 32-pixel tile ran at half the bandwidth), the writes one full 32-byte sector per pixel.
+// grid (ceil(HW/PX), ceil(Cp/16), N), 256 threads.  4 B read + 2 B written per element.
+template <int PX>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ in,
                                                                 __nv_bfloat16* __restrict__ out, int C, int HW, int Cp) {
-    __shared__ float tile[64][33];
+    constexpr int PITCH = PX + 4;
+    constexpr int V4 = PX / 4;
+    constexpr int PER_CH = V4 / 32 > 0 ? V4 / 32 : 1;
+    __shared__ __align__(16) float tile[16][PITCH];
     const int n = blockIdx.z;
-    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int hw0 = blockIdx.x * PX, c0 = blockIdx.y * 16;
     const float* src = in + (int64_t)n * C * HW;
-    __nv_bfloat16* dst = out + (int64_t)n * HW * Cp;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool vec = (HW & 3) == 0 && (((uintptr_t)in & 15) == 0);
 #pragma unroll
-    for (int j = 0; j < 64; j += 8) {
-        int c = c0 + ty + j, hw = hw0 + tx;
-        tile[ty + j][tx] = (c < C && hw < HW) ? src[(int64_t)c * HW + hw] : 0.f;
+    for (int half = 0; half < 2; ++half) {
+        const int cl = w + half * 8, c = c0 + cl;
+        if (vec) {
+            float4 v[PER_CH];
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;
+                const int hw = hw0 + p4 * 4;
+                v[u] = (c < C && p4 < V4 && hw < HW) ? *(const float4*)(src + (int64_t)c * HW + hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;
+                if (p4 < V4) *(float4*)&tile[cl][p4 * 4] = v[u];
+            }
+        } else {
+            for (int p = lane; p < PX; p += 32) {
+                const int hw = hw0 + p;
+                tile[cl][p] = (c < C && hw < HW) ? src[(int64_t)c * HW + hw] : 0.f;
+            }
+        }
     }
     __syncthreads();
-    // write: each thread packs 2 channels; 32 threads cover 64 channels of one pixel (128 contiguous bytes)
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        int hw = hw0 + ty + j;
-        int c = c0 + tx * 2;
+    __nv_bfloat16* dst = out + (int64_t)n * HW * Cp;
+    for (int idx = threadIdx.x; idx < PX * 2; idx += 256) {
+        const int p = idx >> 1, h = idx & 1;
+        const int hw = hw0 + p, c = c0 + h * 8;
         if (hw < HW && c < Cp) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(tile[tx * 2][ty + j], tile[tx * 2 + 1][ty + j]);
-            *(__nv_bfloat162*)(dst + (int64_t)hw * Cp + c) = v;
+            __nv_bfloat162 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __floats2bfloat162_rn(tile[h * 8 + 2 * k][p], tile[h * 8 + 2 * k + 1][p]);
+            *(uint4*)(dst + (int64_t)hw * Cp + c) = *(uint4*)v;
         }
     }
 }
@@ -116,13 +141,14 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
 // KCRS fp32 -> packed bf16 through a shared-memory tile, so that both the fp32 reads (runs of TC*RS contiguous floats) and
 // the bf16 writes (128-byte rows of 64 channels) are coalesced.  6 B/element.
 //   MODE 0 (fwd):   out[k][(r*S+s)*Cp + c] = w[k][c][R-1-r][S-1-s]     tile 4 k x 64 c
-//   MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]     tile 64 k x 4 c
-// (small tiles: a 160x160x3x3 filter still gives 120 CTAs)
+//   MODE 1 (dgrad): out[c][(r*S+s)*Kp + k] = w[k][c][R-1-r][S-1-s]     tile 16 k x 16 c (reads: 16*RS-float runs; writes: full
+//                                                                      32-byte sectors, neighbours complete the lines in L2)
+// (small tiles: a 160x160x3x3 filter still gives 100+ CTAs)
 // grid (ceil(Kx/TK), ceil(Cx/TCc)) over the padded extents, 256 threads, dynamic smem TK*(TCc*RS+1) floats.
 template <int MODE>
 __device__ __forceinline__ void pack_filters_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int C,
                                                   int RS, int Kp, int Cp, int bx, int by, float* pf_tile) {
-    constexpr int TK = MODE == 0 ? 4 : 64, TCc = MODE == 0 ? 64 : 4;
+    constexpr int TK = MODE == 0 ? 4 : 16, TCc = MODE == 0 ? 64 : 16;
     const int ld = TCc * RS + 1;   // pf_tile: [TK k][TCc c * RS (+1)]
     const int k0 = bx * TK, c0 = by * TCc;
     const int run = min(TCc, C - c0) * RS;   // contiguous floats of one k row inside this tile (<= 0: padding tile)
@@ -165,14 +191,15 @@ __device__ __forceinline__ void pack_filters_tile(const float* __restrict__ w, _
             }
         }
     } else {
-        // one (c, tap) row of 64 output channels k = 128 bytes per warp trip, two k per lane
-        for (int row = wid; row < TCc * RS; row += 8) {
+        // rows (c, tap) of 16 output channels k = 32 bytes, two k per thread
+        for (int item = threadIdx.x; item < TCc * RS * (TK / 2); item += 256) {
+            const int row = item / (TK / 2), kp = item - row * (TK / 2);
             const int cc = row / RS, t = row - cc * RS;
-            const int c = c0 + cc, k = k0 + lane * 2;
+            const int c = c0 + cc, k = k0 + kp * 2;
             if (c < Cp && k < Kp) {   // Kp is even
                 const float* src = pf_tile + cc * RS + (RS - 1 - t);
                 *(__nv_bfloat162*)(out + ((int64_t)c * RS + t) * Kp + k) =
-                    __floats2bfloat162_rn(src[(lane * 2) * ld], src[(lane * 2 + 1) * ld]);
+                    __floats2bfloat162_rn(src[(kp * 2) * ld], src[(kp * 2 + 1) * ld]);
             }
         }
     }
@@ -236,7 +263,7 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 }
 
 static void pack_filters(const float* w, __nv_bfloat16* out, int K, int C, int RS, int Kp, int Cp, int mode, cudaStream_t s) {
-    const int TK = mode == 0 ? 4 : 64, TCc = mode == 0 ? 64 : 4;
+    const int TK = mode == 0 ? 4 : 16, TCc = mode == 0 ? 64 : 16;
     const size_t smem = (size_t)TK * (TCc * RS + 1) * sizeof(float);
     DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the packing kernel");
     DB_REQUIRE(Kp % 2 == 0 || mode == 0, "packed Kout extent must be even");
@@ -261,7 +288,7 @@ void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_
     size_t smem = 0;
     for (int i = 0; i < n; ++i) {
         FilterPack& f = rows[i];
-        const int TK = f.mode == 0 ? 4 : 64, TCc = f.mode == 0 ? 64 : 4;
+        const int TK = f.mode == 0 ? 4 : 16, TCc = f.mode == 0 ? 64 : 16;
         f.tiles_x = (int)ceil_div(f.Kp, TK);
         f.tile0 = tiles;
         tiles += f.tiles_x * (int)ceil_div(f.Cp, TCc);
@@ -283,8 +310,13 @@ void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size
 }
 
 static void nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int N, int C, int HW, int Cp, cudaStream_t s) {
-    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(Cp, 64), (unsigned)N);
-    nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, s>>>(in, out, C, HW, Cp);
+    if (HW > 64) {
+        dim3 grid((unsigned)ceil_div(HW, 256), (unsigned)ceil_div(Cp, 16), (unsigned)N);
+        nchw_to_nhwc_bf16_kernel<256><<<grid, 256, 0, s>>>(in, out, C, HW, Cp);
+    } else {
+        dim3 grid((unsigned)ceil_div(HW, 64), (unsigned)ceil_div(Cp, 16), (unsigned)N);
+        nchw_to_nhwc_bf16_kernel<64><<<grid, 256, 0, s>>>(in, out, C, HW, Cp);
+    }
     DB_LAUNCH_CHECK();
 }
 

@@ -50,7 +50,7 @@ TRAIN_GFLOP_PER_IMAGE = 31.459
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, round 1 final)
-TC_DRAM_BYTES_PER_STEP = 3107299328 + 559083264
+TC_DRAM_BYTES_PER_STEP = 3106400512 + 557725696
 
 
 def peaks():

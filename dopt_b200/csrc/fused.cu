@@ -21,6 +21,23 @@ __device__ __forceinline__ float fz_apply(int op, float a, float b) {
     }
     return 0.f;
 }
+// the same on four lanes with ONE dispatch: the switch is the expensive part of an interpreted instruction
+__device__ __forceinline__ float4 fz_apply4(int op, const float4& a, const float4& b) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    switch (op) {
+#define C(OP)                                         \
+    case dbk::OP:                                     \
+        d.x = dbk::apply<dbk::OP, float>(a.x, b.x);   \
+        d.y = dbk::apply<dbk::OP, float>(a.y, b.y);   \
+        d.z = dbk::apply<dbk::OP, float>(a.z, b.z);   \
+        d.w = dbk::apply<dbk::OP, float>(a.w, b.w);   \
+        break;
+        C(OP_ADD) C(OP_SUB) C(OP_MUL) C(OP_DIV) C(OP_LT) C(OP_LTE) C(OP_GT) C(OP_GTE) C(OP_EQ) C(OP_NEQ) C(OP_MAX)
+        C(OP_MIN) C(OP_POW) C(OP_NEG) C(OP_ABS) C(OP_SGN) C(OP_EXP) C(OP_LOG) C(OP_SQRT)
+#undef C
+    }
+    return d;
+}
 
 __device__ __forceinline__ int fz_find_row(const FzRow* rows, int n_rows, int64_t chunk) {
     int lo = 0, hi = n_rows - 1;
@@ -51,18 +68,30 @@ __global__ void __launch_bounds__(kFzThreads) fused_kernel(const FzRow* __restri
         }
         // vector lanes: 4 elements per thread per trip; a scalar tail (or the whole row when unaligned) uses lane x only
         const int64_t vend = vec ? (base + ((end - base) & ~(int64_t)3)) : base;
-        for (int64_t i = base + (int64_t)tid * 4; i < vend; i += kFzThreads * 4) {
-            for (int t = 0; t < nt; ++t) regs[t * kFzThreads + tid] = dbk::ld_stream((const float4*)(r.in[t] + i));
+        // the loads of trip i+1 are issued before the program of trip i runs (registers `pre`), so that global-memory latency
+        // overlaps the interpreter's shared-memory round trips instead of adding to them
+        float4 pre[FZ_MAX_TENSORS];
+        int64_t i = base + (int64_t)tid * 4;
+        if (i < vend) {
+#pragma unroll
+            for (int t = 0; t < FZ_MAX_TENSORS; ++t)
+                if (t < nt) pre[t] = dbk::ld_stream((const float4*)(r.in[t] + i));
+        }
+        for (; i < vend; i += kFzThreads * 4) {
+#pragma unroll
+            for (int t = 0; t < FZ_MAX_TENSORS; ++t)
+                if (t < nt) regs[t * kFzThreads + tid] = pre[t];
+            const int64_t inext = i + kFzThreads * 4;
+            if (inext < vend) {
+#pragma unroll
+                for (int t = 0; t < FZ_MAX_TENSORS; ++t)
+                    if (t < nt) pre[t] = dbk::ld_stream((const float4*)(r.in[t] + inext));
+            }
             for (int k = 0; k < prog.n_instr; ++k) {
                 const FzInstr ins = prog.instr[k];
                 const float4 a = regs[ins.a * kFzThreads + tid];
                 const float4 b = regs[ins.b * kFzThreads + tid];
-                float4 d;
-                d.x = fz_apply(ins.op, a.x, b.x);
-                d.y = fz_apply(ins.op, a.y, b.y);
-                d.z = fz_apply(ins.op, a.z, b.z);
-                d.w = fz_apply(ins.op, a.w, b.w);
-                regs[ins.dst * kFzThreads + tid] = d;
+                regs[ins.dst * kFzThreads + tid] = fz_apply4(ins.op, a, b);
             }
             for (int o = 0; o < prog.n_outputs; ++o)
                 dbk::st_stream((float4*)(r.out[o] + i), regs[prog.out_reg[o] * kFzThreads + tid]);

@@ -593,6 +593,37 @@ static FzProgram make_program(Plan& p, const Region& R) {
     }
     g.n_outputs = (int)R.out_nodes.size();
     for (int o = 0; o < g.n_outputs; ++o) g.out_reg[o] = (uint8_t)reg_of[R.out_nodes[o]];
+    // Register re-use.  The interpreter's register file lives in shared memory (one float4 per register per thread), and its
+    // size decides how many CTAs fit on an SM, i.e. how much of the HBM latency is hidden.  A slot is recycled as soon as its
+    // value has been read for the last time (tensor inputs included: they are reloaded every trip); scalar slots are loaded
+    // once per chunk and output values are stored at the end of the trip, so both stay.
+    {
+        const int n_virtual = next, first_free = g.n_tensors + g.n_scalars;
+        std::vector<int> last_use(n_virtual, -1), phys(n_virtual, -1);
+        for (int k = 0; k < g.n_instr; ++k) last_use[g.instr[k].a] = last_use[g.instr[k].b] = k;
+        for (int o = 0; o < g.n_outputs; ++o) last_use[g.out_reg[o]] = 1 << 30;
+        for (int s2 = g.n_tensors; s2 < first_free; ++s2) last_use[s2] = 1 << 30;
+        for (int v = 0; v < first_free; ++v) phys[v] = v;
+        std::vector<int> free_slots;
+        int n_phys = first_free;
+        for (int k = 0; k < g.n_instr; ++k) {
+            FzInstr& ins = g.instr[k];
+            const int va = ins.a, vb = ins.b, vd = ins.dst;
+            ins.a = (uint8_t)phys[va];
+            ins.b = (uint8_t)phys[vb];
+            if (last_use[va] == k) free_slots.push_back(phys[va]);
+            if (vb != va && last_use[vb] == k) free_slots.push_back(phys[vb]);
+            if (!free_slots.empty()) {
+                phys[vd] = free_slots.back();
+                free_slots.pop_back();
+            } else {
+                phys[vd] = n_phys++;
+            }
+            ins.dst = (uint8_t)phys[vd];
+            if (last_use[vd] < 0) free_slots.push_back(phys[vd]);   // dead value (cannot happen for needed nodes)
+        }
+        for (int o = 0; o < g.n_outputs; ++o) g.out_reg[o] = (uint8_t)phys[g.out_reg[o]];
+    }
     return g;
 }
 

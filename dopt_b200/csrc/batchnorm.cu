@@ -139,23 +139,29 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
                 sdx += (q.x * a + q.y * b) + (q.z * cc + q.w * d);
             }
         };
-        int64_t i = threadIdx.x;
-        for (; i + (U - 1) * (int64_t)blockDim.x < total; i += U * (int64_t)blockDim.x) {
+        // index arithmetic in 32 bits (a 64-bit division per load made this memory-bound kernel ALU-heavy); the host keeps
+        // (images per split) * HW/4 below 2^31
+        const uint32_t hw4u = (uint32_t)hw4, totalu = total > 0 ? (uint32_t)total : 0u, bd = blockDim.x;   // empty tail splits
+        const int64_t img_stride = g.C * g.HW;
+        const float* xb = x + ((int64_t)n0 * g.C + c) * g.HW;
+        const float* db = GRAD ? dy + ((int64_t)n0 * g.C + c) * g.HW : nullptr;
+        uint32_t i = threadIdx.x;
+        for (; i + (U - 1) * bd < totalu; i += U * bd) {
             float4 v[U], q[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int64_t iu = i + u * (int64_t)blockDim.x;
-                const int64_t n = n0 + iu / hw4, j = iu % hw4;
-                const int64_t off = ((n * g.C + c) * g.HW) + (j << 2);
-                v[u] = *(const float4*)(x + off);
-                q[u] = GRAD ? *(const float4*)(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t iu = i + u * bd;
+                const uint32_t n = iu / hw4u, j = iu - n * hw4u;
+                const int64_t off = (int64_t)n * img_stride + (j << 2);
+                v[u] = *(const float4*)(xb + off);
+                q[u] = GRAD ? *(const float4*)(db + off) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) accumulate(v[u], q[u]);
         }
-        for (; i < total; i += blockDim.x) {
-            const int64_t n = n0 + i / hw4, j = i % hw4;
-            const int64_t off = ((n * g.C + c) * g.HW) + (j << 2);
+        for (; i < totalu; i += bd) {
+            const uint32_t n = i / hw4u, j = i - n * hw4u;
+            const int64_t off = ((((int64_t)n0 + n) * g.C + c) * g.HW) + (j << 2);
             const float4 v = *(const float4*)(x + off);
             const float4 q = GRAD ? *(const float4*)(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
             accumulate(v, q);
@@ -222,8 +228,16 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if ((g.HW & 3) == 0 && (((uintptr_t)out | (uintptr_t)x | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0) {
         const int64_t nv = V >> 2, hw4 = g.HW >> 2;
+        const bool small = nv < (1ll << 31);   // 32-bit index arithmetic: a 64-bit division per vector is most of this loop's ALU work
+        const uint32_t hw4u = (uint32_t)hw4, Cu = (uint32_t)g.C;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-            int c = (int)((i / hw4) % g.C);
+            int c;
+            if (small) {
+                const uint32_t row = (uint32_t)i / hw4u;
+                c = (int)(row % Cu);
+            } else {
+                c = (int)((i / hw4) % g.C);
+            }
             float4 v = dbk::ld_stream((const float4*)x + i), r;
             const float mu = coef[c];
             bool m0 = true, m1 = true, m2 = true, m3 = true;

@@ -145,9 +145,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
 //                                                                      32-byte sectors, neighbours complete the lines in L2)
 // (small tiles: a 160x160x3x3 filter still gives 100+ CTAs)
 // grid (ceil(Kx/TK), ceil(Cx/TCc)) over the padded extents, 256 threads, dynamic smem TK*(TCc*RS+1) floats.
-template <int MODE>
+// RS9: the 3x3 case with RS as a compile-time constant (the index arithmetic is full of divisions by RS)
+template <int MODE, bool RS9 = false>
 __device__ __forceinline__ void pack_filters_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int C,
-                                                  int RS, int Kp, int Cp, int bx, int by, float* pf_tile) {
+                                                  int RS_, int Kp, int Cp, int bx, int by, float* pf_tile) {
+    const int RS = RS9 ? 9 : RS_;
     constexpr int TK = MODE == 0 ? 4 : 16, TCc = MODE == 0 ? 64 : 16;
     const int ld = TCc * RS + 1;   // pf_tile: [TK k][TCc c * RS (+1)]
     const int k0 = bx * TK, c0 = by * TCc;
@@ -222,8 +224,14 @@ __global__ void __launch_bounds__(256) pack_filters_multi_kernel(const FilterPac
     const FilterPack r = rows[lo];
     const int t = (int)blockIdx.x - r.tile0;
     const int bx = t % r.tiles_x, by = t / r.tiles_x;
-    if (r.mode == 0) pack_filters_tile<0>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
-    else pack_filters_tile<1>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
+    if (r.RS == 9) {
+        if (r.mode == 0) pack_filters_tile<0, true>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, 9, r.Kp, r.Cp, bx, by, pf_tile);
+        else pack_filters_tile<1, true>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, 9, r.Kp, r.Cp, bx, by, pf_tile);
+    } else if (r.mode == 0) {
+        pack_filters_tile<0>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
+    } else {
+        pack_filters_tile<1>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, r.RS, r.Kp, r.Cp, bx, by, pf_tile);
+    }
 }
 
 // convolutionFiltersGrad: the tensor-core kernel accumulates into a scratch laid out [tap][C][K] (K contiguous = the

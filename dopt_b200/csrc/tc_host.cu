@@ -363,8 +363,20 @@ void tc_prof_read(double* us, int64_t* launches) {
 }
 
 template <int MODE>
-static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int n_ctas, cudaStream_t s) {
+static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, int n_ctas, cudaStream_t s) {
     // n_ctas on entry = number of work items (m_tiles * n_tiles * splits)
+    TcArgs a = a_in;
+    {   // multiply-high constants for the kernel's tile decoding
+        const int csize = (MODE == TC_MODE_CONV && a.pair) ? 2 : 1;
+        a.fd_mgroups = tc_fastdiv(a.m_tiles / csize);
+        a.fd_splits = tc_fastdiv(a.splits);
+        a.fd_tiles_q = tc_fastdiv(a.tiles_q);
+        a.fd_tiles_p = tc_fastdiv(a.tiles_p);
+        const int mt = (a.M + TC_BM - 1) / TC_BM;
+        a.fd_wg_mg = tc_fastdiv(MODE == TC_MODE_WGRAD ? (mt + std::max(1, a.wg_nm) - 1) / std::max(1, a.wg_nm) : 1);
+        const int total = (MODE == TC_MODE_WGRAD) ? a.pix_tiles : a.k_iters;
+        a.per_split = (total + std::max(1, a.splits) - 1) / std::max(1, a.splits);
+    }
     TcSmemLayout L = tc_smem_layout(a);
     static int configured = 0;
     if (configured < (int)L.total) {

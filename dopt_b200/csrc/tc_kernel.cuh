@@ -25,6 +25,18 @@ static constexpr int TC_BK = 64;                 // bf16 elements per 128-byte s
 static constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining every other 16-column chunk
 static constexpr int TC_THREADS = 352;   // warp 0: TMA (A) | warp 1: MMA | warps 2-9: epilogue | warp 10: TMA (B, CONV mode)
 
+// exact x / d for the small operands of the tile decoding (x * d < 2^32): one multiply-high instead of a ~100-cycle division.
+// Every role decodes every work item, so the divisions sat on the critical path of each tile boundary.
+struct TcFastDiv {
+    unsigned d, m;   // m = ceil(2^32 / d); d == 1 -> m = 0 (identity)
+};
+__host__ __device__ inline TcFastDiv tc_fastdiv(int d) {
+    TcFastDiv f;
+    f.d = (unsigned)(d > 0 ? d : 1);
+    f.m = f.d == 1 ? 0u : (unsigned)(((1ull << 32) + f.d - 1) / f.d);
+    return f;
+}
+
 struct TcArgs {
     int mode;
     int BN;             // accumulator columns (multiple of 16, <= 256)
@@ -59,6 +71,8 @@ struct TcArgs {
     int wg_tap;         // unused (tap comes from the tile index)
     int pix_tiles;      // number of pixel boxes (the reduction dimension), split over `splits`
     int kmma;           // MMAs per stage (box pixels / 16)
+    TcFastDiv fd_mgroups, fd_splits, fd_tiles_q, fd_tiles_p, fd_wg_mg;   // filled by tc_launch
+    int per_split;      // ceil(iterations / splits), filled by tc_launch
     int kbox;           // CONV pair tiles: (tap, channel block) boxes per pipeline stage (1, or 2 = tc_kernel<.., KBOX = 2>)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
 };
@@ -134,31 +148,32 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
     struct Work {
         int m_tile, n_tile, split, it_begin, n_iters, img0, p0, q0, wg_tap;
     };
+    auto fdiv = [](unsigned x, const TcFastDiv& f) -> unsigned { return f.m ? __umulhi(x, f.m) : x; };
     auto decode = [&](int cw) {
         Work w;
-        int cm = cw % m_groups;
-        int rest = cw / m_groups;
-        w.split = rest % args.splits;
-        w.n_tile = rest / args.splits;
+        const unsigned rest = fdiv((unsigned)cw, args.fd_mgroups);
+        const int cm = cw - (int)rest * m_groups;
+        w.n_tile = (int)fdiv(rest, args.fd_splits);
+        w.split = (int)rest - w.n_tile * args.splits;
         w.m_tile = cm * csize + (int)crank;
-        int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + KBOX - 1) / KBOX;
-        int per = (total + args.splits - 1) / args.splits;
+        const int total = (MODE == TC_MODE_WGRAD) ? args.pix_tiles : (args.k_iters + KBOX - 1) / KBOX;
+        const int per = (KBOX == 1) ? args.per_split : total;   // (KBOX = 2 is only used with splits == 1)
         w.it_begin = w.split * per;
         w.n_iters = max(0, min(total, w.it_begin + per) - w.it_begin);
         w.img0 = w.p0 = w.q0 = w.wg_tap = 0;
         if (MODE == TC_MODE_CONV) {
-            int tq = w.m_tile % args.tiles_q;
-            int t2 = w.m_tile / args.tiles_q;
-            int tp = t2 % args.tiles_p;
-            int ng = t2 / args.tiles_p;
-            w.img0 = ng * args.bn;
+            const unsigned t2 = fdiv((unsigned)w.m_tile, args.fd_tiles_q);
+            const int tq = w.m_tile - (int)t2 * args.tiles_q;
+            const unsigned ng = fdiv(t2, args.fd_tiles_p);
+            const int tp = (int)t2 - (int)ng * args.tiles_p;
+            w.img0 = (int)ng * args.bn;
             w.p0 = tp * args.bh;
             w.q0 = tq * args.bw;
         }
         if (MODE == TC_MODE_WGRAD) {   // m_tile = (tap, group of wg_nm Kout tiles)
             const int mt = (args.M + TC_BM - 1) / TC_BM;
-            const int mg = (mt + args.wg_nm - 1) / args.wg_nm;
-            w.wg_tap = w.m_tile / mg;
+            const int mg = (int)args.fd_wg_mg.d;
+            w.wg_tap = (int)fdiv((unsigned)w.m_tile, args.fd_wg_mg);
             w.p0 = (w.m_tile - w.wg_tap * mg) * args.wg_nm;   // first Kout tile of the group
             w.q0 = min(args.wg_nm, mt - w.p0);                // Kout tiles in the group
         }

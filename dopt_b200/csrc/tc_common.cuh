@@ -72,14 +72,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 
 // multicast variant: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each destination
 // CTA's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                                  uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-        "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-        : "memory");
-}
 
 // cta_group::2 variants: issued by BOTH CTAs of a pair, each into its own shared memory; the transaction bytes are
 // credited to the barrier of the pair's leader (even rank): clearing bit 24 of the shared-window address selects it
@@ -176,13 +168,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 // same, arriving on the barrier at this offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"(cta_mask)
-        : "memory");
-}
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread t of the warp <-> TMEM lane base+t)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(

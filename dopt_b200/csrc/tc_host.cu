@@ -497,22 +497,6 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
     return st;
 }
 
-// CTAs per cluster that share one filter tile through TMA multicast.  The implicit-GEMM kernel is bound by L2->SM
-// bandwidth (profiles/r01a_tc_kernel.md): every CTA of a 128 x BN tile pulls the full BN x 64 filter slab per k-step.
-// With a cluster of c CTAs working on c different pixel tiles, each CTA pulls 1/c of it.
-static int g_max_cluster = 4;
-void tc_set_max_cluster(int c) { g_max_cluster = c; }
-static int pick_cluster(int m_tiles, int bn) {
-    static bool env_read = false;
-    if (!env_read) {
-        env_read = true;
-        if (const char* e = getenv("DOPT_B200_MAX_CLUSTER")) g_max_cluster = atoi(e);   // tuning knob for experiments
-    }
-    for (int c = g_max_cluster; c > 1; c >>= 1)
-        if (m_tiles >= 2 * c && bn % (8 * c) == 0) return c;
-    return 1;
-}
-
 // cta_group::2 pair tiles (256 x BN): each SM ingests only half of the filter tile
 static int g_use_pair = 1;
 static bool pick_pair(int m_tiles, int bn) {

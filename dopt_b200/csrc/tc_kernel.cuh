@@ -42,8 +42,8 @@ struct TcArgs {
     int BN;             // accumulator columns (multiple of 16, <= 256)
     int stages;
     int n_tiles;        // tiles along N; blockIdx.x = ((n_tile * splits) + split) * m_tiles + m_tile
-    int m_tiles;        // tiles along M (padded to a multiple of `cluster`)
-    int cluster;        // CTAs per cluster sharing one B tile through TMA multicast (1, 2 or 4; CONV mode)
+    int m_tiles;        // tiles along M (even in pair mode)
+    int cluster;        // always 1 (filter-tile multicast across larger clusters was measured neutral and removed)
     unsigned long long* trace;   // experiments only: CTA 0 records clock64() per pipeline event (see tools/exp_conv.sh)
     int dbg;            // experiments only: bit 0 = skip A loads, bit 1 = skip B loads (results are then garbage)
     int nacc;           // TMEM accumulators per CTA: 2 (512 columns, one CTA per SM) or 1 (256 columns, two CTAs per SM)

@@ -1040,11 +1040,19 @@ static void absorb(Plan& p) {
         int64_t off = 0;
         const int b = root_of(p, st.src_dep, &off);
         Node& B = N[b];
-        if (off != 0 || B.type != "batchNormGrad" || !B.kernel || !B.kernel->can_absorb() || B.absorb_stage >= 0) continue;
+        // producers that can write the staged copy themselves: batchNormGrad (its dx slice) and a stand-alone `add`
+        // (the gradient sums of the residual connections)
+        const bool is_add = B.type == "add" && B.region < 0 && B.pw_op >= 0 && B.pw_mode == dbk::B_TENSOR &&
+                            !getenv("DOPT_B200_NO_ADD_STAGE");
+        if (off != 0 || (B.type != "batchNormGrad" && !is_add) || !B.kernel || !B.kernel->can_absorb() || B.absorb_stage >= 0)
+            continue;
         const int64_t head = N[st.src_dep].bytes;
         if (head != (int64_t)st.n * st.c * st.hw * 4) continue;
+        if (is_add && (B.bytes != head || B.op.output.rank != 4 || B.op.output.shape[0] != st.n || B.op.output.shape[1] != st.c))
+            continue;
         st.producer = b;
         B.absorb_stage = (int)si;
+        if (is_add) continue;   // the fp32 sum is always written
         bool all_staged = !head_is_output(b, head);
         for (auto& rd : readers_of_head(b, head))
             if (std::find(st.users.begin(), st.users.end(), rd) == st.users.end()) all_staged = false;

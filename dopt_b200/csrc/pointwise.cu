@@ -133,11 +133,87 @@ int pointwise_op_id(const char* name) {
 }
 bool pointwise_is_unary(int op) { return op >= dbk::OP_NEG; }
 
+// a + b on NCHW fp32 tensors that ALSO emits the NHWC bf16 copy the tensor-core convolutions read (the plan folds the staging
+// of a gradient sum into the add that produces it).  Same tile structure as bn_apply_stage_kernel: 16 channels x PX pixels,
+// PX*4-byte contiguous reads, one full 32-byte sector of bf16 per pixel.  grid (ceil(HW/PX), ceil(Cp/16), N), 256 threads.
+template <int PX>
+__global__ void __launch_bounds__(256) add_stage_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        float* __restrict__ out, __nv_bfloat16* __restrict__ staged, int C,
+                                                        int HW, int Cp) {
+    constexpr int PITCH = PX + 4;
+    constexpr int V4 = PX / 4;
+    constexpr int PER_CH = V4 / 32 > 0 ? V4 / 32 : 1;
+    __shared__ __align__(16) float tile[16][PITCH];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * PX, c0 = blockIdx.y * 16;
+    const int64_t img = (int64_t)n * C * HW;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool vec = (HW & 3) == 0 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int cl = w + half * 8, c = c0 + cl;
+        if (vec) {
+            float4 av[PER_CH], bv[PER_CH];
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;
+                const int hw = hw0 + p4 * 4;
+                const bool ok = c < C && p4 < V4 && hw < HW;
+                const int64_t i = img + (int64_t)c * HW + hw;
+                av[u] = ok ? *(const float4*)(a + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bv[u] = ok ? *(const float4*)(b + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < PER_CH; ++u) {
+                const int p4 = lane + u * 32;
+                const int hw = hw0 + p4 * 4;
+                float4 r;
+                r.x = dbk::apply<dbk::OP_ADD, float>(av[u].x, bv[u].x); r.y = dbk::apply<dbk::OP_ADD, float>(av[u].y, bv[u].y);
+                r.z = dbk::apply<dbk::OP_ADD, float>(av[u].z, bv[u].z); r.w = dbk::apply<dbk::OP_ADD, float>(av[u].w, bv[u].w);
+                if (c < C && p4 < V4 && hw < HW) *(float4*)(out + img + (int64_t)c * HW + hw) = r;
+                if (p4 < V4) *(float4*)&tile[cl][p4 * 4] = r;
+            }
+        } else {
+            for (int p = lane; p < PX; p += 32) {
+                const int hw = hw0 + p;
+                float r = 0.f;
+                if (c < C && hw < HW) {
+                    const int64_t i = img + (int64_t)c * HW + hw;
+                    r = dbk::apply<dbk::OP_ADD, float>(a[i], b[i]);
+                    out[i] = r;
+                }
+                tile[cl][p] = r;
+            }
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = staged + (int64_t)n * HW * Cp;
+    for (int idx = threadIdx.x; idx < PX * 2; idx += 256) {
+        const int p = idx >> 1, h = idx & 1;
+        const int hw = hw0 + p, c = c0 + h * 8;
+        if (hw < HW && c < Cp) {
+            __nv_bfloat162 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __floats2bfloat162_rn(tile[h * 8 + 2 * k][p], tile[h * 8 + 2 * k + 1][p]);
+            *(uint4*)(dst + (int64_t)hw * Cp + c) = *(uint4*)v;
+        }
+    }
+}
+
 namespace {
 struct PointwiseKernel : Kernel {
     int op, dtype;
     int64_t n;
     bool unary;
+    int64_t aN = 0, aC = 0, aHW = 0;   // NCHW view of the result (rank 4), for the add + staging variant
+    Absorb ab;
+    bool can_absorb() const override {
+        return op == dbk::OP_ADD && dtype == DOPT_B200_FLOAT32 && aN > 0 && aN < 65536 && aC < (1 << 24) && aHW < (1ll << 30);
+    }
+    void set_absorbed(const Absorb& a) override {
+        DB_REQUIRE(!a.relu && !a.redirect && !a.skip_fp32, "pointwise add can only absorb the NHWC staging");
+        ab = a;
+    }
     PointwiseKernel(const dopt_b200_op& d) {
         op = pointwise_op_id(d.op_type);
         DB_REQUIRE(op >= 0, "unknown pointwise op");
@@ -145,6 +221,11 @@ struct PointwiseKernel : Kernel {
         DB_REQUIRE(d.n_inputs == (unary ? 1 : 2), "pointwise: wrong number of operands");
         dtype = d.output.dtype;
         n = volume(d.output);
+        if (d.output.rank == 4) {
+            aN = d.output.shape[0];
+            aC = d.output.shape[1];
+            aHW = d.output.shape[2] * d.output.shape[3];
+        }
         // verifier of the reference: operand types must be identical (core/source/dopt/core/ops/math.d:22-25)
         for (int i = 0; i < d.n_inputs; ++i) {
             DB_REQUIRE(d.inputs[i].dtype == dtype && volume(d.inputs[i]) == n, "pointwise: operand type mismatch");
@@ -152,6 +233,20 @@ struct PointwiseKernel : Kernel {
     }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == (unary ? 1 : 2), "pointwise: wrong number of inputs");
+        if (ab.staged) {
+            const int Cp = (int)((aC + 7) / 8 * 8);
+            if (aHW > 64) {
+                dim3 grid((unsigned)ceil_div(aHW, (int64_t)256), (unsigned)ceil_div(Cp, 16), (unsigned)aN);
+                add_stage_kernel<256><<<grid, 256, 0, s>>>((const float*)in[0], (const float*)in[1], (float*)out,
+                                                           (__nv_bfloat16*)ab.staged, (int)aC, (int)aHW, Cp);
+            } else {
+                dim3 grid((unsigned)ceil_div(aHW, (int64_t)64), (unsigned)ceil_div(Cp, 16), (unsigned)aN);
+                add_stage_kernel<64><<<grid, 256, 0, s>>>((const float*)in[0], (const float*)in[1], (float*)out,
+                                                          (__nv_bfloat16*)ab.staged, (int)aC, (int)aHW, Cp);
+            }
+            DB_LAUNCH_CHECK();
+            return;
+        }
         pointwise_launch(op, dtype, dbk::B_TENSOR, in[0], unary ? in[0] : in[1], out, n, s);
     }
 };

@@ -223,10 +223,11 @@ __global__ void bn_infer_coef(const float* __restrict__ scale, const float* __re
 template <int MODE, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                        const float* __restrict__ coef, float* __restrict__ out,
-                                                       BnGeom g, const float* __restrict__ fcoef = nullptr) {
+                                                       BnGeom g, const float* __restrict__ fcoef = nullptr,
+                                                       const float* __restrict__ addend = nullptr) {
     const int64_t V = g.N * g.C * g.HW;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    if ((g.HW & 3) == 0 && (((uintptr_t)out | (uintptr_t)x | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0) {
+    if ((g.HW & 3) == 0 && (((uintptr_t)out | (uintptr_t)x | (uintptr_t)addend | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0) {
         const int64_t nv = V >> 2, hw4 = g.HW >> 2;
         const bool small = nv < (1ll << 31);   // 32-bit index arithmetic: a 64-bit division per vector is most of this loop's ALU work
         const uint32_t hw4u = (uint32_t)hw4, Cu = (uint32_t)g.C;
@@ -257,6 +258,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                 if (RELU) { q.x = m0 ? q.x : 0.f; q.y = m1 ? q.y : 0.f; q.z = m2 ? q.z : 0.f; q.w = m3 ? q.w : 0.f; }
                 r.x = fmaf(q.x, A, fmaf(v.x, B, Cc)); r.y = fmaf(q.y, A, fmaf(v.y, B, Cc));
                 r.z = fmaf(q.z, A, fmaf(v.z, B, Cc)); r.w = fmaf(q.w, A, fmaf(v.w, B, Cc));
+                if (addend) {   // the `add` node that follows, folded in (same rounding as the stand-alone add)
+                    const float4 e = dbk::ld_stream((const float4*)addend + i);
+                    r.x = __fadd_rn(r.x, e.x); r.y = __fadd_rn(r.y, e.y); r.z = __fadd_rn(r.z, e.z); r.w = __fadd_rn(r.w, e.w);
+                }
             }
             dbk::st_stream((float4*)out + i, r);
         }
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                 float q = dy[i];
                 if (RELU) q = fmaf(x[i] - fcoef[c], fcoef[g.C + c], fcoef[2 * g.C + c]) > 0.f ? q : 0.f;
                 r = fmaf(q, coef[g.C + c], fmaf(v, coef[2 * g.C + c], coef[3 * g.C + c]));
+                if (addend) r = __fadd_rn(r, addend[i]);
             }
             out[i] = r;
         }
@@ -291,7 +297,8 @@ template <int MODE, bool RELU, int PX>
 __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ coef, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ staged, BnGeom g, int Cp,
-                                                             const float* __restrict__ fcoef = nullptr) {
+                                                             const float* __restrict__ fcoef = nullptr,
+                                                             const float* __restrict__ addend = nullptr) {
     constexpr int PITCH = PX + 4;            // floats; keeps 128-bit shared stores aligned
     constexpr int V4 = PX / 4;               // float4 per channel row
     constexpr int PER_CH = V4 / 32 > 0 ? V4 / 32 : 1;   // float4 per lane per channel (PX=256: 2, PX=64: 1 for 16 lanes)
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
     const int HW = (int)g.HW, C = (int)g.C;
     const int64_t img = (int64_t)n * C * HW;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const bool vec = (HW & 3) == 0 && ((((uintptr_t)x | (uintptr_t)out | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0);
+    const bool vec = (HW & 3) == 0 && ((((uintptr_t)x | (uintptr_t)out | (uintptr_t)addend | (MODE == 1 ? (uintptr_t)dy : (uintptr_t)0)) & 15) == 0);
     // warp w handles channels c0 + w and c0 + w + 8
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
             return fmaf(q, ca, fmaf(v, cb, cc));
         };
         if (vec) {
-            float4 xv[PER_CH], qv[PER_CH];
+            float4 xv[PER_CH], qv[PER_CH], ev[PER_CH];
 #pragma unroll
             for (int u = 0; u < PER_CH; ++u) {
                 const int p4 = lane + u * 32;                  // float4 index inside the tile row
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
                 const int64_t i = img + (int64_t)c * HW + hw;
                 xv[u] = ok ? *(const float4*)(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 qv[u] = (MODE == 1 && ok) ? *(const float4*)(dy + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ev[u] = (MODE == 1 && ok && addend) ? *(const float4*)(addend + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < PER_CH; ++u) {
@@ -342,6 +350,10 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
                 if (ok) {
                     r.x = apply(xv[u].x, qv[u].x); r.y = apply(xv[u].y, qv[u].y);
                     r.z = apply(xv[u].z, qv[u].z); r.w = apply(xv[u].w, qv[u].w);
+                    if (MODE == 1 && addend) {
+                        r.x = __fadd_rn(r.x, ev[u].x); r.y = __fadd_rn(r.y, ev[u].y);
+                        r.z = __fadd_rn(r.z, ev[u].z); r.w = __fadd_rn(r.w, ev[u].w);
+                    }
                     if (out) *(float4*)(out + img + (int64_t)c * HW + hw) = r;
                 }
                 if (p4 < V4) *(float4*)&tile[cl][p4 * 4] = r;
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(256) bn_apply_stage_kernel(const float* __rest
                 if (c < C && hw < HW) {
                     const int64_t i = img + (int64_t)c * HW + hw;
                     r = apply(x[i], MODE == 1 ? dy[i] : 0.f);
+                    if (MODE == 1 && addend) r = __fadd_rn(r, addend[i]);
                     if (out) out[i] = r;
                 }
                 tile[cl][p] = r;
@@ -380,16 +393,16 @@ namespace {
 // relu: forward -> relu on the result; backward -> gate dy by the forward relu (fcoef).  fp32 == nullptr: no fp32 result.
 template <int MODE>
 static void bn_apply_tiled(const float* x, const float* dy, const float* coef, float* fp32, void* staged, bool relu,
-                           const float* fcoef, const BnGeom& g, cudaStream_t s) {
+                           const float* fcoef, const BnGeom& g, cudaStream_t s, const float* addend = nullptr) {
     const int Cp = (int)((g.C + 7) / 8 * 8);
     if (g.HW > 64) {
         dim3 grid((unsigned)ceil_div(g.HW, 256), (unsigned)ceil_div(Cp, 16), (unsigned)g.N);
-        if (relu) bn_apply_stage_kernel<MODE, true, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
-        else bn_apply_stage_kernel<MODE, false, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+        if (relu) bn_apply_stage_kernel<MODE, true, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef, addend);
+        else bn_apply_stage_kernel<MODE, false, 256><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef, addend);
     } else {
         dim3 grid((unsigned)ceil_div(g.HW, 64), (unsigned)ceil_div(Cp, 16), (unsigned)g.N);
-        if (relu) bn_apply_stage_kernel<MODE, true, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
-        else bn_apply_stage_kernel<MODE, false, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef);
+        if (relu) bn_apply_stage_kernel<MODE, true, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef, addend);
+        else bn_apply_stage_kernel<MODE, false, 64><<<grid, 256, 0, s>>>(x, dy, coef, fp32, (__nv_bfloat16*)staged, g, Cp, fcoef, addend);
     }
     DB_LAUNCH_CHECK();
 }
@@ -482,7 +495,8 @@ struct BnGradKernel : Kernel {
     const void* counters_for = nullptr;
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
     void set_absorbed(const Absorb& a) override {
-        DB_REQUIRE(!a.relu && !a.redirect, "batchNormGrad cannot absorb a relu");
+        DB_REQUIRE(!a.relu, "batchNormGrad cannot absorb a relu");
+        DB_REQUIRE((a.redirect != nullptr) == (a.addend != nullptr), "batchNormGrad: redirect and addend come together");
         ab = a;
     }
     void set_gate_source(const Kernel* forward) override { fwd = forward; }
@@ -518,12 +532,13 @@ struct BnGradKernel : Kernel {
         if (fcoef) bn_stats_kernel<true, true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fin, fcoef);
         else bn_stats_kernel<true><<<dim3((unsigned)g.C, (unsigned)splits), 256, 0, s>>>(x, dy, part, g, splits, fin);
         DB_LAUNCH_CHECK();
+        float* dst = ab.redirect ? ab.redirect : dx;   // with an absorbed add: the add node's buffer receives dx + addend
         if (ab.staged || ab.skip_fp32) {
-            bn_apply_tiled<1>(x, dy, coef, ab.skip_fp32 ? nullptr : dx, ab.staged, fcoef != nullptr, fcoef, g, s);
+            bn_apply_tiled<1>(x, dy, coef, ab.skip_fp32 ? nullptr : dst, ab.staged, fcoef != nullptr, fcoef, g, s, ab.addend);
             return;
         }
-        if (fcoef) bn_apply_kernel<1, true><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g, fcoef);
-        else bn_apply_kernel<1, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dx, g);
+        if (fcoef) bn_apply_kernel<1, true><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dst, g, fcoef, ab.addend);
+        else bn_apply_kernel<1, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>(x, dy, coef, dst, g, nullptr, ab.addend);
         DB_LAUNCH_CHECK();
     }
 };

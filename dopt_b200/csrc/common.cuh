@@ -94,6 +94,7 @@ struct Absorb {
     float* redirect = nullptr;  // write the fp32 result here instead of the kernel's own output (the relu node's buffer)
     bool skip_fp32 = false;     // nobody reads the fp32 result: do not write it
     void* staged = nullptr;     // also write the result as [N][HW][Cp] bf16 here
+    const float* addend = nullptr;   // batchNormGrad: the result is dx + addend (the residual gradient sum that follows it)
 };
 
 struct Kernel {

@@ -64,6 +64,8 @@ struct Node {
     int absorb_relu = -1;       // producer: relu node whose buffer receives relu(result)
     int absorb_stage = -1;      // producer: stage whose NHWC bf16 buffer it also writes
     bool absorb_skip = false;   // producer: its fp32 result (or the relu output it writes instead) has no reader left
+    int absorb_add = -1;        // batchNormGrad: `add` node whose buffer receives dx + addend (the add itself disappears)
+    int absorb_addend = -1;     //                the other operand of that add
     bool msum = false;          // full `sum` run as a row of a batched reduction (msum.cu)
     int msum_a = -1, msum_b = -1;   // operands: sum_i a[i]*b[i] (b = -1: plain sum)
     int gate_from = -1;         // batchNormGrad: batchNormTrain node whose relu gates the incoming gradient (reluGrad absorbed)
@@ -1058,6 +1060,36 @@ static void absorb(Plan& p) {
             if (std::find(st.users.begin(), st.users.end(), rd) == st.users.end()) all_staged = false;
         B.absorb_skip = all_staged;
     }
+    // residual gradient sums: add(batchNormGrad(...).dx, other) where nothing else reads dx -- the batch-norm apply pass adds
+    // `other` before it stores (and stages, when the sum feeds tensor-core convolutions), the add launch and one write +
+    // one read of the activation disappear
+    if (!getenv("DOPT_B200_NO_ADD_ABSORB"))
+        for (size_t i = 0; i < N.size(); ++i) {
+            Node& A = N[i];
+            if (!A.needed || A.alias_of >= 0 || A.type != "add" || A.region >= 0 || A.pw_op < 0 || A.pw_mode != dbk::B_TENSOR ||
+                A.deps.size() != 2 || !A.kernel || A.absorbed_by >= 0)
+                continue;
+            for (int k = 0; k < 2; ++k) {
+                int64_t off = 0, ooff = 0;
+                const int gi = root_of(p, A.deps[k], &off);
+                Node& G = N[gi];
+                if (off != 0 || G.type != "batchNormGrad" || !G.kernel || !G.kernel->can_absorb() || G.absorb_add >= 0) continue;
+                if (N[A.deps[k]].bytes != A.bytes || head_is_output(gi, A.bytes)) continue;
+                if (root_of(p, A.deps[1 - k], &ooff) == gi) continue;
+                auto rd = readers_of_head(gi, A.bytes);
+                if (rd.size() != 1 || rd[0].first != (int)i) continue;
+                if (G.absorb_stage >= 0 || G.absorb_skip) continue;   // (cannot happen: dx has a single fp32 reader)
+                A.absorbed_by = gi;
+                G.absorb_add = (int)i;
+                G.absorb_addend = A.deps[1 - k];
+                if (A.absorb_stage >= 0) {   // the sum was going to be staged by the add kernel: now by the batch-norm pass
+                    G.absorb_stage = A.absorb_stage;
+                    p.stages[G.absorb_stage].producer = gi;
+                    A.absorb_stage = -1;
+                }
+                break;
+            }
+        }
     // reluGrad folded into batchNormGrad: dz = reluGrad(dy, relu(y), y) feeding batchNormGrad(dz, x, scale) of the SAME
     // batch norm whose relu was absorbed above.  The gate [y > 0] is recomputed from x and the forward coefficients, so the
     // reluGrad pass disappears, and when the relu output then has only staged readers left, its fp32 copy does too.
@@ -1419,10 +1451,14 @@ static void run_items(Plan& p, cudaStream_t s) {
             Node& n = N[it.id];
             const void* in[DOPT_B200_MAX_INPUTS];
             for (size_t k = 0; k < n.deps.size(); ++k) in[k] = N[n.in_override[k] >= 0 ? n.in_override[k] : n.deps[k]].ptr;
-            if (n.absorb_relu >= 0 || n.absorb_stage >= 0) {
+            if (n.absorb_relu >= 0 || n.absorb_stage >= 0 || n.absorb_add >= 0) {
                 Absorb ab;
                 ab.relu = n.absorb_relu >= 0;
                 ab.redirect = ab.relu ? (float*)N[n.absorb_relu].ptr : nullptr;
+                if (n.absorb_add >= 0) {
+                    ab.redirect = (float*)N[n.absorb_add].ptr;
+                    ab.addend = (const float*)N[n.absorb_addend].ptr;
+                }
                 ab.skip_fp32 = n.absorb_skip;
                 ab.staged = n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr;
                 n.kernel->set_absorbed(ab);

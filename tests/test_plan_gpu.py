@@ -251,7 +251,7 @@ def test_bn_relu_staging_absorption_is_bit_exact(monkeypatch):
 
 
 @pytest.mark.parametrize("knob", ["DOPT_B200_NO_MSUM", "DOPT_B200_NO_FILTER_STAGE", "DOPT_B200_NO_BN_DIRECT", "DOPT_B200_NO_GATE",
-                                  "DOPT_B200_NO_MERGE", "DOPT_B200_NO_SINGLES", "DOPT_B200_NO_BATCH", "DOPT_B200_NO_ADD_STAGE"])
+                                  "DOPT_B200_NO_MERGE", "DOPT_B200_NO_SINGLES", "DOPT_B200_NO_BATCH", "DOPT_B200_NO_ADD_STAGE", "DOPT_B200_NO_ADD_ABSORB"])
 def test_plan_passes_do_not_change_results(monkeypatch, knob):
     # every lowering pass of the plan compiler can be switched off with an environment knob (read when the plan is built):
     # batched reductions, filter staging, direct BN statistics, the relu gate in batchNormGrad, region merging, single-node

@@ -66,6 +66,46 @@ def main():
         ok = ok and bool(torch.equal(t, ref))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+
+    # second phase: a WRN with batch norm on the bf16 tensor-core path, so that every plan pass (relu / staging / add absorbed
+    # into batch norm, gradient buckets, filter staging, batched reductions) runs under data parallelism.  BN statistics
+    # are per rank, so there is no single-process oracle for this one; what must hold is that the replicas stay bit-identical
+    # (every rank applies the same averaged gradients) and that the loss is finite and falls.
+    H.reset()
+    H.set_data_parallel_world(WORLD)
+    H.set_math(db.MATH_BF16)
+    H.seed(13)
+    xw, yw = H.float32((8, 3, 16, 16)), H.float32((8, 10))
+    preds = H.wide_resnet(xw, 10, 4).dense(10).softmax()
+    netw = H.Network([xw], [preds])
+    lossw = H.cross_entropy(preds.train_output, yw) + netw.param_loss
+    updw = H.Updater(H.SGD, [lossw], network=netw, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+    rw = np.random.RandomState(100 + RANK)
+    batches = [((rw.rand(8, 3, 16, 16) * 2 - 1).astype(F), np.eye(10, dtype=F)[rw.randint(0, 10, 8)]) for _ in range(2)]
+    losses = [float(updw.step({xw: batches[s % 2][0], yw: batches[s % 2][1]})[0]) for s in range(6)]
+    okw = all(np.isfinite(l) for l in losses) and losses[-1] < losses[0]
+    differing = []
+    for k_, p_ in enumerate(netw.params):
+        t = torch.from_numpy(p_.get()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        if not bool(torch.equal(t, ref)):
+            differing.append((k_, tuple(p_.shape)))
+    # the running mean / variance of batch norm are per-rank by design (the reference has no cross-device BN): they are the
+    # rank-1 [C] parameters that follow a [1,C,1,1] scale and a [C] bias
+    shapes = [tuple(p_.shape) for p_ in netw.params]
+    per_rank_ok = set()
+    for k_ in range(len(shapes) - 3):
+        if len(shapes[k_]) == 4 and shapes[k_][0] == 1 and shapes[k_][2:] == (1, 1):
+            per_rank_ok.update([k_ + 2, k_ + 3])
+    bad = [d for d in differing if d[0] not in per_rank_ok]
+    if RANK == 1 and (bad or not okw):
+        print("dp_check WRN phase: losses", losses, "differing trainable params", bad[:8], flush=True)
+    okw = okw and not bad
+    flagw = torch.tensor([1 if okw else 0], device="cuda")
+    dist.all_reduce(flagw, op=dist.ReduceOp.MIN)
+    flag = torch.minimum(flag, flagw)
+    wrn_launches = updw.stats()["launches"]
     if RANK == 0:
         H.set_data_parallel_world(1)
         x1, y1, net1, upd1 = build(total)
@@ -77,8 +117,9 @@ def main():
             want = oracle.value_of(p)
             worst = max(worst, float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)))
         good = bool(flag.item()) and worst < 1e-4
-        print("dp_check world=%d replicas_identical=%s max_rel_err_vs_single_process_oracle=%.3g launches=%d -> %s"
-              % (WORLD, bool(flag.item()), worst, stats["launches"], "PASS" if good else "FAIL"))
+        print("dp_check world=%d replicas_identical=%s (incl. WRN-10-4 bf16: %s, %d launches) "
+              "max_rel_err_vs_single_process_oracle=%.3g launches=%d -> %s"
+              % (WORLD, bool(flag.item()), bool(flagw.item()), wrn_launches, worst, stats["launches"], "PASS" if good else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
 

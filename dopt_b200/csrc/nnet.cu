@@ -14,6 +14,7 @@
 // All are HBM-bound; bytes per launch are listed at each kernel.
 #include "common.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace db {
 
@@ -316,9 +317,13 @@ struct MaxpoolKernel : Kernel {
 };
 struct MaxpoolGradKernel : Kernel {
     int64_t maps;
-    int H, W, OH, OW, dh, dw;
+    int H, W, OH, OW, dh, dw, tie;
     MaxpoolGradKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 3 && d.inputs[2].rank == 4, "maxpoolGrad: deps are [parentGrad, y, x]");
+        // DOPT_B200_POOL_TIES=first selects tie_mode 1 at kernel construction; the default (every tied element receives
+        // the gradient) is what tests/test_cudnn_replay_gpu.py checks against cuDNN's own PoolingBackward
+        tie = g_pool_tie_mode;
+        if (const char* e = getenv("DOPT_B200_POOL_TIES")) tie = (e[0] == 'f' || e[0] == '1') ? 1 : 0;
         const auto& x = d.inputs[2];
         dh = (int)d.pool_dims[0];
         dw = (int)d.pool_dims[1];
@@ -335,7 +340,7 @@ struct MaxpoolGradKernel : Kernel {
         if (n == 0) return;
         maxpool_grad_kernel<<<stream_grid(n, 256, 16), 256, 0, s>>>((const float*)in[0], (const float*)in[1],
                                                                     (const float*)in[2], (float*)out, maps, H, W, OH,
-                                                                    OW, dh, dw, g_pool_tie_mode);
+                                                                    OW, dh, dw, tie);
         DB_LAUNCH_CHECK();
     }
 };

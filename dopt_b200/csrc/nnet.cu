@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
 }
 
 // ---- maxpoolGrad: (V/d^2 + V + V)*4 B.  thread per INPUT element: dx = dy[window] where x equals the window max --------
-// tie_mode 0: every element equal to the maximum receives dy (what the windowed comparison of cuDNN's legacy backward does);
-// tie_mode 1: only the first (row-major) maximum does.
+// tie_mode 1 (default): only the first (row-major) element equal to the window maximum receives dy -- what cuDNN's
+// PoolingBackward does for CUDNN_POOLING_MAX, measured on the GPU box against the replayed reference call
+// (tests/test_cudnn_replay_gpu.py::test_maxpool_grad_tie_rule_is_cudnns, profiles/r01p_cudnn_replay_report.jsonl);
+// tie_mode 0: every tied element does.  The scan over the window only runs for elements that equal the maximum.
 __global__ void __launch_bounds__(256) maxpool_grad_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                            const float* __restrict__ x, float* __restrict__ dx,
                                                            int64_t maps, int H, int W, int OH, int OW, int dh, int dw,
@@ -216,7 +218,7 @@ void relu_grad_launch(const float* dy, const float* x, float* dx, int64_t n, cud
     DB_LAUNCH_CHECK();
 }
 
-static int g_pool_tie_mode = 0;
+static int g_pool_tie_mode = 1;
 
 namespace {
 
@@ -320,10 +322,10 @@ struct MaxpoolGradKernel : Kernel {
     int H, W, OH, OW, dh, dw, tie;
     MaxpoolGradKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 3 && d.inputs[2].rank == 4, "maxpoolGrad: deps are [parentGrad, y, x]");
-        // DOPT_B200_POOL_TIES=first selects tie_mode 1 at kernel construction; the default (every tied element receives
-        // the gradient) is what tests/test_cudnn_replay_gpu.py checks against cuDNN's own PoolingBackward
+        // DOPT_B200_POOL_TIES=all|first overrides the rule at kernel construction (diagnostics; the default, first, is
+        // the one tests/test_cudnn_replay_gpu.py measures cuDNN's own PoolingBackward to follow)
         tie = g_pool_tie_mode;
-        if (const char* e = getenv("DOPT_B200_POOL_TIES")) tie = (e[0] == 'f' || e[0] == '1') ? 1 : 0;
+        if (const char* e = getenv("DOPT_B200_POOL_TIES")) tie = (e[0] == 'a' || e[0] == '0') ? 0 : 1;
         const auto& x = d.inputs[2];
         dh = (int)d.pool_dims[0];
         dw = (int)d.pool_dims[1];

@@ -1,7 +1,9 @@
 // random.cu -- `uniform` (cuda/source/dopt/cuda/random.d:56-83: curandGenerateUniform, default generator, seeded from
 // unpredictableSeed).  cuRAND's uniform is (0, 1]; so is this one.  The reference is unseeded, so parity is at the level of
 // the distribution, not the stream.  Counter-based Philox-4x32-10: thread i produces elements 4i..4i+3.  Write-only:
-// V*4 B per launch.
+// V*4 B per launch.  The per-kernel call counter (so that every execution draws fresh numbers) lives in DEVICE memory and
+// is advanced by a one-thread launch that follows the generator on the same stream: a plan that contains `uniform`
+// (dropout) can therefore be captured in a CUDA graph and still produces a new mask on every replay.
 #include "common.cuh"
 #include <random>
 
@@ -15,7 +17,9 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
-__global__ void __launch_bounds__(256) uniform_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t call) {
+__global__ void __launch_bounds__(256) uniform_kernel(float* __restrict__ out, int64_t n, uint64_t seed,
+                                                      const uint64_t* __restrict__ calls) {
+    const uint64_t call = *calls;
     int64_t nq = (n + 3) >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
@@ -35,10 +39,14 @@ __global__ void __launch_bounds__(256) uniform_kernel(float* __restrict__ out, i
     }
 }
 
+__global__ void uniform_advance_kernel(uint64_t* calls) { *calls += 1; }
+
 namespace {
 struct UniformKernel : Kernel {
     int64_t n;
-    uint64_t seed, calls = 0;
+    uint64_t seed;
+    uint64_t* calls = nullptr;   // device-resident execution counter
+    ~UniformKernel() override { if (calls) cudaFree(calls); }
     UniformKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 0 && d.output.dtype == DOPT_B200_FLOAT32, "uniform: no operands, float32 result");
         n = volume(d.output);
@@ -47,11 +55,15 @@ struct UniformKernel : Kernel {
             std::random_device rd;
             seed = ((uint64_t)rd() << 32) | rd();
         }
+        DB_CUDA(cudaMalloc(&calls, sizeof(uint64_t)));
+        DB_CUDA(cudaMemset(calls, 0, sizeof(uint64_t)));
     }
     void run(const void* const*, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == 0, "uniform: no inputs");
         if (n == 0) return;
-        uniform_kernel<<<stream_grid(ceil_div(n, 4), 256, 8), 256, 0, s>>>((float*)out, n, seed, calls++);
+        uniform_kernel<<<stream_grid(ceil_div(n, 4), 256, 8), 256, 0, s>>>((float*)out, n, seed, calls);
+        DB_LAUNCH_CHECK();
+        uniform_advance_kernel<<<1, 1, 0, s>>>(calls);
         DB_LAUNCH_CHECK();
     }
 };

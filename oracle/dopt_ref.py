@@ -21,8 +21,10 @@ Pinning: tests/test_oracle_golden.py checks this module against every known-answ
 tests (convolution, maxpool, softmax, matmul, sum, argmin, maxElement, slice, pad, reshape, transpose, repeat, d(x*x)/dx,
 sliceGrad, the CUDA smoke test and the batch-norm running-mean test).  Ops with no reference test (conv gradients,
 maxpoolGrad tie routing, softmaxGrad, relu*, addBias*, batchNormGrad/Inference, optimiser numerics) are "parity
-unpinned" by the reference; for those the oracle is cross-checked against float64 finite differences / closed forms in
-the same test file and, on the GPU box, against torch's cuDNN-backed fp32 ops.
+unpinned" by the reference's own tests; for those the oracle is cross-checked against float64 finite differences / closed
+forms in the same test file and, on the GPU box, against the reference CUDA backend's own cuDNN / cuBLAS calls replayed
+from C++ (oracle/cudnn_replay.cpp, tests/test_cudnn_replay_gpu.py: conv family, pooling incl. tie routing, softmax, relu,
+bias, batch norm -- agreement 1e-6 or better, measured errors in profiles/r01p_cudnn_replay_report.jsonl).
 
 All arithmetic is float32 unless a comment says otherwise (reductions whose order cuDNN does not document accumulate
 in float64 and round once; the parity tolerance covers the difference).
@@ -226,9 +228,11 @@ def maxpool(x, dims):
     return v.max(axis=(3, 5)).astype(x.dtype)
 
 
-def maxpool_grad(dy, y, x, dims, tie_all=True):
-    """cudnnPoolingBackward(y, dy, x) for CUDNN_POOLING_MAX (cudnn7.d:309-333): dy goes to the element(s) equal to the
-    window maximum.  tie_all=True routes to every tied element, False only to the first in row-major order."""
+def maxpool_grad(dy, y, x, dims, tie_all=False):
+    """cudnnPoolingBackward(y, dy, x) for CUDNN_POOLING_MAX (cudnn7.d:309-333): dy goes to the element equal to the
+    window maximum.  On ties cuDNN routes it to the FIRST such element in row-major window order only (measured with the
+    replayed call on a B200, cuDNN 9.22: tests/test_cudnn_replay_gpu.py::test_maxpool_grad_tie_rule_is_cudnns); tie_all=True
+    gives the other plausible rule (every tied element) for comparison."""
     dh, dw = dims
     N, Cc, H, W = x.shape
     OH, OW = H // dh, W // dw

@@ -293,8 +293,8 @@ def test_maxpool_and_grad(shape, dims):
 
 
 def test_maxpool_grad_ties_after_relu():
-    # all-zero windows are common after ReLU; every tied element receives the gradient (see test_cudnn_semantics_gpu.py
-    # for the measurement of what cuDNN itself does)
+    # all-zero windows are common after ReLU; only the first tied element receives the gradient, as in cuDNN
+    # (measured in test_cudnn_replay_gpu.py::test_maxpool_grad_tie_rule_is_cudnns)
     x = np.zeros((2, 3, 4, 4), F)
     x[0, 0, 0, 1] = 2.0
     y = R.maxpool(x, [2, 2])

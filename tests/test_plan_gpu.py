@@ -320,3 +320,22 @@ def test_inference_plan_and_checkpoint_roundtrip(tmp_path):
         np.testing.assert_array_equal(p.get(), b)
     import os
     assert os.path.getsize(path) == 4 * sum(p.volume for p in net.params)   # raw fp32, no header (networks.d:130-164)
+
+
+@pytest.mark.parametrize("flags", [0, FUSE | GRAPH], ids=["plain", "fused+graph"])
+def test_uniform_draws_fresh_numbers_every_execution(flags):
+    """`uniform` (cuda/source/dopt/cuda/random.d:56-83) feeds dropout masks: every plan execution must draw new numbers, also
+    when the step is replayed from a CUDA graph (the call counter lives in device memory)."""
+    H.set_plan_flags(flags)
+    u = H.create("uniform", [], shape=[1 << 16])
+    keep = H.binary("gt", u, H.constant((1 << 16,), np.full(1 << 16, 0.25, F)))     # dropout's mask (layers/dropout.d:22-23)
+    p = H.Plan([u, keep])
+    draws = [p.execute() for _ in range(5)]
+    for v, k in draws:
+        assert v.min() > 0.0 and v.max() <= 1.0
+        assert abs(float(v.mean()) - 0.5) < 1e-2
+        np.testing.assert_array_equal(k, (v > 0.25).astype(F))
+        assert abs(float(k.mean()) - 0.75) < 1e-2
+    for i in range(len(draws)):
+        for j in range(i):
+            assert not np.array_equal(draws[i][0], draws[j][0])

@@ -85,6 +85,57 @@ def synthetic_batch(batch, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# per-kernel-class rooflines (the north star asks for the memory-bound classes as a fraction of HBM bandwidth)
+# ---------------------------------------------------------------------------------------------------------------------
+def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs):
+    """ALGORITHMIC bytes per step of the memory-bound op classes, from the exported dopt graph and SURVEY.md section 8(d)'s
+    per-element figures at the fp32 boundary (batchNormTrain 2V*4, batchNormGrad 3V*4 -- the relu / reluGrad / NHWC staging
+    the plan folds into those passes add no algorithmic bytes --, residual add 3V*4, SGD+momentum 5P*4), divided by the
+    device time the plan's profiler attributes to that op type inside the training step.
+
+    nodes: H.export(plan outputs); prof_us / prof_n: per-op-type microseconds and launches PER STEP."""
+    by_id = dict((n["id"], n) for n in nodes)
+
+    def vol(n):
+        v = 1
+        for d in n["shape"]:
+            v *= d
+        return v
+
+    # forward nodes = ancestors of the loss
+    fwd, stack = set(), [loss_id]
+    while stack:
+        i = stack.pop()
+        if i in fwd:
+            continue
+        fwd.add(i)
+        stack.extend(by_id[i]["deps"])
+    v_bn = sum(vol(by_id[n["deps"][0]]) for n in nodes if n["type"] == "batchNormTrain")
+    v_bng = sum(vol(by_id[n["deps"][1]]) for n in nodes if n["type"] == "batchNormGrad")
+    res_adds = [n for n in nodes if n["type"] == "add" and len(n["shape"]) == 4 and n["id"] in fwd]
+    out = {}
+
+    def put(name, ops, alg_bytes, note):
+        us = sum(prof_us.get(o, 0.0) for o in ops)
+        if us <= 0 or alg_bytes <= 0:
+            return
+        gbs = alg_bytes / (us * 1e-6) / 1e9
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                     "alg_bytes_per_step": int(alg_bytes), "us_per_step": us,
+                     "launches_per_step": int(sum(prof_n.get(o, 0) for o in ops)), "what": note}
+
+    put("batchNormTrain", ["batchNormTrain"], 2 * v_bn * 4,
+        "2V*4 B; the pass also applies relu and writes the NHWC bf16 operand copy of the next convolution")
+    put("batchNormGrad", ["batchNormGrad"], 3 * v_bng * 4,
+        "3V*4 B; the pass also applies the relu gate, the residual-gradient add and the NHWC bf16 staging of dx")
+    if res_adds and prof_n.get("add", 0) == len(res_adds):
+        put("residual_add", ["add"], 3 * sum(vol(n) for n in res_adds) * 4, "3V*4 B, forward residual sums (+ staging)")
+    put("optimiser", ["fusedRegion"], 5 * n_params * 4,
+        "5P*4 B (SGD+momentum); the fused regions also carry the weight-decay gradient and the loss chain")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # CPU reference arm / baseline
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, sample_batch, standalone=True):
@@ -335,6 +386,17 @@ def main():
                                       "(profiles/r01_final_tc_dram.csv), per step like `achieved`",
                     "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                     "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3}
+    classes = None
+    if RANK == 0:
+        try:
+            plan_outs, _ = upd.plan_outputs()
+            nodes = H.export(plan_outs)
+            loss_id = [n["id"] for n in nodes if n["op"].h == plan_outs[0].h][0]
+            per_us = dict((k, v / 2.0) for k, v in prof.items() if "#" not in k)
+            per_n = dict((k[:-2], v / 2.0) for k, v in prof.items() if k.endswith("#n"))
+            classes = class_rooflines(nodes, loss_id, per_us, per_n, n_params, peaks()["hbm_gbs"])
+        except Exception as e:  # diagnostics only: never lose the bench line over it
+            classes = {"error": repr(e)}
     barrier()
 
     if RANK == 0:
@@ -358,7 +420,8 @@ def main():
                     "h2d_bytes_per_step": int(nbytes[0] + nbytes[1]), "d2h_bytes_per_step": int(4 + pred_out.nbytes),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "launches_per_step": st["launches"], "plan_nodes": st["lowered_nodes"],
-            "plan_device_bytes": st["device_bytes"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "plan_device_bytes": st["device_bytes"], "clocks": clocks, "roofline": roof, "roofline_classes": classes,
+            "cpu_baseline": cpu,
             "loss_first": first_loss, "loss_last": last_loss,
             "per_op_us_per_step": dict((k, [v / 2.0, prof.get(k + "#n", 0) // 2]) for k, v in
                                        sorted(((k, v) for k, v in prof.items() if "#" not in k and k != "tc_kernel_launches"),

@@ -16,7 +16,7 @@ import ctypes as C
 from . import _lib
 
 __all__ = ["lib", "DoptError", "check", "make_op", "CUDAKernel", "run_op", "list_operations", "FLOAT32", "INT32",
-           "MATH_DEFAULT", "MATH_FP32", "MATH_BF16"]
+           "MATH_DEFAULT", "MATH_FP32", "MATH_BF16", "image_transform", "one_hot", "jitter_sample"]
 
 FLOAT32, INT32 = _lib.FLOAT32, _lib.INT32
 MATH_DEFAULT, MATH_FP32, MATH_BF16 = _lib.MATH_DEFAULT, _lib.MATH_FP32, _lib.MATH_BF16
@@ -141,4 +141,44 @@ def run_op(op_type, inputs, out_shape, out_dtype=FLOAT32, math=MATH_DEFAULT, **a
     k = CUDAKernel(op)
     k.execute(ins, out, torch.cuda.current_stream().cuda_stream)
     k.close()
+    return out
+
+
+# ---- on-device input pipeline (include/dopt_b200.h, "on-device input pipeline") ------------------------------------------
+def image_transform(src, jitter_x=0, jitter_y=0, per_image=None, stream=None):
+    """src: torch CUDA tensor [N, C, H, W], uint8 (normalised x/128-1 on the fly) or float32.  per_image: None or an int32
+    CUDA tensor [N, 4] = (x_off, y_off, flip_x, flip_y).  Returns the float32 NCHW batch the plan reads."""
+    import torch
+
+    src = src.contiguous()
+    n, c, h, w = (int(v) for v in src.shape)
+    dst = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+    fn = {torch.uint8: lib.dopt_b200_image_transform_u8, torch.float32: lib.dopt_b200_image_transform_f32}[src.dtype]
+    if per_image is not None:
+        per_image = per_image.contiguous()
+        assert per_image.dtype == torch.int32 and tuple(per_image.shape) == (n, 4)
+    check(fn(src.data_ptr(), dst.data_ptr(), n, c, h, w, int(jitter_x), int(jitter_y),
+             per_image.data_ptr() if per_image is not None else None,
+             stream if stream is not None else torch.cuda.current_stream().cuda_stream))
+    return dst
+
+
+def one_hot(labels, classes, stream=None):
+    import torch
+
+    labels = labels.contiguous()
+    assert labels.dtype == torch.uint8
+    dst = torch.empty((labels.numel(), int(classes)), dtype=torch.float32, device=labels.device)
+    check(lib.dopt_b200_one_hot_u8(labels.data_ptr(), dst.data_ptr(), labels.numel(), int(classes),
+                                   stream if stream is not None else torch.cuda.current_stream().cuda_stream))
+    return dst
+
+
+def jitter_sample(n, jitter_x, jitter_y, flip_x, flip_y, seed, call=0, stream=None):
+    import torch
+
+    out = torch.empty((int(n), 4), dtype=torch.int32, device="cuda")
+    check(lib.dopt_b200_jitter_sample(out.data_ptr(), int(n), int(jitter_x), int(jitter_y), int(bool(flip_x)),
+                                      int(bool(flip_y)), int(seed), int(call),
+                                      stream if stream is not None else torch.cuda.current_stream().cuda_stream))
     return out

@@ -52,12 +52,17 @@ class Param(C.Structure):
                 ("n", C.c_int64)]
 
 
+class Jitter(C.Structure):
+    _fields_ = [("x_off", C.c_int32), ("y_off", C.c_int32), ("flip_x", C.c_int32), ("flip_y", C.c_int32)]
+
+
 # every symbol include/dopt_b200.h declares; tests/test_abi.py checks the library exports each of them
 SYMBOLS = [
     "dopt_b200_init", "dopt_b200_last_error", "dopt_b200_version", "dopt_b200_device_info",
     "dopt_b200_set_default_math", "dopt_b200_launch_count", "dopt_b200_tc_profile", "dopt_b200_list_operations", "dopt_b200_has_operation",
     "dopt_b200_kernel_create", "dopt_b200_kernel_execute", "dopt_b200_kernel_destroy",
     "dopt_b200_sgd_update", "dopt_b200_adam_update",
+    "dopt_b200_image_transform_u8", "dopt_b200_image_transform_f32", "dopt_b200_one_hot_u8", "dopt_b200_jitter_sample",
     "dopt_b200_plan_create", "dopt_b200_plan_add_node", "dopt_b200_plan_set_outputs", "dopt_b200_plan_finalize",
     "dopt_b200_plan_execute", "dopt_b200_plan_stats", "dopt_b200_plan_profile", "dopt_b200_plan_destroy",
     "dopt_b200_comm_unique_id", "dopt_b200_comm_init", "dopt_b200_comm_world_size", "dopt_b200_comm_rank",
@@ -88,6 +93,11 @@ def load():
     fp = vp
     lib.dopt_b200_sgd_update.argtypes = [C.POINTER(Param), C.c_int, fp, fp, C.c_int, C.c_float, vp]
     lib.dopt_b200_adam_update.argtypes = [C.POINTER(Param), C.c_int, fp, fp, fp, fp, fp, fp, C.c_int, C.c_float, vp]
+    img = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.dopt_b200_image_transform_u8.argtypes = img
+    lib.dopt_b200_image_transform_f32.argtypes = img
+    lib.dopt_b200_one_hot_u8.argtypes = [vp, vp, i64, C.c_int, vp]
+    lib.dopt_b200_jitter_sample.argtypes = [vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp]
     lib.dopt_b200_plan_create.argtypes = [C.POINTER(vp)]
     lib.dopt_b200_plan_add_node.argtypes = [vp, C.POINTER(Op), C.POINTER(i32), C.c_int, vp]
     lib.dopt_b200_plan_set_outputs.argtypes = [vp, C.POINTER(i32), C.c_int]

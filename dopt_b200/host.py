@@ -46,6 +46,7 @@ _h.dh_conv2d.argtypes = [C.c_int, C.c_int64, i64p, i64p, i64p, C.c_float, C.c_in
 _h.dh_dense.argtypes = [C.c_int, C.c_int64, C.c_float, C.c_int]
 _h.dh_batch_norm.argtypes = [C.c_int, C.c_float]
 _h.dh_max_pool.argtypes = [C.c_int, i64p]
+_h.dh_dropout.argtypes = [C.c_int, C.c_float]
 _h.dh_wide_resnet.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_float]
 _h.dh_vgg19.argtypes = [C.c_int, i64p, C.c_int, C.c_int]
 _h.dh_network.argtypes = [i32p, C.c_int, i32p, C.c_int]
@@ -307,6 +308,7 @@ class Layer(object):
     def batch_norm(self, momentum=0.9): return Layer(_h.dh_batch_norm(self.h, momentum))
     def relu(self): return Layer(_h.dh_relu(self.h))
     def max_pool(self, dims): return Layer(_h.dh_max_pool(self.h, _i64(dims)))
+    def dropout(self, drop_prob): return Layer(_h.dh_dropout(self.h, float(drop_prob)))
     def softmax(self): return Layer(_h.dh_softmax(self.h))
 
 

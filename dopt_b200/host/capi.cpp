@@ -328,6 +328,11 @@ int dh_max_pool(int in, const int64_t* dims) {
     return addLayer(nnet::maxPool(layer(in), sizes(dims, 2)));
     DH_CATCH(-1)
 }
+int dh_dropout(int in, float drop_prob) {
+    DH_TRY
+    return addLayer(nnet::dropout(layer(in), drop_prob));
+    DH_CATCH(-1)
+}
 int dh_softmax(int in) {
     DH_TRY
     return addLayer(nnet::softmax(layer(in)));

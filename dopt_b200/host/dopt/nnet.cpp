@@ -140,6 +140,17 @@ LayerPtr maxPool(LayerPtr input, std::vector<size_t> dims) {
     auto yTr = input->output() == input->trainOutput() ? y : dopt::maxpool(input->trainOutput(), dims);
     return std::make_shared<Layer>(std::vector<LayerPtr>{input}, y, yTr, std::vector<Parameter>{});
 }
+LayerPtr dropout(LayerPtr input, float dropProb) {
+    // nnet/layers/dropout.d:14-29: train output = (uniform > dropProb) * x with a fresh mask per execution; test output =
+    // x * (1 - dropProb).  dropMask and scale are plain variables filled with the constant, exactly as in the reference.
+    auto x = input->output();
+    auto xTr = input->trainOutput();
+    auto dropMask = float32(xTr->shape(), std::vector<float>(xTr->volume(), dropProb));
+    auto yTr = gt(uniformSample(xTr->shape()), dropMask) * xTr;
+    auto scale = float32(x->shape(), std::vector<float>(x->volume(), 1.0f - dropProb));
+    auto y = x * scale;
+    return std::make_shared<Layer>(std::vector<LayerPtr>{input}, y, yTr, std::vector<Parameter>{});
+}
 LayerPtr softmax(LayerPtr input) {
     auto y = dopt::softmax(input->output());
     auto yTr = input->output() == input->trainOutput() ? y : dopt::softmax(input->trainOutput());

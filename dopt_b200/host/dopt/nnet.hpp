@@ -1,7 +1,7 @@
 // dopt/nnet.hpp -- C++ mirror of the parts of dopt.nnet that generate the hot path's graphs: Layer, the layer
 // constructors, DAGNetwork, the losses and the VGG / Wide-ResNet model builders.  Host-only graph construction; see the
 // .cpp for per-function citations.  Research regularisers (maxgain / Lipschitz / spectral decay projections,
-// nnet/lipschitz.d) and dropout are out of scope (default-off in every BASELINE config).
+// nnet/lipschitz.d) are out of scope (default-off in every BASELINE config).
 #pragma once
 #include <random>
 
@@ -67,6 +67,7 @@ LayerPtr dense(LayerPtr input, size_t numOutputs, DenseOptions opts = DenseOptio
 LayerPtr batchNorm(LayerPtr input, BatchNormOptions opts = BatchNormOptions());
 LayerPtr relu(LayerPtr input);
 LayerPtr maxPool(LayerPtr input, std::vector<size_t> dims);
+LayerPtr dropout(LayerPtr input, float dropProb);   // nnet/layers/dropout.d:14-29
 LayerPtr softmax(LayerPtr input);
 
 class DAGNetwork {   // nnet/networks.d:24-128

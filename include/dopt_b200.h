@@ -131,6 +131,29 @@ int dopt_b200_adam_update(const dopt_b200_param* params, int n_params, const flo
                           const float* beta2, const float* eps, float* b1, float* b2, int amsgrad, float grad_scale,
                           void* stream);
 
+/* ---- on-device input pipeline (the caller's side of the hot path) ---------------------------------------------------
+ * Replaces the host loops that prepare every batch in the reference: the loaders' byte -> float normalisation
+ * `x / 128.0f - 1.0f` and one-hot labels (nnet/source/dopt/nnet/data/cifar.d:50-55) and ImageTransformer.getBatch
+ * (nnet/source/dopt/nnet/data/imagetransformer.d:45-138: reflect-pad by jitter, crop at a random offset, random mirror).
+ * The batch is uploaded as bytes and ONE launch writes the NCHW fp32 tensor the plan reads.  Bit-exact with the host loops.
+ * All pointers are DEVICE pointers.  per_image == NULL means no jitter and no flip (plain normalisation / copy). */
+typedef struct {
+    int32_t x_off, y_off;     /* crop offset in the reflect-padded image: uniform(0, 2*jitter), imagetransformer.d:101-102 */
+    int32_t flip_x, flip_y;   /* mirror rows / columns after cropping, imagetransformer.d:118-137                          */
+} dopt_b200_jitter;
+
+int dopt_b200_image_transform_u8(const uint8_t* src, float* dst, int64_t n, int c, int h, int w, int jitter_x, int jitter_y,
+                                 const dopt_b200_jitter* per_image, void* stream);
+/* the same for an already normalised float batch (what ImageTransformer itself receives); src != dst */
+int dopt_b200_image_transform_f32(const float* src, float* dst, int64_t n, int c, int h, int w, int jitter_x, int jitter_y,
+                                  const dopt_b200_jitter* per_image, void* stream);
+/* dst[n, classes] = one-hot of labels[n] (cifar.d:52-55) */
+int dopt_b200_one_hot_u8(const uint8_t* labels, float* dst, int64_t n, int classes, void* stream);
+/* fills out[n] on the device with the reference's distributions (Philox-4x32-10 keyed by seed, counter = (image, call));
+ * flip_x / flip_y enable the respective mirror (ImageTransformer's flipX / flipY constructor flags) */
+int dopt_b200_jitter_sample(dopt_b200_jitter* out, int64_t n, int jitter_x, int jitter_y, int flip_x, int flip_y,
+                            uint64_t seed, uint64_t call, void* stream);
+
 /* ---- whole-plan compiler: CUDAPlan ---------------------------------------------------------------------------------
  * The host serialises the topologically sorted graph once (node ids are the order of add_node calls) and the library
  * lowers it: reshape/slice aliasing, BN pack/unpack removal, scalar-broadcast folding, pointwise fusion, buffer

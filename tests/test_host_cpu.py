@@ -238,6 +238,21 @@ def test_wrn_graph_inventory():
     assert ts.count("sum") == len(convs) + 1                          # weight decay per conv + the cross-entropy sum
 
 
+def test_dropout_layer_graph():
+    """nnet/layers/dropout.d:14-29: train output = (uniform > p) * x, test output = x * (1 - p); the mask is not
+    differentiable, so the gradient wrt x is parentGrad * mask."""
+    x = H.float32((4, 6), np.arange(24))
+    l = H.data_source(x).dropout(0.25)
+    tr = H.export([l.train_output])
+    assert [n["type"] for n in tr] == ["uniform", "variable", "gt", "variable", "mul"]
+    assert tr[0]["attrs"]["shape"] == [4, 6]
+    np.testing.assert_array_equal(tr[1]["op"].get(), np.full((4, 6), 0.25, F))
+    np.testing.assert_allclose(ev([l.output])[0], np.arange(24, dtype=F).reshape(4, 6) * F(0.75))
+    g = H.grad(H.sum_(l.train_output), [x])[0]
+    ts = types([g])
+    assert "gt" in ts and "uniform" in ts and ts.count("uniform") == 1       # the SAME mask node gates the gradient
+
+
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
     loss = H.sum_(w * w)

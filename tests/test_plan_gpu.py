@@ -339,3 +339,27 @@ def test_uniform_draws_fresh_numbers_every_execution(flags):
     for i in range(len(draws)):
         for j in range(i):
             assert not np.array_equal(draws[i][0], draws[j][0])
+
+
+@pytest.mark.parametrize("flags", [0, FUSE | GRAPH], ids=["plain", "fused+graph"])
+def test_dropout_layer_trains_with_a_fresh_consistent_mask(flags):
+    """nnet/layers/dropout.d:14-29.  Within one execution the forward mask and the mask gating the gradient are the same
+    draw (one `uniform` node); across executions the mask changes; the kept fraction is 1 - dropProb."""
+    H.set_plan_flags(flags)
+    xs = (np.random.RandomState(9).rand(64, 512) + 1.0).astype(F)            # strictly positive: kept <=> output != 0
+    x = H.float32((64, 512), xs)
+    l = H.data_source(x).dropout(0.3)
+    g = H.grad(H.sum_(l.train_output), [x])[0]
+    p = H.Plan([l.train_output, g, l.output])
+    masks = []
+    for _ in range(4):
+        y, gx, y_test = p.execute()
+        mask = (y != 0).astype(F)
+        np.testing.assert_array_equal(y, mask * xs)
+        np.testing.assert_array_equal(gx, mask)
+        np.testing.assert_allclose(y_test, xs * F(0.7), rtol=1e-6)
+        assert abs(float(mask.mean()) - 0.7) < 0.02
+        masks.append(mask)
+    for i in range(len(masks)):
+        for j in range(i):
+            assert not np.array_equal(masks[i], masks[j])

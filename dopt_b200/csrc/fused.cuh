@@ -46,6 +46,7 @@ struct FzLaunch {
     std::vector<FzRow> rows;      // host copy
     FzRow* dev_rows = nullptr;    // device copy (uploaded lazily, re-uploaded when pointers change)
     int64_t n_chunks = 0;
+    int static_id = -1;           // index into fused.cu's table of pre-compiled programs, -1 = interpreted
     bool dirty = true;
 };
 

@@ -1269,8 +1269,18 @@ static void build(Plan& p) {
                 fprintf(stderr, "PLAN %-9s #%d %s vol=%lld <-%s  users:%s\n", kinds[it.kind], it.id, n.type.c_str(),
                         (long long)volume(n.op.output), deps.c_str(), users.c_str());
             } else if (it.kind == ITEM_FUSED) {
-                fprintf(stderr, "PLAN fused     launch %d rows=%zu instr=%d\n", it.id, p.launches[it.id].rows.size(),
-                        p.launches[it.id].prog.n_instr);
+                const FzLaunch& L = p.launches[it.id];
+                const FzProgram& g = L.prog;
+                fprintf(stderr, "PLAN fused     launch %d rows=%zu instr=%d tensors=%d scalars=%d outputs=%d\n", it.id,
+                        L.rows.size(), g.n_instr, g.n_tensors, g.n_scalars, g.n_outputs);
+                // the program itself: "op:a,b>dst" per instruction, then the output registers (fused.cuh encoding)
+                std::string prog;
+                for (int k = 0; k < g.n_instr; ++k)
+                    prog += " " + std::to_string(g.instr[k].op) + ":" + std::to_string(g.instr[k].a) + "," +
+                            std::to_string(g.instr[k].b) + ">" + std::to_string(g.instr[k].dst);
+                prog += " | out";
+                for (int o = 0; o < g.n_outputs; ++o) prog += " " + std::to_string(g.out_reg[o]);
+                fprintf(stderr, "PLAN program  %s\n", prog.c_str());
             } else {
                 fprintf(stderr, "PLAN %-9s %d\n", kinds[it.kind], it.id);
             }

@@ -278,6 +278,41 @@ def test_plan_passes_do_not_change_results(monkeypatch, knob):
         assert float(np.abs(a - b).max()) <= 1e-5 * max(float(np.abs(a).max()), 1e-3)
 
 
+def test_precompiled_update_program_is_bit_identical_to_the_interpreter(monkeypatch, capfd):
+    """The SGD + momentum + weight-decay update of a weight tensor runs as a pre-compiled straight-line program (fused.cu,
+    FzStatic<0>) instead of through the region interpreter.  Same instruction list, same dbk::apply routines: parameters
+    and losses must be identical bit for bit with the table switched off.  A dense net keeps every other kernel of the
+    step deterministic (the convolution filter gradients accumulate with fp32 atomics, whose order varies run to run)."""
+    rng = np.random.RandomState(17)
+    data = [(rng.randn(32, 64).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, 32)]) for _ in range(3)]
+
+    def run(off):
+        if off:
+            monkeypatch.setenv("DOPT_B200_NO_STATIC", "1")
+        else:
+            monkeypatch.delenv("DOPT_B200_NO_STATIC", raising=False)
+        monkeypatch.setenv("DOPT_B200_PLAN_DUMP", "1")
+        H.reset()
+        H.seed(18)
+        H.set_math(db.MATH_FP32)
+        H.set_plan_flags(FUSE | GRAPH)
+        x, y = H.float32((32, 64)), H.float32((32, 10))
+        l = H.data_source(x).dense(4096, weight_decay=1e-3).relu().dense(10, weight_decay=1e-3).softmax()
+        net = H.Network([x], [l])
+        loss = H.cross_entropy(l.train_output, y) + net.param_loss
+        upd = H.Updater(H.SGD, [loss], network=net, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+        capfd.readouterr()
+        outs = [float(upd.step({x: f, y: t})[0]) for f, t in data]
+        dump = capfd.readouterr().err
+        return outs, [p.get().copy() for p in net.params], dump
+    o0, p0, d0 = run(True)
+    o1, p1, d1 = run(False)
+    assert "static=0" in d1 and "static=0" not in d0          # the table was really used / really off
+    assert o0 == o1
+    for a, b in zip(p0, p1):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_wrn_strided_stem_sins_like_amsgrad():
     # sins10.d uses strides [2,2,2]; BASELINE configs[4] trains it with AMSGrad
     _train_compare(_wrn(10, 2, 4, 24, 10, strides=(2, 2, 2)), 2, db.MATH_FP32, 5e-4, 1e-2, kind=H.AMSGRAD,

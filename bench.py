@@ -49,8 +49,16 @@ MODEL = dict(depth=28, width=10, batch=128, hw=32, classes=100, lr=0.1, momentum
 TRAIN_GFLOP_PER_IMAGE = 31.459
 
 
+# images per step of the bounded CPU sample (cpu_baseline and --impl reference): about 10 s of host work per step
+CPU_SAMPLE = 16
+
 # dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, round 1 final)
 TC_DRAM_BYTES_PER_STEP = 3106400512 + 557725696
+
+
+def workload_name(depth=MODEL["depth"], width=MODEL["width"], batch=MODEL["batch"]):
+    return ("WRN-%d-%d + dense(100) + softmax/cross-entropy + weight decay, 3x32x32, batch %d/GPU, "
+            "SGD lr 0.1 momentum 0.9 wd 1e-4 (examples/cifar100.d graph)" % (depth, width, batch))
 
 
 def peaks():
@@ -162,8 +170,8 @@ def cpu_reference_run(steps, warmup, sample_batch, standalone=True):
 def reference_arm(args):
     if RANK != 0:
         return
-    sample = 2
-    steps = max(1, min(args.steps, 3))
+    sample = CPU_SAMPLE
+    steps = max(1, min(args.steps, 2))
     warm = min(args.warmup, 1)
     ips, dt, loss = cpu_reference_run(steps, warm, sample)
     cores = os.cpu_count() or 1
@@ -171,7 +179,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "WRN-28-10 CIFAR train images/sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "WRN-28-10 + dense(100), 3x32x32, SGD lr 0.1 momentum 0.9 wd 1e-4 (examples/cifar100.d recipe)",
+        "config": {"workload": workload_name(), "parallelism": "host cores of rank 0",
                    "sample": "%d images per step (bounded sample of the 128-image batch)" % sample},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "%d steps of %d images, numpy/OpenBLAS oracle over the exported dopt graph" % (steps, sample)},
@@ -403,16 +411,16 @@ def main():
         st = upd.stats()
         cpu = None
         if not args.no_cpu_baseline:
-            ips, dt, _ = cpu_reference_run(1, 0, 2, standalone=False)
+            ips, dt, _ = cpu_reference_run(1, 0, CPU_SAMPLE, standalone=False)
             cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": "1 step of 2 images of the same WRN-28-10 train graph, numpy/OpenBLAS oracle (%.1f s)" % dt}
+                   "sample": "1 step of %d images of the same WRN-28-10 train graph, numpy/OpenBLAS oracle (%.1f s)"
+                             % (CPU_SAMPLE, dt)}
         ms_step = dev_ms / args.steps
         line = {
             "metric": "WRN-28-10 CIFAR train images/sec", "value": B * world * args.steps / (dev_ms * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "WRN-%d-%d + dense(100) + softmax/cross-entropy + weight decay, 3x32x32, batch %d/GPU, "
-                                   "SGD lr 0.1 momentum 0.9 wd 1e-4 (examples/cifar100.d graph)" % (args.depth, args.width, B),
+            "config": {"workload": workload_name(args.depth, args.width, B),
                        "parallelism": "dp%d" % world, "params": n_params,
                        "cache": "inputs larger than L2: one step streams several GB of activations through the 126 MB L2",
                        "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; everything else fp32"},

@@ -57,6 +57,16 @@ extern(C) nothrow @nogc
     int dopt_b200_plan_execute(dopt_b200_plan_t p, const(int)* varIds, const(void*)* varPtrs, const(int)* varOnHost, int nVars,
                                void** rets, int nRets, void* stream);
     int dopt_b200_plan_destroy(dopt_b200_plan_t p);
+
+    // on-device input pipeline (replaces the host loops of nnet/data/cifar.d:50-55 and nnet/data/imagetransformer.d:45-138)
+    struct dopt_b200_jitter { int x_off, y_off, flip_x, flip_y; }
+    int dopt_b200_image_transform_u8(const(ubyte)* src, float* dst, long n, int c, int h, int w, int jitterX, int jitterY,
+                                     const(dopt_b200_jitter)* perImage, void* stream);
+    int dopt_b200_image_transform_f32(const(float)* src, float* dst, long n, int c, int h, int w, int jitterX, int jitterY,
+                                      const(dopt_b200_jitter)* perImage, void* stream);
+    int dopt_b200_one_hot_u8(const(ubyte)* labels, float* dst, long n, int classes, void* stream);
+    int dopt_b200_jitter_sample(dopt_b200_jitter* dst, long n, int jitterX, int jitterY, int flipX, int flipY, ulong seed,
+                                ulong call, void* stream);
 }
 
 enum DOPT_B200_PLAN_FUSE = 1;
@@ -205,6 +215,58 @@ class B200Plan : Plan
         dopt_b200_plan_t mPlan;
         int[Operation] mIds;
         Operation[] mVariables;
+    }
+}
+
+/**
+    Device-side counterpart of `ImageTransformer` (nnet/source/dopt/nnet/data/imagetransformer.d): same constructor
+    arguments, but the batch is uploaded as the dataset's raw bytes and one kernel launch performs normalisation
+    (`x / 128.0f - 1.0f`, nnet/data/cifar.d:50), reflect-padding, the random crop and the random mirrors, writing the NCHW
+    float tensor straight into a `CUDABuffer`.  Labels become one-hot rows on the device as well.  The buffers are handed to
+    the updater as they are (`updater([features: t.features, labels: t.labels])`): `CUDAPlan.executeImpl` uses a `CUDABuffer`
+    argument in place instead of uploading it (cuda/source/dopt/cuda/package.d:373-381).
+*/
+class DeviceImageTransformer
+{
+    this(size_t batchSize, size_t[] imageShape, size_t numLabels, size_t jitterX, size_t jitterY, bool flipX, bool flipY,
+         ulong seed = 0)
+    {
+        import std.random : unpredictableSeed;
+
+        mBatch = batchSize; mShape = imageShape.dup; mClasses = numLabels;
+        mJitterX = jitterX; mJitterY = jitterY; mFlipX = flipX; mFlipY = flipY;
+        mSeed = seed == 0 ? unpredictableSeed : seed;       // the reference draws from an unseeded std.random
+        auto vol = imageShape[0] * imageShape[1] * imageShape[2];
+        mRaw = CUDABuffer.create(batchSize * vol);
+        mRawLabels = CUDABuffer.create(batchSize);
+        mDraws = CUDABuffer.create(batchSize * dopt_b200_jitter.sizeof);
+        features = CUDABuffer.create(batchSize * vol * float.sizeof);
+        labels = CUDABuffer.create(batchSize * numLabels * float.sizeof);
+    }
+
+    /// pixels: batchSize * C*H*W dataset bytes; labelBytes: batchSize class indices
+    void nextBatch(const(ubyte)[] pixels, const(ubyte)[] labelBytes)
+    {
+        mRaw.set(pixels);
+        mRawLabels.set(labelBytes);
+        check(dopt_b200_jitter_sample(cast(dopt_b200_jitter*)mDraws.ptr, cast(long)mBatch, cast(int)mJitterX,
+                                      cast(int)mJitterY, mFlipX, mFlipY, mSeed, mCall++, null));
+        check(dopt_b200_image_transform_u8(cast(const(ubyte)*)mRaw.ptr, cast(float*)features.ptr, cast(long)mBatch,
+                                           cast(int)mShape[0], cast(int)mShape[1], cast(int)mShape[2], cast(int)mJitterX,
+                                           cast(int)mJitterY, cast(const(dopt_b200_jitter)*)mDraws.ptr, null));
+        check(dopt_b200_one_hot_u8(cast(const(ubyte)*)mRawLabels.ptr, cast(float*)labels.ptr, cast(long)mBatch,
+                                   cast(int)mClasses, null));
+    }
+
+    CUDABuffer features, labels;
+
+    private
+    {
+        size_t mBatch, mClasses, mJitterX, mJitterY;
+        size_t[] mShape;
+        bool mFlipX, mFlipY;
+        ulong mSeed, mCall;
+        CUDABuffer mRaw, mRawLabels, mDraws;
     }
 }
 

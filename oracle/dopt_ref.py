@@ -24,7 +24,9 @@ maxpoolGrad tie routing, softmaxGrad, relu*, addBias*, batchNormGrad/Inference, 
 unpinned" by the reference's own tests; for those the oracle is cross-checked against float64 finite differences / closed
 forms in the same test file and, on the GPU box, against the reference CUDA backend's own cuDNN / cuBLAS calls replayed
 from C++ (oracle/cudnn_replay.cpp, tests/test_cudnn_replay_gpu.py: conv family, pooling incl. tie routing, softmax, relu,
-bias, batch norm -- agreement 1e-6 or better, measured errors in profiles/r01p_cudnn_replay_report.jsonl).
+bias, batch norm -- agreement 1e-6 or better, measured errors in profiles/r01p_cudnn_replay_report.jsonl).  Outputs of
+those replayed calls are committed as tests/golden/cudnn_golden.npz and checked on CPU by
+tests/test_oracle_vs_cudnn_golden.py.
 
 All arithmetic is float32 unless a comment says otherwise (reductions whose order cuDNN does not document accumulate
 in float64 and round once; the parity tolerance covers the difference).

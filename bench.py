@@ -410,7 +410,7 @@ def main():
     if RANK == 0:
         st = upd.stats()
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:    # reported at N=1 only (rank 0's host cores)
             ips, dt, _ = cpu_reference_run(1, 0, CPU_SAMPLE, standalone=False)
             cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": "1 step of %d images of the same WRN-28-10 train graph, numpy/OpenBLAS oracle (%.1f s)"

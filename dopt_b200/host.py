@@ -62,6 +62,10 @@ _h.dh_updater_step_device.argtypes = [C.c_int, i32p, C.POINTER(vp), C.c_int]
 _h.dh_updater_plan_outputs.argtypes = [C.c_int, i32p, i32p, C.c_int]
 _h.dh_updater_stats.argtypes = [C.c_int, i64p, i64p, i64p]
 _h.dh_init_data_parallel.argtypes = [C.c_int, C.c_int, vp]
+_h.dh_updater_save_state.argtypes = [C.c_int, C.c_char_p]
+_h.dh_updater_load_state.argtypes = [C.c_int, C.c_char_p]
+_h.dh_updater_state_header_bytes.argtypes = [C.c_int]
+_h.dh_updater_state_header_bytes.restype = C.c_int64
 
 
 class HostError(RuntimeError):
@@ -404,6 +408,14 @@ class Updater(object):
         a, b = (C.c_int * n)(), (C.c_int * n)()
         _ck(_h.dh_updater_plan_outputs(self.h, a, b, n))
         return [Op(a[i]) for i in range(n)], [Op(b[i]) if b[i] >= 0 else None for i in range(n)]
+
+    def save_state(self, path):
+        """Training checkpoint: parameters + optimiser state, header + raw fp32 (online.hpp)."""
+        _ck(_h.dh_updater_save_state(self.h, path.encode()))
+
+    def load_state(self, path): _ck(_h.dh_updater_load_state(self.h, path.encode()))
+
+    def state_header_bytes(self): return _ck(_h.dh_updater_state_header_bytes(self.h))
 
     def stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

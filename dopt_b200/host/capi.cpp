@@ -499,6 +499,24 @@ int dh_updater_plan_outputs(int u, int* plan_outputs, int* destinations, int cap
     return (int)info.planOutputs.size();
     DH_CATCH(-1)
 }
+// training checkpoint (parameters + optimiser state), see online.hpp
+int dh_updater_save_state(int u, const char* file) {
+    DH_TRY
+    online::saveState(g_updaters.at(u).info, file);
+    return 0;
+    DH_CATCH(-1)
+}
+int dh_updater_load_state(int u, const char* file) {
+    DH_TRY
+    online::loadState(g_updaters.at(u).info, file);
+    return 0;
+    DH_CATCH(-1)
+}
+int64_t dh_updater_state_header_bytes(int u) {
+    DH_TRY
+    return (int64_t)online::stateHeaderBytes(g_updaters.at(u).info);
+    DH_CATCH(-1)
+}
 int dh_updater_stats(int u, int64_t* launches, int64_t* bytes, int64_t* nodes) {
     DH_TRY
     auto bp = std::dynamic_pointer_cast<cuda::B200Plan>(g_updaters.at(u).info.plan);

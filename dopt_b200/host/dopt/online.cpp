@@ -1,11 +1,73 @@
 // dopt/online.cpp -- see online.hpp.
 #include "online.hpp"
 
+#include <cstdio>
+#include <cstring>
+
 namespace dopt {
 namespace online {
 
 static LastUpdate g_last;
 const LastUpdate& lastUpdate() { return g_last; }
+
+// ---- training checkpoint ---------------------------------------------------------------------------------------------------
+static const char kCkptMagic[8] = {'D', 'O', 'P', 'T', 'C', 'K', 'P', 'T'};
+static const uint32_t kCkptVersion = 1;
+
+static std::vector<Operation> stateTensors(const LastUpdate& u) {
+    std::vector<Operation> v;
+    for (auto& d : u.destinations)
+        if (d) v.push_back(d);
+    return v;
+}
+size_t stateHeaderBytes(const LastUpdate& u) { return 8 + 4 + 4 + 8 * stateTensors(u).size(); }
+
+void saveState(const LastUpdate& u, const std::string& filename) {
+    auto tensors = stateTensors(u);
+    for (auto& t : tensors) enforce(t->elementType() == DataType::float32, "checkpoint: only float32 state is supported");
+    FILE* f = std::fopen(filename.c_str(), "wb");
+    enforce(f != nullptr, "cannot open " + filename);
+    bool ok = std::fwrite(kCkptMagic, 1, 8, f) == 8;
+    uint32_t n = (uint32_t)tensors.size();
+    ok = ok && std::fwrite(&kCkptVersion, 4, 1, f) == 1 && std::fwrite(&n, 4, 1, f) == 1;
+    for (auto& t : tensors) {
+        uint64_t vol = t->volume();
+        ok = ok && std::fwrite(&vol, 8, 1, f) == 1;
+    }
+    for (auto& t : tensors) {
+        auto v = t->value()->get<float>();
+        ok = ok && std::fwrite(v.data(), sizeof(float), v.size(), f) == v.size();
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    enforce(ok, "short write to " + filename);
+}
+
+void loadState(const LastUpdate& u, const std::string& filename) {
+    auto tensors = stateTensors(u);
+    FILE* f = std::fopen(filename.c_str(), "rb");
+    enforce(f != nullptr, "cannot open " + filename);
+    auto fail = [&](const std::string& why) {
+        std::fclose(f);
+        throw Exception("checkpoint " + filename + ": " + why);
+    };
+    char magic[8];
+    uint32_t version = 0, n = 0;
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, kCkptMagic, 8) != 0) fail("not a dopt_b200 checkpoint");
+    if (std::fread(&version, 4, 1, f) != 1 || version != kCkptVersion) fail("unsupported version");
+    if (std::fread(&n, 4, 1, f) != 1 || n != tensors.size()) fail("tensor count does not match this updater");
+    for (auto& t : tensors) {
+        uint64_t vol = 0;
+        if (std::fread(&vol, 8, 1, f) != 1 || vol != (uint64_t)t->volume()) fail("tensor sizes do not match this updater");
+    }
+    // read everything before touching any variable: a truncated file must not leave a half-restored model behind
+    std::vector<std::vector<float>> data;
+    for (auto& t : tensors) {
+        data.emplace_back(t->volume());
+        if (std::fread(data.back().data(), sizeof(float), data.back().size(), f) != data.back().size()) fail("file is too short");
+    }
+    std::fclose(f);
+    for (size_t i = 0; i < tensors.size(); ++i) tensors[i]->value()->set(data[i].data(), data[i].size() * sizeof(float));
+}
 
 // data-parallel: the mean over ranks of every gradient, as a registered `allreduce` op between grad() and the update rule
 static std::vector<Operation> exchange(std::vector<Operation> grads) {

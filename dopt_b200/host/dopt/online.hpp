@@ -31,5 +31,16 @@ struct LastUpdate {
 };
 const LastUpdate& lastUpdate();
 
+// Training checkpoint: everything the updater overwrites every step -- the parameters, the
+// optimiser state (momenta / means / variances / varhats) and Adam's running b1, b2 -- in the order of `destinations`.
+// The reference only has DAGNetwork.save/load (nnet/networks.d:130-164: raw fp32 of the parameters, no header, no optimiser
+// state), so a resumed run restarts its momenta from zero.  File layout:
+//   "DOPTCKPT" | u32 version (1) | u32 n_tensors | n_tensors x u64 element count | raw fp32 of every tensor in order
+// With a network-built updater the tensors start with the network's parameters in DAGNetwork order, so the first part of
+// the body is byte-for-byte the file DAGNetwork::save writes.  loadState refuses a file whose tensor list does not match.
+void saveState(const LastUpdate& u, const std::string& filename);
+void loadState(const LastUpdate& u, const std::string& filename);
+size_t stateHeaderBytes(const LastUpdate& u);
+
 }  // namespace online
 }  // namespace dopt

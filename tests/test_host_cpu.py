@@ -253,6 +253,62 @@ def test_dropout_layer_graph():
     assert "gt" in ts and "uniform" in ts and ts.count("uniform") == 1       # the SAME mask node gates the gradient
 
 
+@pytest.mark.parametrize("kind", [H.SGD, H.ADAM, H.AMSGRAD])
+def test_training_checkpoint_roundtrip(tmp_path, kind):
+    """Parameters + optimiser state (+ Adam's running b1 / b2) survive save_state / load_state; the body of the file starts
+    with exactly the bytes DAGNetwork.save writes (nnet/networks.d:130-164); mismatching or truncated files are refused
+    without touching the model."""
+    import os
+    import struct
+    H.seed(3)
+    x, y = H.float32((4, 3, 8, 8)), H.float32((4, 5))
+    l = H.data_source(x).conv2d(4, (3, 3), padding=(1, 1), weight_decay=1e-3).batch_norm().relu().dense(5).softmax()
+    net = H.Network([x], [l])
+    loss = H.cross_entropy(l.train_output, y) + net.param_loss
+    upd = H.Updater(kind, [loss], network=net)
+    _, dests = upd.plan_outputs()
+    state = [d for d in dests if d is not None]
+    n_slots = {H.SGD: 2, H.ADAM: 3, H.AMSGRAD: 4}[kind]
+    assert len(state) == n_slots * len(net.params) + (0 if kind == H.SGD else 2)
+    rng = np.random.RandomState(4)
+    want = []
+    for v in state:                                              # pretend some training happened
+        a = rng.randn(*v.shape).astype(F) if v.shape else np.array(rng.rand(), F)
+        v.set(a)
+        want.append(a)
+    path, ppath = str(tmp_path / "train.ckpt"), str(tmp_path / "params.bin")
+    upd.save_state(path)
+    net.save(ppath)
+    raw = open(path, "rb").read()
+    hdr = upd.state_header_bytes()
+    assert raw[:8] == b"DOPTCKPT" and struct.unpack("<II", raw[8:16]) == (1, len(state))
+    assert list(struct.unpack("<%dQ" % len(state), raw[16:hdr])) == [v.volume for v in state]
+    assert len(raw) == hdr + 4 * sum(v.volume for v in state)
+    params = open(ppath, "rb").read()
+    assert raw[hdr:hdr + len(params)] == params                  # reference-format parameter file is a prefix of the body
+    for v in state:
+        v.set(np.zeros(v.shape, F))
+    upd.load_state(path)
+    for v, a in zip(state, want):
+        np.testing.assert_array_equal(v.get(), a)
+    # refused: truncated file, wrong magic, an updater with a different tensor list
+    open(path, "wb").write(raw[:-8])
+    for v in state:
+        v.set(np.ones(v.shape, F))
+    with pytest.raises(H.HostError):
+        upd.load_state(path)
+    for v in state:
+        np.testing.assert_array_equal(v.get(), np.ones(v.shape, F))   # nothing was half-restored
+    open(path, "wb").write(b"NOTACKPT" + raw[8:])
+    with pytest.raises(H.HostError):
+        upd.load_state(path)
+    open(path, "wb").write(raw)
+    other = H.Updater(H.SGD if kind != H.SGD else H.ADAM, [loss], network=net)
+    with pytest.raises(H.HostError):
+        other.load_state(path)
+    assert os.path.getsize(ppath) == 4 * sum(p.volume for p in net.params)
+
+
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
     loss = H.sum_(w * w)

@@ -62,6 +62,9 @@ _h.dh_updater_step_device.argtypes = [C.c_int, i32p, C.POINTER(vp), C.c_int]
 _h.dh_updater_plan_outputs.argtypes = [C.c_int, i32p, i32p, C.c_int]
 _h.dh_updater_stats.argtypes = [C.c_int, i64p, i64p, i64p]
 _h.dh_init_data_parallel.argtypes = [C.c_int, C.c_int, vp]
+_h.dh_matrix_norm.argtypes = [C.c_int, C.c_int]
+_h.dh_conv_params_norm.argtypes = [C.c_int, i64p, i64p, i64p, C.c_int]
+_h.dh_max_norm.argtypes = [C.c_int, C.c_int, C.c_int]
 _h.dh_updater_save_state.argtypes = [C.c_int, C.c_char_p]
 _h.dh_updater_load_state.argtypes = [C.c_int, C.c_char_p]
 _h.dh_updater_state_header_bytes.argtypes = [C.c_int]
@@ -267,6 +270,13 @@ def grad(objective, wrt):
     out = (C.c_int * len(wrt))()
     _ck(_h.dh_grad(objective.h, _i32([w.h for w in wrt]), len(wrt), out))
     return [Op(out[i]) for i in range(len(wrt))]
+
+
+def _p_code(p): return 0 if p == float("inf") else int(p)
+def matrix_norm(param, p=2): return Op(_h.dh_matrix_norm(param.h, _p_code(p)))                    # nnet/lipschitz.d:43-97
+def conv_params_norm(param, in_shape, stride=(1, 1), padding=(0, 0), p=2):                        # nnet/lipschitz.d:111-147
+    return Op(_h.dh_conv_params_norm(param.h, _i64(in_shape), _i64(stride), _i64(padding), _p_code(p)))
+def max_norm(param, norm, maxval): return Op(_h.dh_max_norm(param.h, norm.h, maxval.h))           # nnet/lipschitz.d:162-165
 
 
 def cross_entropy(hyp, truth): return Op(_h.dh_cross_entropy(hyp.h, truth.h))

@@ -3,6 +3,7 @@
 // tables.  This is harness plumbing, not part of the drop-in boundary (that is include/dopt_b200.h).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstring>
 #include <sstream>
 
@@ -376,6 +377,23 @@ int dh_network_params(int net, int* out, int cap) {
     auto& p = g_nets.at(net)->params();
     for (size_t i = 0; i < p.size() && (int)i < cap; ++i) out[i] = findOp(p[i]);
     return (int)p.size();
+    DH_CATCH(-1)
+}
+// nnet/lipschitz.d: norms (p_code 1, 2, or 0 for infinity) and the max-norm projection
+int dh_matrix_norm(int param, int p_code) {
+    DH_TRY
+    return addOp(nnet::matrixNorm(op(param), p_code == 0 ? INFINITY : (float)p_code));
+    DH_CATCH(-1)
+}
+int dh_conv_params_norm(int param, const int64_t* in_shape, const int64_t* stride, const int64_t* padding, int p_code) {
+    DH_TRY
+    return addOp(nnet::convParamsNorm(op(param), sizes(in_shape, 2), sizes(stride, 2), sizes(padding, 2),
+                                      p_code == 0 ? INFINITY : (float)p_code));
+    DH_CATCH(-1)
+}
+int dh_max_norm(int param, int norm, int maxval) {
+    DH_TRY
+    return addOp(nnet::maxNorm(op(param), op(norm), op(maxval)));
     DH_CATCH(-1)
 }
 int dh_network_save(int net, const char* file) {

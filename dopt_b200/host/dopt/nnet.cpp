@@ -196,6 +196,57 @@ void DAGNetwork::load(const std::string& filename) {
     std::fclose(f);
 }
 
+// ---- nnet/lipschitz.d ----------------------------------------------------------------------------------------------------------
+Operation matrixNorm(Operation param, float p, size_t n) {
+    enforce(param->rank() == 2, "This function only operates on matrices");
+    if (p == 1.0f) {
+        // maximum absolute ROW sum: dense / convolution weights are transposed before use (lipschitz.d:49-63)
+        return maxElement(sum(abs(param), {1}));
+    } else if (p == 2.0f) {
+        // power iteration on W W^T from a random start (lipschitz.d:65-79)
+        auto x = uniformSample({param->shape()[0], 1}) * 2.0f - 1.0f;
+        auto weightsT = transpose(param, {1, 0});
+        auto wwT = matmul(param, weightsT);
+        for (size_t i = 0; i < n; ++i) x = matmul(wwT, x);
+        auto v = x / sqrt(sum(x * x));
+        auto y = matmul(weightsT, v);
+        return sqrt(sum(y * y));
+    } else if (std::isinf(p) && p > 0) {
+        return maxElement(sum(abs(param), {0}));   // maximum absolute column sum (lipschitz.d:81-90)
+    }
+    throw Exception("Cannot compute matrix norm for p=" + std::to_string(p));
+}
+
+Operation convParamsNorm(Operation param, std::vector<size_t> inShape, std::vector<size_t> stride,
+                         std::vector<size_t> padding, float p, size_t n) {
+    if (p == 2.0f) {
+        // power iteration on conv^T conv over a random image (lipschitz.d:114-128)
+        std::vector<size_t> xs{1, param->shape()[1]};
+        xs.insert(xs.end(), inShape.begin(), inShape.end());
+        auto x = uniformSample(xs) * 2.0f - 1.0f;
+        for (size_t i = 0; i < n; ++i) x = convolutionTranspose(convolution(x, param, padding, stride), param, padding, stride);
+        auto v = x / sqrt(sum(x * x));
+        auto y = convolution(v, param, padding, stride);
+        return sqrt(sum(y * y));
+    } else if (p == 1.0f || (std::isinf(p) && p > 0)) {
+        if (param->rank() != 2) param = reshape(param, {param->shape()[0], param->volume() / param->shape()[0]});
+        return matrixNorm(param, p);
+    }
+    throw Exception("Cannot compute convolution params norm for p=" + std::to_string(p));
+}
+
+Operation maxNorm(Operation param, Operation norm, Operation maxval) {
+    return param * (1.0f / max(float32({}, {1.0f}), norm / maxval));
+}
+
+Projection projMatrix(Operation maxnorm, float p) {
+    return [maxnorm, p](Operation param) { return maxNorm(param, matrixNorm(param, p), maxnorm); };
+}
+Projection projConvParams(Operation maxnorm, std::vector<size_t> inShape, std::vector<size_t> stride,
+                          std::vector<size_t> padding, float p) {
+    return [=](Operation param) { return maxNorm(param, convParamsNorm(param, inShape, stride, padding, p), maxnorm); };
+}
+
 Operation crossEntropy(Operation hypothesis, Operation groundTruth) {
     return sum(groundTruth * log(hypothesis + 1e-6f)) * (-1.0f / (float)hypothesis->shape()[0]);
 }

@@ -1,7 +1,7 @@
 // dopt/nnet.hpp -- C++ mirror of the parts of dopt.nnet that generate the hot path's graphs: Layer, the layer
 // constructors, DAGNetwork, the losses and the VGG / Wide-ResNet model builders.  Host-only graph construction; see the
-// .cpp for per-function citations.  Research regularisers (maxgain / Lipschitz / spectral decay projections,
-// nnet/lipschitz.d) are out of scope (default-off in every BASELINE config).
+// .cpp for per-function citations.  The Lipschitz projections of nnet/lipschitz.d are available as free functions; the
+// per-layer maxgain / spectralDecay option branches (default-off in every BASELINE config) are not.
 #pragma once
 #include <random>
 
@@ -87,6 +87,16 @@ private:
     Operation mParameterLoss;
     std::map<Operation, Projection> mParameterProj;
 };
+
+// nnet/lipschitz.d (Gouk et al. 2018): projections that bound the operator norm of a weight matrix / convolution, for the
+// `projs` argument of the dopt.online updaters.  p is 1, 2 (n power iterations from a random start) or infinity.
+Operation matrixNorm(Operation param, float p, size_t n = 2);                                   // lipschitz.d:43-97
+Operation convParamsNorm(Operation param, std::vector<size_t> inShape, std::vector<size_t> stride,
+                         std::vector<size_t> padding, float p = 2.0f, size_t n = 2);            // lipschitz.d:111-147
+Operation maxNorm(Operation param, Operation norm, Operation maxval);                           // lipschitz.d:162-165
+Projection projMatrix(Operation maxnorm, float p = 2.0f);                                       // lipschitz.d:28-38
+Projection projConvParams(Operation maxnorm, std::vector<size_t> inShape, std::vector<size_t> stride,
+                          std::vector<size_t> padding, float p = 2.0f);                         // lipschitz.d:99-109
 
 Operation crossEntropy(Operation hypothesis, Operation groundTruth);   // nnet/losses.d:23-26
 Operation squaredError(Operation hypothesis, Operation groundTruth);   // nnet/losses.d:35-40

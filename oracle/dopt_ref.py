@@ -371,6 +371,15 @@ def adam_step(w, g, m, v, b1, b2, alpha, beta1, beta2, eps, vhat=None):
     return nw, nm, nv, nb1, nb2
 
 
+_UNIFORM_RNG = np.random.RandomState(0)
+
+
+def uniform(shape):
+    """cpu/source/dopt/cpu/random.d:18-26: `uniform01!float + float.epsilon`, i.e. (0, 1] like cuRAND's generator.  The
+    reference draws from an unseeded std.random, so only the distribution is defined; this stream is seeded for tests."""
+    return (_UNIFORM_RNG.random_sample(tuple(int(s) for s in shape)).astype(np.float32) + np.finfo(np.float32).eps)
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # one entry point keyed by op type -- the shape of cpu/source/dopt/cpu/package.d's kernel registry
 # --------------------------------------------------------------------------------------------------------------------
@@ -429,4 +438,6 @@ def evaluate_op(op_type, inputs, attrs=None, out_shape=None):
         return batch_norm_grad(*inputs, out_volume=vol)
     if op_type == "batchNormInference":
         return batch_norm_inference(*inputs)
+    if op_type == "uniform":
+        return uniform(a["shape"])
     raise KeyError("oracle has no kernel for '%s'" % op_type)

@@ -309,6 +309,38 @@ def test_training_checkpoint_roundtrip(tmp_path, kind):
     assert os.path.getsize(ppath) == 4 * sum(p.volume for p in net.params)
 
 
+def test_lipschitz_norms_and_projection():
+    """nnet/lipschitz.d: operator norms of a weight matrix / a convolution and the max-norm projection, evaluated with the
+    oracle.  p = 1 / infinity are exact row / column sums; p = 2 is a two-step power iteration from a random start, so it
+    is a lower bound that gets close to the true spectral norm."""
+    rng = np.random.RandomState(5)
+    wv = rng.randn(6, 9).astype(F)
+    w = H.float32((6, 9), wv)
+    n1, ninf, n2 = ev([H.matrix_norm(w, 1), H.matrix_norm(w, float("inf")), H.matrix_norm(w, 2)])
+    np.testing.assert_allclose(n1, np.abs(wv).sum(axis=1).max(), rtol=1e-6)
+    np.testing.assert_allclose(ninf, np.abs(wv).sum(axis=0).max(), rtol=1e-6)
+    true2 = np.linalg.svd(wv.astype(np.float64), compute_uv=False)[0]
+    assert 0.7 * true2 <= float(n2) <= true2 * (1 + 1e-5)
+    assert types([H.matrix_norm(w, 2)]).count("uniform") == 1
+    # convolution: p = 1 / infinity reduce to the reshaped matrix (lipschitz.d:130-138); p = 2 power-iterates conv^T conv
+    kv = rng.randn(4, 3, 3, 3).astype(F)
+    k = H.float32((4, 3, 3, 3), kv)
+    c1 = ev([H.conv_params_norm(k, (8, 8), p=1)])[0]
+    np.testing.assert_allclose(c1, np.abs(kv.reshape(4, -1)).sum(axis=1).max(), rtol=1e-6)
+    ts = types([H.conv_params_norm(k, (8, 8), (1, 1), (1, 1), 2)])
+    assert ts.count("convolution") == 3 and ts.count("convolutionFeaturesGrad") == 2      # n = 2 round trips + the final conv
+    c2 = float(ev([H.conv_params_norm(k, (8, 8), (1, 1), (1, 1), 2)])[0])
+    # the operator norm of a padded convolution is bounded by the sum over taps of the tap matrices' spectral norms
+    bound = sum(np.linalg.svd(kv[:, :, r, q].astype(np.float64), compute_uv=False)[0] for r in range(3) for q in range(3))
+    assert 0 < c2 <= bound * (1 + 1e-5)
+    # maxNorm: scale down only when the norm exceeds the bound (lipschitz.d:162-165)
+    for bound_v, factor in ((1.0, 1.0 / float(n1)), (1e6, 1.0)):
+        proj = H.max_norm(w, H.matrix_norm(w, 1), H.float32((), [bound_v]))
+        np.testing.assert_allclose(ev([proj])[0], wv * F(factor), rtol=2e-6)
+    with pytest.raises(H.HostError):
+        H.matrix_norm(k, 1)                                           # "This function only operates on matrices"
+
+
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
     loss = H.sum_(w * w)

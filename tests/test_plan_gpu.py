@@ -398,3 +398,27 @@ def test_dropout_layer_trains_with_a_fresh_consistent_mask(flags):
     for i in range(len(masks)):
         for j in range(i):
             assert not np.array_equal(masks[i], masks[j])
+
+
+def test_lipschitz_projection_graphs_on_gpu():
+    """nnet/lipschitz.d graphs (abs / axis sums / maxElement / transpose / matmul / uniform / convolutionTranspose) through
+    the plan: the deterministic norms against numpy, the power-iteration norm against its bound, the projection against
+    the oracle value."""
+    H.set_plan_flags(FUSE | GRAPH)
+    rng = np.random.RandomState(5)
+    wv = rng.randn(64, 96).astype(F)
+    w = H.float32((64, 96), wv)
+    kv = (rng.randn(8, 4, 3, 3) * 0.2).astype(F)
+    k = H.float32((8, 4, 3, 3), kv)
+    n1, ninf, n2, c1, c2, proj = H.Plan([
+        H.matrix_norm(w, 1), H.matrix_norm(w, float("inf")), H.matrix_norm(w, 2), H.conv_params_norm(k, (16, 16), p=1),
+        H.conv_params_norm(k, (16, 16), (1, 1), (1, 1), 2),
+        H.max_norm(w, H.matrix_norm(w, 1), H.float32((), [1.0]))]).execute()
+    np.testing.assert_allclose(n1, np.abs(wv).sum(axis=1).max(), rtol=1e-5)
+    np.testing.assert_allclose(ninf, np.abs(wv).sum(axis=0).max(), rtol=1e-5)
+    true2 = np.linalg.svd(wv.astype(np.float64), compute_uv=False)[0]
+    assert 0.6 * true2 <= float(n2) <= true2 * (1 + 1e-4)
+    np.testing.assert_allclose(c1, np.abs(kv.reshape(8, -1)).sum(axis=1).max(), rtol=1e-5)
+    bound = sum(np.linalg.svd(kv[:, :, r, q].astype(np.float64), compute_uv=False)[0] for r in range(3) for q in range(3))
+    assert 0 < float(c2) <= bound * (1 + 1e-4)
+    np.testing.assert_allclose(proj, wv / np.abs(wv).sum(axis=1).max(), rtol=1e-5)

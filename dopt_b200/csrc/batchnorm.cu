@@ -15,6 +15,7 @@
 // HBM-bound.  Algorithmic bytes: train 2V*4 (+ the statistics re-read, which the 126 MB L2 absorbs when the tensor was
 // just produced), grad 3V*4, inference 2V*4.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace db {
 
@@ -418,8 +419,14 @@ static BnGeom geom_of(const dopt_b200_tensor& x) {
     return g;
 }
 
+// grid = C x splits CTAs of 256 threads (40 registers: up to 6 resident per SM).  Experiment knobs, read per kernel
+// construction: DOPT_B200_BN_CTAS_PER_SM (default 4) sets the target number of CTAs per SM, DOPT_B200_BN_SPLITS forces the
+// split count (tools/bn_sweep.sh sweeps them; 640 CTAs on 148 SMs leave 48 SMs with one CTA more than the rest).
 static int pick_splits(const BnGeom& g) {
-    int64_t want = ceil_div(4 * (int64_t)sm_count(), g.C);
+    int per_sm = 4;
+    if (const char* e = getenv("DOPT_B200_BN_CTAS_PER_SM")) per_sm = std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("DOPT_B200_BN_SPLITS")) return (int)std::max<int64_t>(1, std::min<int64_t>(atoi(e), g.N));
+    int64_t want = ceil_div(per_sm * (int64_t)sm_count(), g.C);
     int64_t s = std::min<int64_t>(want, g.N);
     // keep at least ~2048 elements per CTA
     int64_t per = g.N * g.HW;

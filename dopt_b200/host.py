@@ -45,6 +45,11 @@ _h.dh_export.argtypes = [i32p, C.c_int]
 _h.dh_conv2d.argtypes = [C.c_int, C.c_int64, i64p, i64p, i64p, C.c_float, C.c_int]
 _h.dh_dense.argtypes = [C.c_int, C.c_int64, C.c_float, C.c_int]
 _h.dh_batch_norm.argtypes = [C.c_int, C.c_float]
+_h.dh_conv2d_reg.argtypes = [C.c_int, C.c_int64, i64p, i64p, i64p, C.c_float, C.c_int, C.c_float, C.c_float]
+_h.dh_dense_reg.argtypes = [C.c_int, C.c_int64, C.c_float, C.c_int, C.c_float, C.c_float]
+_h.dh_batch_norm_reg.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+_h.dh_wide_resnet_reg.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                  C.c_float]
 _h.dh_max_pool.argtypes = [C.c_int, i64p]
 _h.dh_dropout.argtypes = [C.c_int, C.c_float]
 _h.dh_wide_resnet.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_float]
@@ -316,10 +321,22 @@ class Layer(object):
     def output(self): return Op(_h.dh_layer_output(self.h, 0))
     @property
     def train_output(self): return Op(_h.dh_layer_output(self.h, 1))
-    def conv2d(self, channels, fdims, padding=(0, 0), stride=(1, 1), weight_decay=0.0, use_bias=True):
-        return Layer(_h.dh_conv2d(self.h, channels, _i64(fdims), _i64(padding), _i64(stride), weight_decay, int(use_bias)))
-    def dense(self, outputs, weight_decay=0.0, use_bias=True): return Layer(_h.dh_dense(self.h, outputs, weight_decay, int(use_bias)))
-    def batch_norm(self, momentum=0.9): return Layer(_h.dh_batch_norm(self.h, momentum))
+    def conv2d(self, channels, fdims, padding=(0, 0), stride=(1, 1), weight_decay=0.0, use_bias=True,
+               maxgain=float("inf"), spectral_decay=0.0):
+        if maxgain == float("inf") and spectral_decay == 0.0:
+            return Layer(_h.dh_conv2d(self.h, channels, _i64(fdims), _i64(padding), _i64(stride), weight_decay, int(use_bias)))
+        return Layer(_h.dh_conv2d_reg(self.h, channels, _i64(fdims), _i64(padding), _i64(stride), weight_decay, int(use_bias),
+                                      maxgain, spectral_decay))
+
+    def dense(self, outputs, weight_decay=0.0, use_bias=True, maxgain=float("inf"), spectral_decay=0.0):
+        if maxgain == float("inf") and spectral_decay == 0.0:
+            return Layer(_h.dh_dense(self.h, outputs, weight_decay, int(use_bias)))
+        return Layer(_h.dh_dense_reg(self.h, outputs, weight_decay, int(use_bias), maxgain, spectral_decay))
+
+    def batch_norm(self, momentum=0.9, maxgain=float("inf"), lipschitz=float("inf")):
+        if maxgain == float("inf") and lipschitz == float("inf"):
+            return Layer(_h.dh_batch_norm(self.h, momentum))
+        return Layer(_h.dh_batch_norm_reg(self.h, momentum, maxgain, lipschitz))
     def relu(self): return Layer(_h.dh_relu(self.h))
     def max_pool(self, dims): return Layer(_h.dh_max_pool(self.h, _i64(dims)))
     def dropout(self, drop_prob): return Layer(_h.dh_dropout(self.h, float(drop_prob)))
@@ -327,8 +344,13 @@ class Layer(object):
 
 
 def data_source(var): return Layer(_h.dh_data_source(var.h))
-def wide_resnet(features, depth, width, stride=(1, 2, 2), weight_decay=1e-4):
-    return Layer(_h.dh_wide_resnet(features.h, depth, width, _i64(stride), weight_decay))
+def wide_resnet(features, depth, width, stride=(1, 2, 2), weight_decay=1e-4, dropout=False, maxgain_norm=float("nan"),
+                lipschitz_norm=float("nan"), max_norm=float("inf"), spectral_decay=0.0):
+    """wideResNet(features, depth, width, WRNOptions) -- nnet/models/wrn.d:56-102; the regulariser fields default to off."""
+    if not dropout and maxgain_norm != maxgain_norm and lipschitz_norm != lipschitz_norm and spectral_decay == 0.0:
+        return Layer(_h.dh_wide_resnet(features.h, depth, width, _i64(stride), weight_decay))
+    return Layer(_h.dh_wide_resnet_reg(features.h, depth, width, _i64(stride), weight_decay, int(dropout), maxgain_norm,
+                                       lipschitz_norm, max_norm, spectral_decay))
 def vgg19(features, dense_sizes=(4096, 4096), batchnorm=False):
     return Layer(_h.dh_vgg19(features.h, _i64(dense_sizes), len(dense_sizes), int(batchnorm)))
 

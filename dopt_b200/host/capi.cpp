@@ -319,6 +319,39 @@ int dh_batch_norm(int in, float momentum) {
     return addLayer(nnet::batchNorm(layer(in), o));
     DH_CATCH(-1)
 }
+// the same three layers with the regulariser options of conv.d / dense.d / batchnorm.d (infinity / 0 = off)
+int dh_conv2d_reg(int in, int64_t channels, const int64_t* fdims, const int64_t* pad, const int64_t* stride, float wd,
+                  int use_bias, float maxgain, float spectral_decay) {
+    DH_TRY
+    nnet::Conv2DOptions o;
+    o.padding = sizes(pad, 2);
+    o.stride = sizes(stride, 2);
+    o.weightDecay = wd;
+    o.useBias = use_bias != 0;
+    o.maxgain = maxgain;
+    o.spectralDecay = spectral_decay;
+    return addLayer(nnet::conv2D(layer(in), (size_t)channels, sizes(fdims, 2), o));
+    DH_CATCH(-1)
+}
+int dh_dense_reg(int in, int64_t outputs, float wd, int use_bias, float maxgain, float spectral_decay) {
+    DH_TRY
+    nnet::DenseOptions o;
+    o.weightDecay = wd;
+    o.useBias = use_bias != 0;
+    o.maxgain = maxgain;
+    o.spectralDecay = spectral_decay;
+    return addLayer(nnet::dense(layer(in), (size_t)outputs, o));
+    DH_CATCH(-1)
+}
+int dh_batch_norm_reg(int in, float momentum, float maxgain, float lipschitz) {
+    DH_TRY
+    nnet::BatchNormOptions o;
+    o.momentum = momentum;
+    o.maxgain = maxgain;
+    o.lipschitz = lipschitz;
+    return addLayer(nnet::batchNorm(layer(in), o));
+    DH_CATCH(-1)
+}
 int dh_relu(int in) {
     DH_TRY
     return addLayer(nnet::relu(layer(in)));
@@ -344,6 +377,21 @@ int dh_wide_resnet(int features, int64_t depth, int64_t width, const int64_t* st
     nnet::WRNOptions o;
     o.weightDecay = wd;
     for (int i = 0; i < 3; ++i) o.stride[i] = (size_t)stride3[i];
+    return addLayer(nnet::wideResNet(op(features), (size_t)depth, (size_t)width, o));
+    DH_CATCH(-1)
+}
+// WRNOptions with the regulariser fields of wrn.d:11-54 (NaN / infinity / 0 = off)
+int dh_wide_resnet_reg(int features, int64_t depth, int64_t width, const int64_t* stride3, float wd, int dropout,
+                       float maxgain_norm, float lipschitz_norm, float max_norm, float spectral_decay) {
+    DH_TRY
+    nnet::WRNOptions o;
+    o.weightDecay = wd;
+    for (int i = 0; i < 3; ++i) o.stride[i] = (size_t)stride3[i];
+    o.dropout = dropout != 0;
+    o.maxgainNorm = maxgain_norm;
+    o.lipschitzNorm = lipschitz_norm;
+    o.maxNorm = max_norm;
+    o.spectralDecay = spectral_decay;
     return addLayer(nnet::wideResNet(op(features), (size_t)depth, (size_t)width, o));
     DH_CATCH(-1)
 }

@@ -56,6 +56,43 @@ static Operation safeAdd(Operation a, Operation b) {
     return a + b;
 }
 
+// The max-gain projection shared by conv2D / dense / batchNorm (conv.d:125-150, dense.d:105-131, batchnorm.d:97-113):
+// scale the new weights down so that the largest ratio ||after_n|| / ||before_n|| over the training batch stays below
+// `maxgain`.  `before` / `after` are the layer's train-time input and output; they are flattened to [N, volume / N] here.
+static Projection maxGainProjection(Operation before, Operation after, float maxgain, Projection inner) {
+    before = reshape(before, {before->shape()[0], before->volume() / before->shape()[0]});
+    after = reshape(after, {after->shape()[0], after->volume() / after->shape()[0]});
+    return [before, after, maxgain, inner](Operation newWeights) {
+        auto beforeNorms = sum(before * before, {1}) + 1e-8f;
+        auto afterNorms = sum(after * after, {1}) + 1e-8f;
+        auto mg = maxElement(sqrt(afterNorms / beforeNorms));
+        auto projected = newWeights * (1.0f / max(float32Constant({}, {1.0f}), mg / maxgain));
+        return inner ? inner(projected) : projected;
+    };
+}
+
+// conv.d:173-189: the (deliberately simplified, Yoshida & Miyato 2017) spectral-norm penalty of the reshaped filter matrix --
+// one power iteration from a random start; returns the SQUARED norm estimate, as the reference does
+static Operation convSpectralNorm(Operation filters, size_t numIts = 1) {
+    filters = reshape(filters, {filters->shape()[0], filters->volume() / filters->shape()[0]});
+    auto x = uniformSample({filters->shape()[1], 1}) * 2.0f - 1.0f;
+    for (size_t i = 0; i < numIts; ++i) x = matmul(transpose(filters, {1, 0}), matmul(filters, x));
+    auto v = x / sqrt(sum(x * x));
+    auto y = matmul(filters, v);
+    return sum(y * y);
+}
+
+// dense.d:152-169: the same penalty for a dense layer's [outputs, inputs] weight matrix, power-iterating W W^T
+static Operation denseSpectralNorm(Operation weights, size_t numIts = 1) {
+    auto x = uniformSample({weights->shape()[0], 1}) * 2.0f - 1.0f;
+    auto weightsT = transpose(weights, {1, 0});
+    auto wwT = matmul(weights, weightsT);
+    for (size_t i = 0; i < numIts; ++i) x = matmul(wwT, x);
+    auto v = x / sqrt(sum(x * x));
+    auto y = matmul(weightsT, v);
+    return sum(y * y);
+}
+
 LayerPtr conv2D(LayerPtr input, size_t outputChannels, std::vector<size_t> filterDims, Conv2DOptions opts) {
     // nnet/layers/conv.d:74-165
     auto x = input->output();
@@ -66,9 +103,12 @@ LayerPtr conv2D(LayerPtr input, size_t outputChannels, std::vector<size_t> filte
     opts.filterInit(filters);
     Operation filterLoss;
     filterLoss = safeAdd(filterLoss, opts.weightDecay == 0.0f ? nullptr : (opts.weightDecay * sum(filters * filters)));
+    filterLoss = safeAdd(filterLoss, opts.spectralDecay == 0.0f ? nullptr : (opts.spectralDecay * convSpectralNorm(filters)));
     auto y = convolution(x, filters, opts.padding, opts.stride);
     auto yTr = (xTr == x) ? y : convolution(xTr, filters, opts.padding, opts.stride);
-    std::vector<Parameter> params{Parameter{filters, filterLoss, opts.filterProj}};
+    Projection filterProj = opts.filterProj;
+    if (opts.maxgain != INFINITY) filterProj = maxGainProjection(xTr, yTr, opts.maxgain, opts.filterProj);   // conv.d:125-155
+    std::vector<Parameter> params{Parameter{filters, filterLoss, filterProj}};
     if (opts.useBias) {
         auto biases = float32(std::vector<size_t>{outputChannels});
         opts.biasInit(biases);
@@ -91,9 +131,12 @@ LayerPtr dense(LayerPtr input, size_t numOutputs, DenseOptions opts) {
     opts.weightInit(weights);
     Operation weightLoss;
     weightLoss = safeAdd(weightLoss, opts.weightDecay == 0.0f ? nullptr : (opts.weightDecay * sum(weights * weights)));
+    weightLoss = safeAdd(weightLoss, opts.spectralDecay == 0.0f ? nullptr : (opts.spectralDecay * denseSpectralNorm(weights)));
     auto y = matmul(x, transpose(weights, {1, 0}));
     auto yTr = same ? y : matmul(xTr, transpose(weights, {1, 0}));
-    std::vector<Parameter> params{Parameter{weights, weightLoss, opts.weightProj}};
+    Projection weightProj = opts.weightProj;
+    if (opts.maxgain != INFINITY) weightProj = maxGainProjection(xTr, yTr, opts.maxgain, opts.weightProj);   // dense.d:105-136
+    std::vector<Parameter> params{Parameter{weights, weightLoss, weightProj}};
     if (opts.useBias) {
         auto bias = float32(std::vector<size_t>{numOutputs});
         opts.biasInit(bias);
@@ -124,8 +167,24 @@ LayerPtr batchNorm(LayerPtr input, BatchNormOptions opts) {
     auto y = batchNormInference(x, gamma, beta, mean, var);
     Projection meanUpdater = [meanUpdateSym](Operation) { return meanUpdateSym; };
     Projection varUpdater = [varUpdateSym](Operation) { return varUpdateSym; };
+    Projection gammaProj = opts.gammaProj;
+    if (opts.maxgain != INFINITY) {
+        // batchnorm.d:93-113: gain of the layer without its shift (zero beta, zero mean) on the train batch
+        auto zeros = float32Constant({C}, std::vector<float>(C, 0.0f));
+        auto after = batchNormInference(xTr, gamma, zeros, zeros, var);
+        gammaProj = maxGainProjection(xTr, after, opts.maxgain, opts.gammaProj);
+    } else if (opts.lipschitz != INFINITY) {
+        // batchnorm.d:115-129
+        float bound = opts.lipschitz;
+        Projection inner = opts.gammaProj;
+        gammaProj = [varUpdateSym, bound, inner](Operation newGamma) {
+            auto norm = maxElement(abs(newGamma / sqrt(reshape(varUpdateSym, newGamma->shape()) + 1e-6f)));
+            auto g = newGamma * (1.0f / max(float32Constant(1.0f), norm / bound));
+            return inner ? inner(g) : g;
+        };
+    }
     std::vector<Parameter> params{
-        Parameter{gamma, opts.gammaDecay == 0.0f ? nullptr : (opts.gammaDecay * sum(gamma * gamma)), opts.gammaProj},
+        Parameter{gamma, opts.gammaDecay == 0.0f ? nullptr : (opts.gammaDecay * sum(gamma * gamma)), gammaProj},
         Parameter{beta, nullptr, opts.betaProj}, Parameter{mean, nullptr, meanUpdater}, Parameter{var, nullptr, varUpdater}};
     return std::make_shared<Layer>(std::vector<LayerPtr>{input}, y, yTr, params);
 }
@@ -290,28 +349,77 @@ static LayerPtr meanPool(LayerPtr input) {
     return std::make_shared<Layer>(std::vector<LayerPtr>{input}, y, yTr, std::vector<Parameter>{});
 }
 
+void WRNOptions::verify() const {
+    // wrn.d:24-42
+    int regCtr = 0;
+    if (!std::isnan(maxgainNorm)) {
+        regCtr++;
+        enforce(maxgainNorm == 2.0f, "Only a maxgainNorm of 2 is currently supported.");
+    }
+    if (!std::isnan(lipschitzNorm)) regCtr++;
+    enforce(regCtr <= 1, "VGG models currently only support using one of maxgain and the lipschitz constraint");
+}
+
+// the regulariser settings every layer of a WRN derives from its options (wrn.d:60-74,106-121)
+struct WrnReg {
+    float maxgain = INFINITY, lambda = INFINITY, lipschitzNorm = NAN;
+    Operation lambdaSym;
+    explicit WrnReg(const WRNOptions& o) {
+        if (o.maxgainNorm == 2.0f) maxgain = o.maxNorm;
+        if (!std::isnan(o.lipschitzNorm)) {
+            lipschitzNorm = o.lipschitzNorm;
+            lambda = o.maxNorm;
+        }
+        lambdaSym = float32Constant(lambda);
+    }
+    BatchNormOptions bnOpts() const {
+        BatchNormOptions b;
+        b.maxgain = maxgain;
+        b.lipschitz = lambda;
+        return b;
+    }
+    // operator-norm projection for a convolution reading `in` (null when the constraint is off)
+    Projection proj(const LayerPtr& in, size_t stride, size_t pad) const {
+        if (lambda == INFINITY) return nullptr;
+        auto sh = in->trainOutput()->shape();
+        return projConvParams(lambdaSym, std::vector<size_t>(sh.begin() + 2, sh.end()), {stride, stride}, {pad, pad},
+                              lipschitzNorm);
+    }
+};
+
 static LayerPtr wrnBlock(LayerPtr inLayer, size_t u, size_t n, size_t s, const WRNOptions& opts) {
     // wrn.d:104-201
+    WrnReg reg(opts);
     auto convOpts = [&]() {
         Conv2DOptions o;
         o.padding = {1, 1};
         o.useBias = false;
         o.weightDecay = opts.weightDecay;
+        o.spectralDecay = opts.spectralDecay;
+        o.maxgain = reg.maxgain;
         return o;
     };
     LayerPtr res;
     for (size_t i = 0; i < n; ++i) {
-        res = relu(batchNorm(inLayer));
+        res = relu(batchNorm(inLayer, reg.bnOpts()));
         auto o1 = convOpts();
         o1.stride = {s, s};
-        res = relu(batchNorm(conv2D(res, u, {3, 3}, o1)));
-        res = conv2D(res, u, {3, 3}, convOpts());
+        // NB the reference passes padding [1, 1] to every projConvParams call, the 1x1 shortcut included (wrn.d:146,164,177)
+        o1.filterProj = reg.proj(res, s, 1);
+        res = relu(batchNorm(conv2D(res, u, {3, 3}, o1), reg.bnOpts()));
+        if (opts.dropout) res = dropout(res, 0.3f);   // maybeDropout, wrn.d:159
+        auto o2 = convOpts();
+        o2.filterProj = reg.proj(res, 1, 1);
+        res = conv2D(res, u, {3, 3}, o2);
         LayerPtr shortcut = inLayer;
         if (inLayer->output()->shape()[1] != res->output()->shape()[1]) {
             Conv2DOptions so;
             so.stride = {s, s};
             so.useBias = false;
             so.weightDecay = opts.weightDecay;
+            so.spectralDecay = opts.spectralDecay;
+            so.maxgain = reg.maxgain;
+            so.filterProj = reg.proj(inLayer, s, 1);
             shortcut = conv2D(inLayer, u, {1, 1}, so);
         }
         res = std::make_shared<Layer>(std::vector<LayerPtr>{res, shortcut}, res->output() + shortcut->output(),
@@ -325,15 +433,21 @@ static LayerPtr wrnBlock(LayerPtr inLayer, size_t u, size_t n, size_t s, const W
 LayerPtr wideResNet(Operation features, size_t depth, size_t width, WRNOptions opts) {
     // wrn.d:56-102
     size_t n = (depth - 4) / 6;
+    opts.verify();
+    WrnReg reg(opts);
+    auto src = dataSource(features);
     Conv2DOptions stem;
     stem.padding = {1, 1};
     stem.useBias = false;
     stem.weightDecay = opts.weightDecay;
-    auto pred = conv2D(dataSource(features), 16, {3, 3}, stem);
+    stem.spectralDecay = opts.spectralDecay;
+    stem.maxgain = reg.maxgain;
+    stem.filterProj = reg.proj(src, 1, 1);
+    auto pred = conv2D(src, 16, {3, 3}, stem);
     pred = wrnBlock(pred, 16 * width, n, opts.stride[0], opts);
     pred = wrnBlock(pred, 32 * width, n, opts.stride[1], opts);
     pred = wrnBlock(pred, 64 * width, n, opts.stride[2], opts);
-    return meanPool(relu(batchNorm(pred)));
+    return meanPool(relu(batchNorm(pred, reg.bnOpts())));
 }
 
 }  // namespace nnet

@@ -1,8 +1,9 @@
 // dopt/nnet.hpp -- C++ mirror of the parts of dopt.nnet that generate the hot path's graphs: Layer, the layer
 // constructors, DAGNetwork, the losses and the VGG / Wide-ResNet model builders.  Host-only graph construction; see the
-// .cpp for per-function citations.  The Lipschitz projections of nnet/lipschitz.d are available as free functions; the
-// per-layer maxgain / spectralDecay option branches (default-off in every BASELINE config) are not.
+// .cpp for per-function citations.  The research regularisers (nnet/lipschitz.d projections, the per-layer maxgain /
+// spectralDecay / lipschitz options, dropout) are default-off in every BASELINE config but mirrored.
 #pragma once
+#include <cmath>
 #include <random>
 
 #include "core.hpp"
@@ -45,12 +46,16 @@ struct Conv2DOptions {   // nnet/layers/conv.d:16-43
     ParamInitializer filterInit = heGaussianInit(), biasInit = constantInit(0.0f);
     Projection filterProj, biasProj;
     float weightDecay = 0.0f;
+    float maxgain = INFINITY;       // conv.d:27,128-150: project so that max_n ||y_n|| / ||x_n|| <= maxgain on the train batch
+    float spectralDecay = 0.0f;     // conv.d:28,112-115: + spectralDecay * (squared spectral-norm estimate of the filters)
     bool useBias = true;
 };
 struct DenseOptions {    // nnet/layers/dense.d:15-37
     ParamInitializer weightInit = heGaussianInit(), biasInit = constantInit(0.0f);
     Projection weightProj, biasProj;
     float weightDecay = 0.0f;
+    float maxgain = INFINITY;       // dense.d:108-131
+    float spectralDecay = 0.0f;     // dense.d:99-102
     bool useBias = true;
 };
 struct BatchNormOptions {   // nnet/layers/batchnorm.d:14-38
@@ -58,6 +63,8 @@ struct BatchNormOptions {   // nnet/layers/batchnorm.d:14-38
     Projection gammaProj, betaProj;
     float gammaDecay = 0.0f;
     float momentum = 0.9f;
+    float maxgain = INFINITY;       // batchnorm.d:97-113
+    float lipschitz = INFINITY;     // batchnorm.d:115-129: bound max_c |gamma_c| / sqrt(var_c + 1e-6)
 };
 
 LayerPtr dataSource(Operation var);
@@ -109,8 +116,14 @@ LayerPtr vgg(Operation features, const std::vector<int>& extractorSizes, std::ve
              VGGOptions opts = VGGOptions());
 
 struct WRNOptions {   // nnet/models/wrn.d:11-54
+    bool dropout = false;           // 0.3 after the first conv-bn-relu of every block (wrn.d:159)
+    float maxgainNorm = NAN;        // only 2 is supported (wrn.d:32)
+    float lipschitzNorm = NAN;      // 1, 2 or infinity: operator-norm constraint on every convolution (wrn.d:118-122)
+    float maxNorm = INFINITY;       // the bound used by whichever of the two is enabled
+    float spectralDecay = 0.0f;
     float weightDecay = 0.0001f;
     size_t stride[3] = {1, 2, 2};
+    void verify() const;            // wrn.d:24-42
 };
 LayerPtr wideResNet(Operation features, size_t depth, size_t width, WRNOptions opts = WRNOptions());
 

@@ -341,6 +341,95 @@ def test_lipschitz_norms_and_projection():
         H.matrix_norm(k, 1)                                           # "This function only operates on matrices"
 
 
+def test_maxgain_projection_bounds_the_layer_gain():
+    """conv.d:125-150 / dense.d:105-131: with `maxgain` set, the projected weights are the updated weights scaled by
+    1 / max(1, g / maxgain), g = max_n ||y_n|| / ||x_n|| over the train batch (evaluated with the weights BEFORE the step)."""
+    rng = np.random.RandomState(6)
+    xs = rng.randn(5, 3, 6, 6).astype(F)
+    x = H.float32((5, 3, 6, 6), xs)
+    H.seed(7)
+    l = H.data_source(x).conv2d(4, (3, 3), padding=(1, 1), use_bias=False, maxgain=0.5)
+    net = H.Network([x], [l])
+    w = net.params[0]
+    upd = H.Updater(H.SGD, [H.sum_(l.train_output * l.train_output)], network=net,
+                    hyper=[H.float32((), [0.0]), H.float32((), [0.0])])     # lr 0: the step is the projection alone
+    o = G.UpdaterOracle(upd)
+    w0 = w.get().copy()
+    o.step({})
+    y = ev([l.train_output])[0]
+    gain = np.sqrt(((y.reshape(5, -1) ** 2).sum(1) + 1e-8) / ((xs.reshape(5, -1) ** 2).sum(1) + 1e-8)).max()
+    assert gain > 0.5                                             # the constraint is active for He-initialised filters
+    np.testing.assert_allclose(o.value_of(w), w0 / (gain / 0.5), rtol=1e-5)
+    # dense: same rule
+    H.reset()
+    xd = H.float32((6, 10), rng.randn(6, 10).astype(F))
+    H.seed(8)
+    ld = H.data_source(xd).dense(7, use_bias=False, maxgain=1e6)
+    netd = H.Network([xd], [ld])
+    updd = H.Updater(H.SGD, [H.sum_(ld.train_output)], network=netd, hyper=[H.float32((), [0.0]), H.float32((), [0.0])])
+    od = G.UpdaterOracle(updd)
+    wd0 = netd.params[0].get().copy()
+    od.step({})
+    np.testing.assert_array_equal(od.value_of(netd.params[0]), wd0)   # gain far below the bound: weights untouched
+
+
+def test_batchnorm_lipschitz_projection_and_spectral_decay_graphs():
+    rng = np.random.RandomState(9)
+    x = H.float32((8, 3, 4, 4), (rng.randn(8, 3, 4, 4) * 2).astype(F))
+    l = H.data_source(x).batch_norm(lipschitz=0.25)
+    net = H.Network([x], [l])
+    gamma = net.params[0]
+    upd = H.Updater(H.SGD, [H.sum_(l.train_output)], network=net, hyper=[H.float32((), [0.0]), H.float32((), [0.0])])
+    o = G.UpdaterOracle(upd)
+    o.step({})
+    # batchnorm.d:115-129: norm = max_c |gamma_c| / sqrt(newRunningVar_c + 1e-6); gamma scaled by 1 / max(1, norm / bound)
+    new_var = o.value_of(net.params[3])
+    norm = np.abs(np.ones(3, F) / np.sqrt(new_var + 1e-6)).max()
+    np.testing.assert_allclose(o.value_of(gamma).ravel(), np.ones(3, F) / max(1.0, norm / 0.25), rtol=1e-5)
+    # spectral decay adds spectralDecay * ||W v||^2 (one power iteration from a uniform start) to the parameter loss
+    H.reset()
+    xc = H.float32((2, 3, 5, 5))
+    H.seed(10)
+    lc = H.data_source(xc).conv2d(4, (3, 3), padding=(1, 1), use_bias=False, spectral_decay=0.1).dense(3, spectral_decay=0.2)
+    netc = H.Network([xc], [lc])
+    ts = types([netc.param_loss])
+    assert ts.count("uniform") == 2
+    wv = netc.params[0].get().reshape(4, -1).astype(np.float64)
+    dv = netc.params[1 if len(netc.params[1].shape) == 2 else 2].get().astype(np.float64)
+    loss = float(ev([netc.param_loss])[0])
+    top = 0.1 * np.linalg.svd(wv, compute_uv=False)[0] ** 2 + 0.2 * np.linalg.svd(dv, compute_uv=False)[0] ** 2
+    assert 0 < loss <= top * (1 + 1e-5)                            # a power-iteration estimate never exceeds the true norm
+
+
+def test_wrn_regulariser_options():
+    """wrn.d:11-54,104-201: dropout after the first conv-bn-relu of each block; a Lipschitz constraint puts an operator-norm
+    projection on every convolution and bounds gamma / sqrt(var) in every batch norm; only one of maxgain / lipschitz."""
+    x = H.float32((2, 3, 8, 8))
+    y = H.float32((2, 10))
+
+    def plan_types(**kw):
+        H.seed(11)
+        l = H.wide_resnet(x, 10, 1, **kw).dense(10).softmax()
+        net = H.Network([x], [l])
+        upd = H.Updater(H.SGD, [H.cross_entropy(l.train_output, y) + net.param_loss], network=net)
+        return types(upd.plan_outputs()[0])
+    base = plan_types()
+    assert base.count("uniform") == 0 and base.count("maxElement") == 0
+    drop = plan_types(dropout=True)
+    assert drop.count("uniform") == 3                              # one per block (n = 1, three groups)
+    lip = plan_types(lipschitz_norm=float("inf"), max_norm=4.0)
+    # stem + 2 convs per block + a shortcut conv where the width changes (not in the first group at width 1: 16 -> 16);
+    # 2 batch norms per block + the final one
+    n_conv, n_bn = 1 + 3 * 2 + 2, 3 * 2 + 1
+    assert lip.count("maxElement") == n_conv + n_bn
+    mg = plan_types(maxgain_norm=2.0, max_norm=3.0)
+    assert mg.count("maxElement") == n_conv + n_bn
+    with pytest.raises(H.HostError):
+        plan_types(maxgain_norm=1.0, max_norm=3.0)                 # "Only a maxgainNorm of 2 is currently supported."
+    with pytest.raises(H.HostError):
+        plan_types(maxgain_norm=2.0, lipschitz_norm=2.0, max_norm=3.0)
+
+
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
     loss = H.sum_(w * w)

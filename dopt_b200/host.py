@@ -50,6 +50,7 @@ _h.dh_dense_reg.argtypes = [C.c_int, C.c_int64, C.c_float, C.c_int, C.c_float, C
 _h.dh_batch_norm_reg.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
 _h.dh_wide_resnet_reg.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float]
+_h.dh_vgg_reg.argtypes = [C.c_int, C.c_int, i64p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
 _h.dh_max_pool.argtypes = [C.c_int, i64p]
 _h.dh_dropout.argtypes = [C.c_int, C.c_float]
 _h.dh_wide_resnet.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_float]
@@ -353,6 +354,11 @@ def wide_resnet(features, depth, width, stride=(1, 2, 2), weight_decay=1e-4, dro
                                        lipschitz_norm, max_norm, spectral_decay))
 def vgg19(features, dense_sizes=(4096, 4096), batchnorm=False):
     return Layer(_h.dh_vgg19(features.h, _i64(dense_sizes), len(dense_sizes), int(batchnorm)))
+def vgg(features, layers=19, dense_sizes=(4096, 4096), batchnorm=False, dropout=False, maxgain_norm=float("nan"),
+        lipschitz_norm=float("nan"), max_norm=float("inf"), spectral_decay=0.0):
+    """vgg16 / vgg19 with the full VGGOptions (nnet/models/vgg.d:12-84)."""
+    return Layer(_h.dh_vgg_reg(features.h, layers, _i64(dense_sizes), len(dense_sizes), int(batchnorm), int(dropout),
+                               maxgain_norm, lipschitz_norm, max_norm, spectral_decay))
 
 
 class Network(object):

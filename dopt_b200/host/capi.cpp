@@ -395,6 +395,22 @@ int dh_wide_resnet_reg(int features, int64_t depth, int64_t width, const int64_t
     return addLayer(nnet::wideResNet(op(features), (size_t)depth, (size_t)width, o));
     DH_CATCH(-1)
 }
+// VGGOptions with the regulariser fields of vgg.d:12-49; layers = 16 or 19
+int dh_vgg_reg(int features, int layers, const int64_t* dense_sizes, int n, int batchnorm, int dropout, float maxgain_norm,
+               float lipschitz_norm, float max_norm, float spectral_decay) {
+    DH_TRY
+    nnet::VGGOptions o;
+    o.batchnorm = batchnorm != 0;
+    o.dropout = dropout != 0;
+    o.maxgainNorm = maxgain_norm;
+    o.lipschitzNorm = lipschitz_norm;
+    o.maxNorm = max_norm;
+    o.spectralDecay = spectral_decay;
+    enforce(layers == 16 || layers == 19, "vgg: 16 or 19 layers");
+    return addLayer(layers == 16 ? nnet::vgg16(op(features), sizes(dense_sizes, n), o)
+                                 : nnet::vgg19(op(features), sizes(dense_sizes, n), o));
+    DH_CATCH(-1)
+}
 int dh_vgg19(int features, const int64_t* dense_sizes, int n, int batchnorm) {
     DH_TRY
     nnet::VGGOptions o;

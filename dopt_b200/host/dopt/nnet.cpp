@@ -315,21 +315,61 @@ Operation squaredError(Operation hypothesis, Operation groundTruth) {
 }
 
 // ---- nnet/models/vgg.d ------------------------------------------------------------------------------------------------------
+void VGGOptions::verify() const {
+    // vgg.d:24-42
+    int regCtr = 0;
+    if (!std::isnan(maxgainNorm)) {
+        regCtr++;
+        enforce(maxgainNorm == 2.0f, "Only a maxgainNorm of 2 is currently supported.");
+    }
+    if (!std::isnan(lipschitzNorm)) regCtr++;
+    enforce(regCtr <= 1, "VGG models currently only support using one of maxgain and the lipschitz constraint");
+}
+
 LayerPtr vgg(Operation features, const std::vector<int>& sizes, std::vector<size_t> denseLayerSizes, VGGOptions opts) {
+    opts.verify();
+    const bool lip = !std::isnan(opts.lipschitzNorm);
+    const float maxgain = std::isnan(opts.maxgainNorm) ? INFINITY : opts.maxNorm;
     auto layers = dataSource(features);
+    int poolCtr = 0;
     for (int s : sizes) {   // makeExtractor, vgg.d:86-144
         if (s == -1) {
             layers = maxPool(layers, {2, 2});
+            poolCtr++;
         } else {
             Conv2DOptions co;
             co.padding = {1, 1};
+            co.maxgain = maxgain;
+            co.spectralDecay = opts.spectralDecay;
+            if (lip) {
+                auto sh = layers->trainOutput()->shape();
+                co.filterProj = projConvParams(float32Constant(opts.maxNorm), std::vector<size_t>(sh.begin() + 2, sh.end()),
+                                               {1, 1}, {1, 1}, opts.lipschitzNorm);
+            }
+            if (opts.dropout && poolCtr != 0) layers = dropout(layers, 0.2f);
             layers = conv2D(layers, (size_t)s, {3, 3}, co);
-            if (opts.batchnorm) layers = batchNorm(layers);
+            if (opts.batchnorm) {
+                BatchNormOptions bo;
+                bo.maxgain = maxgain;
+                bo.lipschitz = lip ? opts.maxNorm : INFINITY;
+                layers = batchNorm(layers, bo);
+            }
             layers = relu(layers);
         }
     }
-    for (auto s : denseLayerSizes) layers = relu(dense(layers, s));   // makeTop, vgg.d:146-174
+    for (auto s : denseLayerSizes) {   // makeTop, vgg.d:146-174
+        DenseOptions d;
+        d.maxgain = maxgain;
+        d.spectralDecay = opts.spectralDecay;
+        if (lip) d.weightProj = projMatrix(float32Constant(opts.maxNorm), opts.lipschitzNorm);
+        if (opts.dropout) layers = dropout(layers, 0.5f);
+        layers = relu(dense(layers, s, d));
+    }
     return layers;
+}
+LayerPtr vgg16(Operation features, std::vector<size_t> denseLayerSizes, VGGOptions opts) {
+    return vgg(features, {64, 64, -1, 128, 128, -1, 256, 256, 256, -1, 512, 512, 512, -1, 512, 512, 512, -1},
+               denseLayerSizes, opts);
 }
 LayerPtr vgg19(Operation features, std::vector<size_t> denseLayerSizes, VGGOptions opts) {
     return vgg(features, {64, 64, -1, 128, 128, -1, 256, 256, 256, 256, -1, 512, 512, 512, 512, -1, 512, 512, 512, 512, -1},

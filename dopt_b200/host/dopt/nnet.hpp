@@ -108,9 +108,16 @@ Projection projConvParams(Operation maxnorm, std::vector<size_t> inShape, std::v
 Operation crossEntropy(Operation hypothesis, Operation groundTruth);   // nnet/losses.d:23-26
 Operation squaredError(Operation hypothesis, Operation groundTruth);   // nnet/losses.d:35-40
 
-struct VGGOptions {   // nnet/models/vgg.d:12-49 (regulariser fields omitted)
+struct VGGOptions {   // nnet/models/vgg.d:12-49
+    bool dropout = false;           // 0.2 before every convolution after the first pool, 0.5 before every dense layer
     bool batchnorm = false;
+    float maxgainNorm = NAN;        // only 2 is supported
+    float lipschitzNorm = NAN;
+    float maxNorm = INFINITY;
+    float spectralDecay = 0.0f;
+    void verify() const;
 };
+LayerPtr vgg16(Operation features, std::vector<size_t> denseLayerSizes = {4096, 4096}, VGGOptions opts = VGGOptions());
 LayerPtr vgg19(Operation features, std::vector<size_t> denseLayerSizes = {4096, 4096}, VGGOptions opts = VGGOptions());
 LayerPtr vgg(Operation features, const std::vector<int>& extractorSizes, std::vector<size_t> denseLayerSizes,
              VGGOptions opts = VGGOptions());

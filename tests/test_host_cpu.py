@@ -430,6 +430,29 @@ def test_wrn_regulariser_options():
         plan_types(maxgain_norm=2.0, lipschitz_norm=2.0, max_norm=3.0)
 
 
+def test_vgg_regulariser_options():
+    """vgg.d:12-174: dropout 0.2 before every convolution after the first pool and 0.5 before every dense layer; the
+    Lipschitz option projects every convolution (projConvParams) and dense layer (projMatrix) and bounds every batch norm."""
+    x = H.float32((2, 3, 32, 32))
+    y = H.float32((2, 10))
+
+    def plan_types(layers, **kw):
+        H.seed(12)
+        l = H.vgg(x, layers, dense_sizes=(16, 16), **kw).dense(10).softmax()
+        net = H.Network([x], [l])
+        upd = H.Updater(H.SGD, [H.cross_entropy(l.train_output, y)], network=net)
+        return types(upd.plan_outputs()[0])
+    base16, base19 = plan_types(16), plan_types(19)
+    assert base16.count("convolution") == 13 and base19.count("convolution") == 16
+    assert base19.count("maxpool") == 5 and base19.count("uniform") == 0
+    drop = plan_types(19, dropout=True)
+    assert drop.count("uniform") == (16 - 2) + 2                   # all convs but the two before the first pool + two dense layers
+    lip = plan_types(19, batchnorm=True, lipschitz_norm=1.0, max_norm=5.0)
+    assert lip.count("maxElement") == 16 + 16 + 2                   # 16 convs + 16 batch norms + the two regularised dense layers
+    with pytest.raises(H.HostError):
+        plan_types(19, maxgain_norm=2.0, lipschitz_norm=2.0)
+
+
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
     loss = H.sum_(w * w)

@@ -96,18 +96,15 @@ struct SliceKernel : Kernel {
         }
         // contiguous when only the outermost non-unit dimension is cut
         bool contig = true;
-        bool seen_cut_or_extent = false;
         for (int i = in.rank - 1; i >= 0; --i) {
             bool full = (d.output.shape[i] == in.shape[i]);
             if (!full) {
                 // every dimension outside (to the left of) this one must have extent 1 in the output
                 for (int j = 0; j < i; ++j)
                     if (d.output.shape[j] != 1) contig = false;
-                seen_cut_or_extent = true;
                 break;
             }
         }
-        (void)seen_cut_or_extent;
         if (contig) {
             int64_t off = 0;
             for (int i = 0; i < in.rank; ++i) off += d.start[i] * p.in_stride[i];

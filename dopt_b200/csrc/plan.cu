@@ -624,7 +624,7 @@ static FzProgram make_program(Plan& p, const Region& R) {
             ins.dst = (uint8_t)phys[vd];
             if (last_use[vd] < 0) free_slots.push_back(phys[vd]);   // dead value (cannot happen for needed nodes)
         }
-        for (int o = 0; o < g.n_outputs; ++o) g.out_reg[o] = (uint8_t)phys[g.out_reg[o]];
+        for (int o = 0; o < g.n_outputs && o < FZ_MAX_OUTPUTS; ++o) g.out_reg[o] = (uint8_t)phys[g.out_reg[o]];
     }
     return g;
 }

@@ -465,25 +465,3 @@ class Updater(object):
         if t is None:
             raise HostError(_h.dh_last_error().decode())
         return dict((k, int(v)) for k, v in (l.split("=") for l in t.decode().splitlines() if l))
-
-
-def smoke_train_step():
-    """One SGD step of a tiny conv-BN-ReLU-dense net through the whole stack, checked against the oracle."""
-    from oracle import graph_eval
-    assert init(), "CUDA backend did not come up: " + init_error()
-    reset()
-    seed(7)
-    rng = np.random.RandomState(0)
-    x = float32((8, 16, 8, 8))
-    y = float32((8, 10))
-    net_out = data_source(x).conv2d(32, (3, 3), padding=(1, 1), weight_decay=1e-4, use_bias=False).batch_norm().relu() \
-        .dense(10).softmax()
-    net = Network([x], [net_out])
-    loss = cross_entropy(net_out.train_output, y) + net.param_loss
-    upd = Updater(SGD, [loss], network=net, hyper=[float32((), [0.1]), float32((), [0.9])])
-    fs = rng.randn(8, 16, 8, 8).astype(np.float32)
-    ls = np.eye(10, dtype=np.float32)[rng.randint(0, 10, 8)]
-    ref = graph_eval.UpdaterOracle(upd)
-    want = ref.step({x: fs, y: ls})[0]
-    got = upd.step({x: fs, y: ls})[0]
-    assert abs(float(got) - float(want)) < 2e-2 * max(1.0, abs(float(want))), (got, want)

@@ -89,3 +89,21 @@ def test_ctypes_layout_equals_c_layout(tmp_path):
     assert int(out["sizeof_param"]) == ctypes.sizeof(_lib.Param)
     for f in fields:
         assert int(out[f]) == getattr(_lib.Op, f).offset, f
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under dopt_b200/ (Python, C++, CUDA, D) may import, include, link or load it."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "dopt_b200")):
+        if os.sep + "build" in base or os.sep + "lib" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".d", "Makefile")):
+                continue
+            text = open(os.path.join(base, f), errors="replace").read()
+            # code references only (comments may cite test files): imports, includes, link flags, dlopen targets
+            for needle in ("from oracle", "import oracle", "#include <cudnn", "#include \"cudnn", "oracle/cudnn_replay",
+                           "libcudnn_replay", "-lcudnn", "\"libcudnn"):
+                if needle in text:
+                    bad.append((os.path.join(base, f), needle))
+    assert not bad, bad

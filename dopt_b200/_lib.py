@@ -15,7 +15,7 @@ MAX_INPUTS = 8
 
 FLOAT32, INT32 = 0, 1
 MATH_DEFAULT, MATH_FP32, MATH_BF16 = 0, 1, 2
-PLAN_FUSE, PLAN_CUDA_GRAPH = 1, 2
+PLAN_FUSE, PLAN_CUDA_GRAPH, PLAN_BF16_INTERIOR = 1, 2, 4
 
 
 class Tensor(C.Structure):

@@ -15,6 +15,7 @@
 // HBM-bound.  Algorithmic bytes: train 2V*4 (+ the statistics re-read, which the 126 MB L2 absorbs when the tensor was
 // just produced), grad 3V*4, inference 2V*4.
 #include "common.cuh"
+#include "flat.cuh"
 #include <cstdlib>
 
 namespace db {
@@ -447,6 +448,16 @@ struct BnTrainKernel : Kernel {
     float* mean_out2 = nullptr;
     float* var_out2 = nullptr;
     const void* counters_for = nullptr;
+    // bf16-interior mode (flat.cu): x and the result are NHWC bf16
+    bool flat = false;
+    const void* staged_x = nullptr;
+    Scratch fws;
+    const void* fws_for = nullptr;
+    bool can_flat() const override { return flat_supported(g.N, g.C, g.HW); }
+    void set_flat(bool on) override { flat = on; }
+    void set_staged_input(int input, const void* p) override {
+        if (input == 0) staged_x = p;
+    }
     bool set_stat_outputs(float* m, float* v) override {
         mean_out2 = m;
         var_out2 = v;
@@ -465,6 +476,27 @@ struct BnTrainKernel : Kernel {
         const float* x = (const float*)in[0];
         int64_t V = g.N * g.C * g.HW;
         float* y = (float*)out;
+        if (flat) {
+            DB_REQUIRE(staged_x && ab.staged && ab.skip_fp32, "batchNormTrain: flat mode needs staged input and output");
+            const size_t wb = flat_bn_workspace_bytes((int)g.C);
+            void* w = fws.get(wb);
+            if (w != fws_for) {
+                DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
+                fws_for = w;
+            }
+            FlatBnTrain a{};
+            a.x = staged_x; a.y = ab.staged;
+            a.scale = (const float*)in[1]; a.bias = (const float*)in[2];
+            a.rmean = (const float*)in[3]; a.rvar = (const float*)in[4];
+            a.new_mean = y + V; a.new_var = y + V + g.C;
+            a.mean2 = mean_out2; a.var2 = var_out2;
+            a.factor = factor;
+            a.relu = ab.relu;
+            a.workspace = w;
+            FlatGeom fg{g.N * g.HW, (int)g.C, (int)((g.C + 7) / 8 * 8)};
+            coef_dev = const_cast<float*>(flat_bn_train(a, fg, s));
+            return;
+        }
         float* part = (float*)ws.get(((size_t)splits * g.C * 2 + 4 * g.C) * sizeof(float));
         float* coef = part + (size_t)splits * g.C * 2;
         unsigned* counters = (unsigned*)(coef + 3 * g.C);
@@ -500,10 +532,20 @@ struct BnGradKernel : Kernel {
     Absorb ab;
     const Kernel* fwd = nullptr;   // batchNormTrain kernel whose relu gates dy (plan pass "absorb")
     const void* counters_for = nullptr;
+    // bf16-interior mode (flat.cu): dy, x, the optional addend and dx are NHWC bf16; mean / istd come from the forward pass
+    bool flat = false;
+    const void* staged_in[4] = {nullptr, nullptr, nullptr, nullptr};   // 0 = dy, 1 = x, 3 = addend
+    Scratch fws;
+    const void* fws_for = nullptr;
+    bool can_flat() const override { return flat_supported(g.N, g.C, g.HW); }
+    void set_flat(bool on) override { flat = on; }
+    void set_staged_input(int input, const void* p) override {
+        if (input >= 0 && input < 4) staged_in[input] = p;
+    }
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
     void set_absorbed(const Absorb& a) override {
         DB_REQUIRE(!a.relu, "batchNormGrad cannot absorb a relu");
-        DB_REQUIRE((a.redirect != nullptr) == (a.addend != nullptr), "batchNormGrad: redirect and addend come together");
+        DB_REQUIRE(flat || (a.redirect != nullptr) == (a.addend != nullptr), "batchNormGrad: redirect and addend come together");
         ab = a;
     }
     void set_gate_source(const Kernel* forward) override { fwd = forward; }
@@ -522,6 +564,28 @@ struct BnGradKernel : Kernel {
         const float* x = (const float*)in[1];
         int64_t V = g.N * g.C * g.HW;
         float* dx = (float*)out;
+        if (flat) {
+            const float* fc = fwd ? (const float*)fwd->aux_ptr() : nullptr;
+            DB_REQUIRE(fc, "batchNormGrad: flat mode needs the forward pass's coefficients");
+            DB_REQUIRE(staged_in[0] && staged_in[1] && ab.staged && ab.skip_fp32, "batchNormGrad: flat mode needs staged operands and output");
+            const size_t wb = flat_bn_workspace_bytes((int)g.C);
+            void* w = fws.get(wb);
+            if (w != fws_for) {
+                DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
+                fws_for = w;
+            }
+            FlatBnGrad a{};
+            a.dy = staged_in[0]; a.x = staged_in[1]; a.addend = staged_in[3];
+            a.dx = ab.staged;
+            a.scale = (const float*)in[2];
+            a.fcoef = fc;
+            a.gate = true;
+            a.dscale = dx + V; a.dbias = dx + V + g.C;
+            a.workspace = w;
+            FlatGeom fg{g.N * g.HW, (int)g.C, (int)((g.C + 7) / 8 * 8)};
+            flat_bn_grad(a, fg, s);
+            return;
+        }
         float* part = (float*)ws.get(((size_t)splits * g.C * 4 + 5 * g.C) * sizeof(float));
         float* coef = part + (size_t)splits * g.C * 4;
         unsigned* counters = (unsigned*)(coef + 4 * g.C);

@@ -122,6 +122,14 @@ struct Kernel {
     // batchNormTrain: also write the running statistics (packed tail of the result) straight to these buffers -- the plan
     // passes the caller's return buffers (dopt.online feeds them back as the new `mean` / `var`) and skips the copies
     virtual bool set_stat_outputs(float* /*new_mean*/, float* /*new_var*/) { return false; }
+    // bf16-interior plans (plan.cu, pass "residency"; kernels in flat.cu).  A tensor-core convolution can write its result
+    // as NHWC bf16 (set_staged_output) instead of NCHW fp32.  A "flat" batchNormTrain / batchNormGrad / add reads its tensor
+    // operands from the NHWC bf16 copies given with set_staged_input (batchNormGrad: index 3 = the addend of an absorbed
+    // residual add) and writes only Absorb::staged; the fp32 pointers passed to run() are then ignored.
+    virtual bool can_stage_output() const { return false; }
+    virtual void set_staged_output(void* /*nhwc_bf16*/) {}
+    virtual bool can_flat() const { return false; }
+    virtual void set_flat(bool /*on*/) {}
     virtual const void* aux_ptr() const { return nullptr; }
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use

@@ -45,6 +45,8 @@ struct ConvKernel : Kernel {
     void set_staged_input(int input, const void* p) override { conv_tc_set_staged(tc, input, p); }
     bool filter_pack(int input, FilterPack* d) const override { return tc && conv_tc_filter_pack(tc, input, d); }
     void set_packed_filter(const void* p) override { conv_tc_set_packed_filter(tc, p); }
+    bool can_stage_output() const override { return conv_tc_can_stage_output(tc); }
+    void set_staged_output(void* p) override { conv_tc_set_staged_output(tc, p); }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == 2, "convolution ops take two inputs");
         const float* a = (const float*)in[0];

@@ -22,6 +22,7 @@
 //   * dead nodes (left over after the rewrites) are dropped.
 // DOPT_B200_PLAN_CUDA_GRAPH captures the launch sequence once and replays it.
 #include "common.cuh"
+#include "flat.cuh"
 #include "fused.cuh"
 #include "pointwise.cuh"
 #include <algorithm>
@@ -70,6 +71,9 @@ struct Node {
     int msum_a = -1, msum_b = -1;   // operands: sum_i a[i]*b[i] (b = -1: plain sum)
     int gate_from = -1;         // batchNormGrad: batchNormTrain node whose relu gates the incoming gradient (reluGrad absorbed)
     int in_override[DOPT_B200_MAX_INPUTS] = {-1, -1, -1, -1, -1, -1, -1, -1};   // read this node instead of deps[k]
+    // bf16-interior activations (pass "residency")
+    bool flat = false;          // batchNormTrain / batchNormGrad / add working on NHWC bf16 operands and result (flat.cu)
+    int out_stage = -1;         // tensor-core convolution whose epilogue writes this stage (NHWC bf16) instead of NCHW fp32
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
     void* ptr = nullptr;        // resolved pointer for this execution
@@ -88,7 +92,8 @@ struct Region {
     std::vector<int> out_nodes;                       // region nodes whose value is needed outside
 };
 
-enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6, ITEM_MSUM = 7 };
+enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6, ITEM_MSUM = 7,
+                ITEM_UNSTAGE = 8 };
 struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
@@ -103,6 +108,8 @@ struct Stage {
     void* buf = nullptr;
     int producer = -1;  // node whose kernel writes the staged copy itself (no staging launch)
     std::vector<std::pair<int, int>> users;   // (node, input index)
+    bool must = false;      // a reader cannot stage for itself (flat kernels), or the value has no fp32 copy at all
+    int unstage_to = -1;    // node whose fp32 buffer receives an NCHW fp32 copy of this stage (a bf16-resident value with fp32 readers)
 };
 
 // gradients that are all-reduced together: their buffers are carved from one arena so that ONE ncclAllReduce covers them
@@ -734,6 +741,15 @@ static void schedule(Plan& p) {
             if (only_buckets && hold >= 0) item_key[kv.second] = std::max(item_key[kv.second], hold);
         }
     }
+    // NCHW fp32 copies of bf16-resident values: made by a conversion launch right after the producer; fp32 readers wait for it
+    std::vector<int> unstage_item(N.size(), -1);
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        const Stage& st = p.stages[si];
+        if (st.unstage_to < 0 || st.producer < 0) continue;
+        items.push_back({ITEM_UNSTAGE, (int)si, false});
+        item_key.push_back(key_of(st.producer) + 1);
+        unstage_item[st.unstage_to] = (int)items.size() - 1;
+    }
     // the item that makes the value read through `d` available: the bucket when the view chain passes an in-place allreduce
     auto producer_item = [&](int d, bool* via_bucket) {
         int id = d;
@@ -748,6 +764,7 @@ static void schedule(Plan& p) {
             if (via_bucket) *via_bucket = true;
             return item_of_bucket[N[id].bucket];
         }
+        if (unstage_item[id] >= 0) return unstage_item[id];
         return item_of_node[id];
     };
     std::vector<std::set<int>> succ(items.size());
@@ -780,6 +797,10 @@ static void schedule(Plan& p) {
     }
     for (size_t b = 0; b < p.buckets.size(); ++b)
         for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        const Stage& st = p.stages[si];
+        if (st.unstage_to >= 0 && st.producer >= 0) add_edge(item_of_node[st.producer], unstage_item[st.unstage_to]);
+    }
     for (size_t si = 0; si < p.stages.size(); ++si) {
         const Stage& st = p.stages[si];
         if (st.users.empty()) continue;
@@ -1138,6 +1159,282 @@ static void absorb(Plan& p) {
         }
 }
 
+// ---- pass "residency": bf16-interior activations (DOPT_B200_PLAN_BF16_INTERIOR) --------------------------------------------
+// After "absorb" an activation between two tensor-core convolutions is touched by: the convolution epilogue that writes it,
+// batchNormTrain (statistics + apply), batchNormGrad (x again, and dy), the residual adds, and the convolutions reading the
+// staged NHWC bf16 copy.  This pass decides, per value, whether it can live ONLY as NHWC bf16:
+//   * a batchNormTrain whose relu'd result only feeds staged convolutions and whose x comes from a producer that can write
+//     NHWC bf16 (tensor-core convolution, residual add) runs "flat": bf16 in, bf16 out (flat.cu);
+//   * its batchNormGrad runs flat when dy (and the addend of an absorbed residual-gradient add) can be produced staged and
+//     the result has a staged reader; a stand-alone add likewise;
+//   * a tensor-core convolution whose result is only read staged writes NHWC bf16 from its epilogue and has no fp32 buffer;
+//   * the rare fp32 reader of a bf16-resident value (the last residual sum of a WRN feeds a legacy batch norm) gets an NCHW
+//     fp32 copy from one conversion launch (ITEM_UNSTAGE).
+// Everything a non-participating op reads, every plan input and output stays fp32.
+static void residency(Plan& p) {
+    auto& N = p.nodes;
+    const int n_nodes = (int)N.size();
+    struct Read {
+        int node, k;   // k = input index; 3 on a batchNormGrad = the addend of its absorbed add
+        int64_t off;
+    };
+    std::vector<std::vector<Read>> reads(n_nodes);
+    for (int u = 0; u < n_nodes; ++u) {
+        const Node& U = N[u];
+        if (!U.needed || U.alias_of >= 0) continue;
+        auto push = [&](int dep, int k, int reader) {
+            int64_t off = 0;
+            const int r = root_of(p, dep, &off);
+            reads[r].push_back({reader, k, off});
+        };
+        if (U.absorbed_by >= 0) {
+            // a relu written by its batchNormTrain reads nothing itself; an add folded into a batchNormGrad: that kernel reads the addend
+            if (N[U.absorbed_by].absorb_add == u) push(N[U.absorbed_by].absorb_addend, 3, U.absorbed_by);
+            continue;
+        }
+        if (U.msum) {
+            for (int d : {U.msum_a, U.msum_b})
+                if (d >= 0) push(d, 7, u);
+            continue;
+        }
+        if (U.pw_op >= 0) {
+            if (U.pw_unary) push(U.eff_in[0], 0, u);
+            else {
+                push(U.eff_in[0], U.pw_mode == dbk::B_SCALAR_A ? 7 : 0, u);
+                push(U.eff_in[1], U.pw_mode == dbk::B_SCALAR_B ? 7 : 1, u);
+            }
+            continue;
+        }
+        for (size_t k = 0; k < U.deps.size(); ++k) push(U.in_override[k] >= 0 ? U.in_override[k] : U.deps[k], (int)k, u);
+    }
+    struct Shape {
+        int n = 0, c = 0;
+        int64_t hw = 0;
+        bool ok = false;
+        bool operator==(const Shape& o) const { return ok && o.ok && n == o.n && c == o.c && hw == o.hw; }
+    };
+    auto shape_of = [](const dopt_b200_tensor& t) {
+        Shape s;
+        if (t.rank != 4 || t.dtype != DOPT_B200_FLOAT32) return s;
+        s.n = (int)t.shape[0];
+        s.c = (int)t.shape[1];
+        s.hw = t.shape[2] * t.shape[3];
+        s.ok = true;
+        return s;
+    };
+    // natural NCHW shape and head size of the value a root node carries
+    auto value_shape = [&](int r) {
+        const Node& R = N[r];
+        if (R.type == "batchNormTrain") return shape_of(R.op.inputs[0]);
+        if (R.type == "batchNormGrad") return shape_of(R.op.inputs[1]);
+        return shape_of(R.op.output);
+    };
+    auto head_bytes = [&](int r) {
+        const Shape s = value_shape(r);
+        return s.ok ? (int64_t)s.n * s.c * s.hw * 4 : N[r].bytes;
+    };
+    std::vector<char> is_out(n_nodes, 0);   // the head (the activation part) of the root is a plan output
+    for (int o : p.outputs) {
+        int64_t off = 0;
+        const int r = root_of(p, o, &off);
+        if (off < head_bytes(r)) is_out[r] = 1;
+    }
+    auto standalone_add = [&](const Node& A) {
+        return A.type == "add" && A.region < 0 && A.pw_op >= 0 && A.pw_mode == dbk::B_TENSOR && A.deps.size() == 2 && A.kernel &&
+               A.op.output.rank == 4;
+    };
+    auto wants_staged = [&](const Read& rd, const Shape& vs) {
+        if (rd.off != 0 || rd.k > 3) return false;
+        const Node& U = N[rd.node];
+        if (!U.kernel) return false;
+        if (U.flat) {
+            if (U.type == "batchNormTrain") return rd.k == 0;
+            if (U.type == "batchNormGrad") return rd.k == 0 || rd.k == 1 || rd.k == 3;
+            return rd.k < 2;   // add
+        }
+        if (rd.k < 2 && U.kernel->staged_bytes(rd.k) > 0) return shape_of(U.op.inputs[rd.k]) == vs;   // tensor-core convolution
+        return false;
+    };
+    // can the value read through `dep` be written as NHWC bf16 by whatever produces it?
+    auto stage_capable = [&](int dep, const Shape& want) {
+        int64_t off = 0;
+        const int r = root_of(p, dep, &off);
+        if (off != 0) return false;
+        const Node* P = &N[r];
+        if (!(value_shape(r) == want)) return false;
+        if (P->absorbed_by >= 0) P = &N[P->absorbed_by];   // a relu / add whose value another kernel writes
+        if (!P->kernel) return false;
+        if (P->kernel->can_stage_output()) return true;
+        if (P->type == "batchNormTrain" || P->type == "batchNormGrad") return P->kernel->can_absorb();
+        return standalone_add(*P) && P->kernel->can_absorb();
+    };
+    auto counts = [&](int r, int* n_staged, int* n_fp32) {
+        const Shape vs = value_shape(r);
+        const int64_t head = head_bytes(r);
+        *n_staged = *n_fp32 = 0;
+        for (const Read& rd : reads[r]) {
+            if (rd.off >= head) continue;
+            if (wants_staged(rd, vs)) ++*n_staged;
+            else ++*n_fp32;
+        }
+    };
+    // A: batchNormTrain (independent of the other decisions: its result only feeds staged convolutions)
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& B = N[i];
+        if (!B.needed || B.alias_of >= 0 || B.type != "batchNormTrain" || !B.kernel || !B.kernel->can_flat()) continue;
+        if (B.absorb_relu < 0 || B.absorb_stage < 0 || !B.absorb_skip) continue;
+        const Shape xs = shape_of(B.op.inputs[0]);
+        if (!xs.ok || !stage_capable(B.deps[0], xs)) continue;
+        B.flat = true;
+    }
+    // B: batchNormGrad and add, readers before producers
+    for (int i = n_nodes - 1; i >= 0; --i) {
+        Node& U = N[i];
+        if (!U.needed || U.alias_of >= 0 || !U.kernel || U.absorbed_by >= 0 || !U.kernel->can_flat()) continue;
+        const bool is_grad = U.type == "batchNormGrad";
+        if (!is_grad && !standalone_add(U)) continue;
+        const int vn = (is_grad && U.absorb_add >= 0) ? U.absorb_add : i;
+        if (N[vn].alias_of >= 0 || is_out[vn]) continue;
+        int n_st = 0, n_fp = 0;
+        counts(vn, &n_st, &n_fp);
+        if (n_st < 1) continue;
+        if (is_grad) {
+            if (U.gate_from < 0 || !N[U.gate_from].flat || U.deps.size() != 3) continue;
+            const Shape xs = shape_of(U.op.inputs[1]);
+            if (!xs.ok || !(value_shape(vn) == xs)) continue;
+            if (!stage_capable(U.in_override[0] >= 0 ? U.in_override[0] : U.deps[0], xs)) continue;
+            if (U.absorb_add >= 0 && !stage_capable(U.absorb_addend, xs)) continue;
+        } else {
+            const Shape os = shape_of(U.op.output);
+            if (!os.ok || !stage_capable(U.deps[0], os) || !stage_capable(U.deps[1], os)) continue;
+        }
+        U.flat = true;
+    }
+    // C: the flat kernels' operands become stage users
+    auto find_stage = [&](int dep, const Shape& sh, bool make) {
+        int64_t off = 0;
+        const int r = root_of(p, dep, &off);
+        for (size_t si = 0; si < p.stages.size(); ++si) {
+            const Stage& st = p.stages[si];
+            int64_t o2 = 0;
+            if (root_of(p, st.src_dep, &o2) == r && o2 == off && st.n == sh.n && st.c == sh.c && st.hw == sh.hw) return (int)si;
+        }
+        if (!make) return -1;
+        Stage st;
+        st.src_dep = dep;
+        st.n = sh.n;
+        st.c = sh.c;
+        st.hw = sh.hw;
+        p.stages.push_back(st);
+        return (int)p.stages.size() - 1;
+    };
+    auto use = [&](int dep, const Shape& sh, int node, int k) {
+        const int si = find_stage(dep, sh, true);
+        p.stages[si].users.push_back({node, k});
+        p.stages[si].must = true;
+    };
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& U = N[i];
+        if (!U.flat) continue;
+        U.kernel->set_flat(true);
+        if (U.type == "batchNormTrain") {
+            use(U.deps[0], shape_of(U.op.inputs[0]), i, 0);
+        } else if (U.type == "batchNormGrad") {
+            const Shape xs = shape_of(U.op.inputs[1]);
+            use(U.in_override[0] >= 0 ? U.in_override[0] : U.deps[0], xs, i, 0);
+            use(U.deps[1], xs, i, 1);
+            if (U.absorb_add >= 0) use(U.absorb_addend, xs, i, 3);
+        } else {
+            use(U.deps[0], shape_of(U.op.output), i, 0);
+            use(U.deps[1], shape_of(U.op.output), i, 1);
+        }
+    }
+    auto drop_buffer = [&](Node& n) {
+        if (!n.buf) return;
+        cudaFree(n.buf);
+        n.buf = nullptr;
+        p.device_bytes -= n.bytes;
+    };
+    // D: results of the flat kernels
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& U = N[i];
+        if (!U.flat) continue;
+        if (U.type == "batchNormTrain") {
+            p.stages[U.absorb_stage].must = true;
+            continue;
+        }
+        const int vn = (U.type == "batchNormGrad" && U.absorb_add >= 0) ? U.absorb_add : i;
+        const int si = find_stage(vn, value_shape(vn), true);
+        Stage& st = p.stages[si];
+        if (st.producer >= 0 && st.producer != i && st.producer != vn) continue;   // (cannot happen: one value, one producer)
+        if (U.absorb_stage >= 0 && U.absorb_stage != si) p.stages[U.absorb_stage].producer = -1;
+        st.producer = i;
+        st.must = true;
+        U.absorb_stage = si;
+        U.absorb_skip = true;
+        int n_st = 0, n_fp = 0;
+        counts(vn, &n_st, &n_fp);
+        if (n_fp > 0) st.unstage_to = vn;
+        else if (vn != i || U.type == "add") drop_buffer(N[vn]);   // (a batchNormGrad's own buffer also holds dscale / dbias)
+    }
+    // E: stages that gained users above and whose value comes from a legacy batchNormGrad / add: that kernel writes them
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        Stage& st = p.stages[si];
+        if (st.producer >= 0 || st.users.empty()) continue;
+        int64_t off = 0;
+        const int b = root_of(p, st.src_dep, &off);
+        Node& B = N[b];
+        if (off != 0 || !B.kernel || B.flat || B.absorbed_by >= 0 || B.absorb_stage >= 0 || !B.kernel->can_absorb()) continue;
+        const Shape bs = value_shape(b);
+        if (!(bs.ok && bs.n == st.n && bs.c == st.c && bs.hw == st.hw)) continue;
+        if (B.type == "batchNormGrad" && B.absorb_add < 0) {
+            st.producer = b;
+            B.absorb_stage = (int)si;
+        } else if (standalone_add(B) && !getenv("DOPT_B200_NO_ADD_STAGE")) {
+            st.producer = b;
+            B.absorb_stage = (int)si;
+        }
+    }
+    // legacy batchNormGrad kernels whose dx is now only read staged need not write the fp32 copy
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& G = N[i];
+        if (!G.needed || G.flat || G.type != "batchNormGrad" || G.absorb_stage < 0 || G.absorb_add >= 0 || is_out[i]) continue;
+        int n_st = 0, n_fp = 0;
+        counts(i, &n_st, &n_fp);
+        if (n_fp == 0 && n_st > 0) {
+            G.absorb_skip = true;
+            p.stages[G.absorb_stage].must = true;
+        }
+    }
+    // F: tensor-core convolutions whose result is only read staged
+    for (int i = 0; i < n_nodes; ++i) {
+        Node& Cn = N[i];
+        if (!Cn.needed || Cn.alias_of >= 0 || !Cn.kernel || !Cn.kernel->can_stage_output() || is_out[i]) continue;
+        const Shape os = shape_of(Cn.op.output);
+        if (!os.ok) continue;
+        int n_st = 0, n_fp = 0;
+        counts(i, &n_st, &n_fp);
+        if (n_st < 1 || n_fp > 0) continue;
+        const int si = find_stage(i, os, false);
+        if (si < 0 || p.stages[si].producer >= 0) continue;
+        // every staged reader must be a user of this one stage
+        if ((int)p.stages[si].users.size() != n_st) continue;
+        p.stages[si].producer = i;
+        p.stages[si].must = true;
+        Cn.out_stage = si;
+        drop_buffer(Cn);
+    }
+    if (getenv("DOPT_B200_PLAN_DUMP")) {
+        int n_flat = 0, n_conv = 0, n_un = 0;
+        for (auto& n : N) {
+            n_flat += n.flat ? 1 : 0;
+            n_conv += n.out_stage >= 0 ? 1 : 0;
+        }
+        for (auto& st : p.stages) n_un += st.unstage_to >= 0 ? 1 : 0;
+        fprintf(stderr, "PLAN residency: %d flat kernels, %d convolutions writing NHWC bf16, %d fp32 copies\n", n_flat, n_conv, n_un);
+    }
+}
+
 static void build(Plan& p) {
     auto& N = p.nodes;
     lower_views(p);
@@ -1239,22 +1536,26 @@ static void build(Plan& p) {
             DB_CUDA(cudaMalloc(&p.packs_dev, p.packs.size() * sizeof(FilterPack)));
         }
         if (!getenv("DOPT_B200_NO_ABSORB")) absorb(p);
-        for (auto& st : p.stages) {
-            if (st.users.size() < 2 && st.producer < 0) {
+        if ((p.flags & DOPT_B200_PLAN_BF16_INTERIOR) && !getenv("DOPT_B200_NO_ABSORB") && !getenv("DOPT_B200_NO_RESIDENT")) residency(p);
+        for (size_t si = 0; si < p.stages.size(); ++si) {
+            Stage& st = p.stages[si];
+            if (st.users.size() < 2 && st.producer < 0 && !st.must) {
                 st.users.clear();   // a single reader stages for itself
                 continue;
             }
             size_t bytes = staged_nhwc_bytes(st.n, st.c, st.hw);
             DB_CUDA(cudaMalloc(&st.buf, bytes));
+            DB_CUDA(cudaMemset(st.buf, 0, bytes));   // channel padding is never written by a convolution epilogue
             p.device_bytes += (int64_t)bytes;
             for (auto& u : st.users) N[u.first].kernel->set_staged_input(u.second, st.buf);
+            if (st.producer >= 0 && N[st.producer].out_stage == (int)si) N[st.producer].kernel->set_staged_output(st.buf);
         }
     }
     schedule(p);
     p.direct_out.assign(p.outputs.size(), 0);
     if (getenv("DOPT_B200_PLAN_DUMP")) {
         // one line per scheduled item: kind, op type, output volume, the op types of its operands
-        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack", "msum"};
+        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack", "msum", "unstage"};
         for (const Item& it : p.order) {
             if (it.kind == ITEM_KERNEL || it.kind == ITEM_PW_SCALAR || it.kind == ITEM_COPY) {
                 const Node& n = N[it.id];
@@ -1452,6 +1753,10 @@ static void run_items(Plan& p, cudaStream_t s) {
             const Stage& st = p.stages[it.id];
             stage_nchw_to_nhwc_bf16((const float*)N[st.src_dep].ptr, st.buf, st.n, st.c, st.hw, s);
             label = "stageNHWC";
+        } else if (it.kind == ITEM_UNSTAGE) {
+            const Stage& st = p.stages[it.id];
+            unstage_nhwc_bf16_to_nchw(st.buf, (float*)N[st.unstage_to].ptr, st.n, st.c, st.hw, s);
+            label = "unstageNCHW";
         } else if (it.kind == ITEM_COPY) {
             Node& n = N[it.id];
             DB_CUDA(cudaMemcpyAsync(n.ptr, N[n.deps[0]].ptr, (size_t)n.bytes, cudaMemcpyDeviceToDevice, s));

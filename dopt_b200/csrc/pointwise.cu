@@ -9,6 +9,7 @@
 //   through double with a truncating conversion back to int).
 // HBM-bound: 2V*4 B (unary) or 3V*4 B (binary) per launch.
 #include "common.cuh"
+#include "flat.cuh"
 #include "pointwise.cuh"
 
 namespace db {
@@ -210,8 +211,16 @@ struct PointwiseKernel : Kernel {
     bool can_absorb() const override {
         return op == dbk::OP_ADD && dtype == DOPT_B200_FLOAT32 && aN > 0 && aN < 65536 && aC < (1 << 24) && aHW < (1ll << 30);
     }
+    // bf16-interior mode (flat.cu): both operands and the result are NHWC bf16
+    bool flat = false;
+    const void* staged_in[2] = {nullptr, nullptr};
+    bool can_flat() const override { return can_absorb() && flat_supported(aN, aC, aHW); }
+    void set_flat(bool on) override { flat = on; }
+    void set_staged_input(int input, const void* p) override {
+        if (input >= 0 && input < 2) staged_in[input] = p;
+    }
     void set_absorbed(const Absorb& a) override {
-        DB_REQUIRE(!a.relu && !a.redirect && !a.skip_fp32, "pointwise add can only absorb the NHWC staging");
+        DB_REQUIRE(!a.relu && !a.redirect && (flat || !a.skip_fp32), "pointwise add can only absorb the NHWC staging");
         ab = a;
     }
     PointwiseKernel(const dopt_b200_op& d) {
@@ -233,6 +242,11 @@ struct PointwiseKernel : Kernel {
     }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == (unary ? 1 : 2), "pointwise: wrong number of inputs");
+        if (flat) {
+            DB_REQUIRE(staged_in[0] && staged_in[1] && ab.staged, "add: flat mode needs staged operands and output");
+            flat_add(staged_in[0], staged_in[1], ab.staged, aN * aHW * ((aC + 7) / 8 * 8), s);
+            return;
+        }
         if (ab.staged) {
             const int Cp = (int)((aC + 7) / 8 * 8);
             if (aHW > 64) {

@@ -24,5 +24,8 @@ void conv_tc_set_staged(ConvTc* c, int input, const void* nhwc_bf16);
 size_t conv_tc_staged_bytes(const ConvTc* c, int input);
 bool conv_tc_filter_pack(const ConvTc* c, int input, FilterPack* desc);
 void conv_tc_set_packed_filter(ConvTc* c, const void* packed);
+// fwd / dgrad: write the result as [N][H][W][Cp] bf16 into `nhwc_bf16` instead of NCHW fp32 into `out` (nullptr: back to fp32)
+bool conv_tc_can_stage_output(const ConvTc* c);
+void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16);
 
 }  // namespace db

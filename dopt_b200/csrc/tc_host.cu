@@ -611,6 +611,7 @@ struct ConvTc {
     PixelBox box;
     const void* pre[2] = {nullptr, nullptr};   // operands already staged as NHWC bf16 by the plan
     const void* pre_w = nullptr;               // filter already packed by the plan (fwd / dgrad)
+    void* out_staged = nullptr;                // fwd / dgrad: write the result as [N][H][W][Cp] bf16 here instead of NCHW fp32
 };
 
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
@@ -634,6 +635,10 @@ void conv_tc_set_packed_filter(ConvTc* c, const void* packed) {
 }
 void conv_tc_set_staged(ConvTc* c, int input, const void* p) {
     if (c && input >= 0 && input < 2) c->pre[input] = p;
+}
+bool conv_tc_can_stage_output(const ConvTc* c) { return c && c->kind != CONV_WGRAD; }
+void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16) {
+    if (c && c->kind != CONV_WGRAD) c->out_staged = nhwc_bf16;
 }
 size_t conv_tc_staged_bytes(const ConvTc* c, int input) {
     if (!c) return 0;
@@ -724,6 +729,11 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
     a.o_off = 0;
     a.o_sn = (long long)g.K * g.P * g.Q; a.o_sc = (long long)g.P * g.Q; a.o_sh = g.Q; a.o_sw = 1;
     a.out = y;
+    if (c->out_staged) {   // bf16-interior plans: the next reader takes NHWC bf16 (channel padding stays zero from allocation)
+        a.out_kind = TC_OUT_BF16;
+        a.o_sn = (long long)g.P * g.Q * c->Kp; a.o_sc = 1; a.o_sh = (long long)g.Q * c->Kp; a.o_sw = c->Kp;
+        a.out = c->out_staged;
+    }
     a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
@@ -817,12 +827,21 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
             a.o_sn = (long long)g.C * g.H * g.W; a.o_sc = (long long)g.H * g.W;
             a.o_sh = (long long)g.u * g.W; a.o_sw = g.v;
             a.out = dx;
+            if (c->out_staged) {
+                const long long Cp = c->Cp;
+                a.out_kind = TC_OUT_BF16;
+                a.o_off = ((long long)pa * g.W + pb) * Cp;
+                a.o_sn = (long long)g.H * g.W * Cp; a.o_sc = 1;
+                a.o_sh = (long long)g.u * g.W * Cp; a.o_sw = (long long)g.v * Cp;
+                a.out = c->out_staged;
+            }
             a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }
     if (need_zero) {
-        DB_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.N * g.C * g.H * g.W * sizeof(float), s));
+        if (c->out_staged) DB_CUDA(cudaMemsetAsync(c->out_staged, 0, (size_t)g.N * g.H * g.W * c->Cp * 2, s));
+        else DB_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.N * g.C * g.H * g.W * sizeof(float), s));
         count_launch();
     }
     for (auto& a : launches) tc_launch<TC_MODE_CONV>(tmA, tmB, a, a.m_tiles * a.n_tiles, s);

@@ -14,7 +14,9 @@ namespace dopt {
 namespace cuda {
 
 static void* g_stream = nullptr;
-static int g_plan_flags = DOPT_B200_PLAN_FUSE | DOPT_B200_PLAN_CUDA_GRAPH;
+// bf16 interior is part of the default (production) configuration together with MATH_BF16; setPlanFlags / setMath(MATH_FP32)
+// select the fp32-storage and strict-fp32 variants (include/dopt_b200.h documents the numerics of each)
+static int g_plan_flags = DOPT_B200_PLAN_FUSE | DOPT_B200_PLAN_CUDA_GRAPH | DOPT_B200_PLAN_BF16_INTERIOR;
 static int g_math = DOPT_B200_MATH_DEFAULT;
 static std::string g_init_error;
 

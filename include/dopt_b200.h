@@ -169,6 +169,12 @@ int dopt_b200_plan_set_outputs(dopt_b200_plan_t p, const int32_t* node_ids, int 
 /* flags */
 #define DOPT_B200_PLAN_FUSE        1   /* graph-level lowering and fusion (off = node-by-node like the reference)   */
 #define DOPT_B200_PLAN_CUDA_GRAPH  2   /* capture the step in a CUDA graph                                          */
+/* bf16 interior (needs PLAN_FUSE; only has an effect where tensor-core convolutions, i.e. MATH_BF16, are in use):
+ * activations that only tensor-core convolutions, batch norms and residual adds read are kept as NHWC bf16 and never
+ * materialised as NCHW fp32 -- the convolution epilogue writes bf16, batchNormTrain / batchNormGrad / add work on that
+ * layout.  Plan inputs, outputs and everything any other op reads stay fp32.  NUMERICS: the stored activations are rounded
+ * to bf16 (8 mantissa bits) where the reference stores fp32; arithmetic stays fp32.  Stated tolerance: DESIGN.md section 5. */
+#define DOPT_B200_PLAN_BF16_INTERIOR 4
 int dopt_b200_plan_finalize(dopt_b200_plan_t p, int flags);
 /* var_ids[i] is a "variable" node id, var_ptrs[i] its buffer; var_on_host[i] != 0 means a host pointer that is
  * uploaded first (CUDAPlan does the same for CPUBuffer args, package.d:373-381).  rets[i] is a DEVICE pointer that

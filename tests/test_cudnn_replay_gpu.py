@@ -110,6 +110,10 @@ CONV = [
     (128, 640, 8, 8, 640, 3, 3, 1, 1),
     (128, 160, 32, 32, 320, 3, 3, 1, 2),
     (128, 160, 32, 32, 320, 1, 1, 0, 2),
+    (128, 16, 32, 32, 160, 3, 3, 1, 1),    # the remaining WRN-28-10 shapes of SURVEY section 8(d) at BASELINE size
+    (128, 16, 32, 32, 160, 1, 1, 0, 1),
+    (128, 320, 16, 16, 640, 3, 3, 1, 2),
+    (128, 320, 16, 16, 640, 1, 1, 0, 2),
 ]
 
 

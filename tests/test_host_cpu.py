@@ -238,6 +238,64 @@ def test_wrn_graph_inventory():
     assert ts.count("sum") == len(convs) + 1                          # weight decay per conv + the cross-entropy sum
 
 
+def test_wrn_28_10_headline_graph_inventory():
+    """The benchmarked graph (BASELINE configs[3]: wideResNet(features, 28, 10).dense(100).softmax(), SGD) pinned against
+    nnet/source/dopt/nnet/models/wrn.d:56-199 independently of the mirror: the expected counts and sizes below are derived
+    from the D source's loops (n = (depth - 4) / 6 blocks per group, a 1x1 shortcut only where the channel count changes,
+    batchNorm before both 3x3 convolutions of a block and once after the last group, every batchNorm holding scale, bias,
+    mean, var)."""
+    depth, width, classes = 28, 10, 100
+    n = (depth - 4) // 6
+    groups = [(16, 16 * width), (16 * width, 32 * width), (32 * width, 64 * width)]
+    want_convs = [(16, 3, 3, 3)]
+    bn_channels = []
+    for cin, u in groups:
+        c = cin
+        for _ in range(n):
+            bn_channels += [c, u]
+            want_convs += [(u, c, 3, 3), (u, u, 3, 3)]
+            if c != u:
+                want_convs.append((u, c, 1, 1))
+            c = u
+    bn_channels.append(64 * width)
+    assert len(want_convs) == 28 and len(bn_channels) == 25
+    want_elems = sum(int(np.prod(s)) for s in want_convs) + 4 * sum(bn_channels) + 64 * width * classes + classes
+    assert want_elems == 36554836
+
+    H.seed(1)
+    x = H.float32((2, 3, 32, 32))
+    labels = H.float32((2, classes))
+    preds = H.wide_resnet(x, depth, width, weight_decay=1e-4).dense(classes).softmax()
+    net = H.Network([x], [preds])
+    assert len(net.params) == 130
+    assert sum(p.volume for p in net.params) == want_elems
+    got_convs = sorted(tuple(p.shape) for p in net.params if len(p.shape) == 4 and p.shape[0] != 1)
+    assert got_convs == sorted(want_convs)
+    assert sorted(p.shape[1] for p in net.params if len(p.shape) == 4 and p.shape[0] == 1) == sorted(bn_channels)   # scale [1,C,1,1]
+    loss = H.cross_entropy(preds.train_output, labels) + net.param_loss
+    upd = H.Updater(H.SGD, [loss, preds.train_output], network=net, hyper=[H.float32((), [0.1]), H.float32((), [0.9])])
+    plan_ops, _ = upd.plan_outputs()
+    nodes = H.export(plan_ops)
+    ts = [nd["type"] for nd in nodes]
+    assert ts.count("convolution") == 28 and ts.count("convolutionFiltersGrad") == 28
+    assert ts.count("convolutionFeaturesGrad") == 27          # the stem's features are the network input
+    assert ts.count("batchNormTrain") == 25 and ts.count("batchNormGrad") == 25
+    assert ts.count("relu") == 25 and ts.count("reluGrad") == 25
+    # forward residual sums: rank-4 adds that the loss depends on
+    by_id = dict((nd["id"], nd) for nd in nodes)
+    loss_id = [nd["id"] for nd in nodes if nd["op"].h == plan_ops[0].h][0]
+    fwd, stack = set(), [loss_id]
+    while stack:
+        i = stack.pop()
+        if i not in fwd:
+            fwd.add(i)
+            stack.extend(by_id[i]["deps"])
+    assert sum(1 for nd in nodes if nd["type"] == "add" and len(nd["shape"]) == 4 and nd["id"] in fwd) == 12
+    # convolution attributes of the three strided 3x3 / 1x1 pairs (wrn.d:143-151,166-178 with stride [1,2,2])
+    strides = sorted(tuple(nd["attrs"]["stride"]) for nd in nodes if nd["type"] == "convolution")
+    assert strides.count((2, 2)) == 4 and strides.count((1, 1)) == 24
+
+
 def test_dropout_layer_graph():
     """nnet/layers/dropout.d:14-29: train output = (uniform > p) * x, test output = x * (1 - p); the mask is not
     differentiable, so the gradient wrt x is parentGrad * mask."""

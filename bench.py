@@ -95,11 +95,13 @@ def synthetic_batch(batch, seed):
 # ---------------------------------------------------------------------------------------------------------------------
 # per-kernel-class rooflines (the north star asks for the memory-bound classes as a fraction of HBM bandwidth)
 # ---------------------------------------------------------------------------------------------------------------------
-def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs):
+def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs, elem=4):
     """ALGORITHMIC bytes per step of the memory-bound op classes, from the exported dopt graph and SURVEY.md section 8(d)'s
-    per-element figures at the fp32 boundary (batchNormTrain 2V*4, batchNormGrad 3V*4 -- the relu / reluGrad / NHWC staging
-    the plan folds into those passes add no algorithmic bytes --, residual add 3V*4, SGD+momentum 5P*4), divided by the
-    device time the plan's profiler attributes to that op type inside the training step.
+    per-element figures (batchNormTrain 2V*s, batchNormGrad 3V*s -- the relu / reluGrad / NHWC staging the plan folds into
+    those passes add no algorithmic bytes --, residual add 3V*s, SGD+momentum 5P*4), divided by the device time the plan's
+    profiler attributes to that op type inside the training step.  s = `elem`: 4 with fp32 activations, 2 with the bf16
+    interior ("element size s = 4 (fp32 drop-in path) or 2 (bf16 interior)") -- the smaller figure is used
+    whenever the plan runs with bf16 interior activations, so the fraction is never flattered by bytes that are not moved.
 
     nodes: H.export(plan outputs); prof_us / prof_n: per-op-type microseconds and launches PER STEP."""
     by_id = dict((n["id"], n) for n in nodes)
@@ -132,12 +134,12 @@ def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs):
                      "alg_bytes_per_step": int(alg_bytes), "us_per_step": us,
                      "launches_per_step": int(sum(prof_n.get(o, 0) for o in ops)), "what": note}
 
-    put("batchNormTrain", ["batchNormTrain"], 2 * v_bn * 4,
-        "2V*4 B; the pass also applies relu and writes the NHWC bf16 operand copy of the next convolution")
-    put("batchNormGrad", ["batchNormGrad"], 3 * v_bng * 4,
-        "3V*4 B; the pass also applies the relu gate, the residual-gradient add and the NHWC bf16 staging of dx")
+    put("batchNormTrain", ["batchNormTrain"], 2 * v_bn * elem,
+        "2V*%d B; the pass also applies relu and writes the NHWC bf16 operand of the next convolution" % elem)
+    put("batchNormGrad", ["batchNormGrad"], 3 * v_bng * elem,
+        "3V*%d B; the pass also applies the relu gate and the residual-gradient add" % elem)
     if res_adds and prof_n.get("add", 0) == len(res_adds):
-        put("residual_add", ["add"], 3 * sum(vol(n) for n in res_adds) * 4, "3V*4 B, forward residual sums (+ staging)")
+        put("residual_add", ["add"], 3 * sum(vol(n) for n in res_adds) * elem, "3V*%d B, forward residual sums" % elem)
     put("optimiser", ["fusedRegion"], 5 * n_params * 4,
         "5P*4 B (SGD+momentum); the fused regions also carry the weight-decay gradient and the loss chain")
     return out
@@ -322,7 +324,7 @@ def main():
         by, busy, gaps, last_end = {}, 0.0, 0.0, None
         for e in evs:
             dur = e.time_range.end - e.time_range.start
-            name = e.name.split("(")[0].replace("void ", "")
+            name = e.name.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "")
             a = by.setdefault(name, [0, 0.0])
             a[0] += 1
             a[1] += dur
@@ -387,12 +389,20 @@ def main():
         conv_flops = TRAIN_GFLOP_PER_IMAGE * 1e9 * B if (args.depth, args.width) == (28, 10) else None
         if tc_us > 0 and conv_flops:
             achieved = conv_flops / (tc_us * 1e-6) / 1e12
+            # which measured peak applies is decided by this run's own clock record: the burst figure when the SM clock
+            # stayed at its maximum without a power cap (a 0.2 s timed region does), the sustained one otherwise
+            burst = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and
+                         clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] and "sw_power_cap" not in clocks.get("reasons", []))
+            peak = pk["bf16_tflops"] if burst else pk["bf16_tflops_sustained"]
             roof = {"bound": "tensor", "kernel": "tc_kernel<CONV|WGRAD> (tcgen05 implicit GEMM)", "achieved": achieved,
-                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "frac_of_burst_peak": achieved / pk["bf16_tflops"],
+                    "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                     "traffic": TC_DRAM_BYTES_PER_STEP if (args.depth, args.width) == (28, 10) else None,
                     "traffic_source": "ncu dram__bytes_read+write summed over the step's tc_kernel launches "
                                       "(profiles/r01_final_tc_dram.csv), per step like `achieved`",
-                    "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                    "peak_source": pk["source"] + (" (burst: SM clock at max, no power cap during the timed region)" if burst
+                                                   else " (sustained: SM clock below max or power-capped during the timed region)"),
                     "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3}
     classes = None
     if RANK == 0:
@@ -402,7 +412,8 @@ def main():
             loss_id = [n["id"] for n in nodes if n["op"].h == plan_outs[0].h][0]
             per_us = dict((k, v / 2.0) for k, v in prof.items() if "#" not in k)
             per_n = dict((k[:-2], v / 2.0) for k, v in prof.items() if k.endswith("#n"))
-            classes = class_rooflines(nodes, loss_id, per_us, per_n, n_params, peaks()["hbm_gbs"])
+            interior = bool(H.plan_flags() & db._lib.PLAN_BF16_INTERIOR)
+            classes = class_rooflines(nodes, loss_id, per_us, per_n, n_params, peaks()["hbm_gbs"], elem=2 if interior else 4)
         except Exception as e:  # diagnostics only: never lose the bench line over it
             classes = {"error": repr(e)}
     barrier()
@@ -423,7 +434,10 @@ def main():
             "config": {"workload": workload_name(args.depth, args.width, B),
                        "parallelism": "dp%d" % world, "params": n_params,
                        "cache": "inputs larger than L2: one step streams several GB of activations through the 126 MB L2",
-                       "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; everything else fp32"},
+                       "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; activations between tensor-core "
+                                    "convolutions stored NHWC bf16 (plan flag BF16_INTERIOR), arithmetic and everything "
+                                    "else fp32" if (H.plan_flags() & db._lib.PLAN_BF16_INTERIOR) else
+                                    "convolutions bf16 operands / fp32 accumulate on tcgen05; everything else fp32"},
             "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": int(nbytes[0] + nbytes[1]), "d2h_bytes_per_step": int(4 + pred_out.nbytes),
                     "ms_per_step": e2e_ms / args.steps},

@@ -453,10 +453,26 @@ struct BnTrainKernel : Kernel {
     const void* staged_x = nullptr;
     Scratch fws;
     const void* fws_for = nullptr;
+    int stats_source = 0;   // 1 / 2: the producer of x accumulates the statistics (flat.cuh)
     bool can_flat() const override { return flat_supported(g.N, g.C, g.HW); }
     void set_flat(bool on) override { flat = on; }
     void set_staged_input(int input, const void* p) override {
         if (input == 0) staged_x = p;
+    }
+    void* flat_workspace(cudaStream_t s, bool sync) {
+        const size_t wb = flat_bn_workspace_bytes((int)g.C);
+        void* w = fws.get(wb);
+        if (w != fws_for) {
+            if (sync) DB_CUDA(cudaMemset(w, 0, wb));
+            else DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
+            fws_for = w;
+        }
+        return w;
+    }
+    void* stats_workspace(int mode) override {
+        if (!flat || (mode != 1 && mode != 2)) return nullptr;
+        stats_source = mode;
+        return flat_workspace(nullptr, true);
     }
     bool set_stat_outputs(float* m, float* v) override {
         mean_out2 = m;
@@ -478,13 +494,9 @@ struct BnTrainKernel : Kernel {
         float* y = (float*)out;
         if (flat) {
             DB_REQUIRE(staged_x && ab.staged && ab.skip_fp32, "batchNormTrain: flat mode needs staged input and output");
-            const size_t wb = flat_bn_workspace_bytes((int)g.C);
-            void* w = fws.get(wb);
-            if (w != fws_for) {
-                DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
-                fws_for = w;
-            }
+            void* w = flat_workspace(s, false);
             FlatBnTrain a{};
+            a.stats_source = stats_source;
             a.x = staged_x; a.y = ab.staged;
             a.scale = (const float*)in[1]; a.bias = (const float*)in[2];
             a.rmean = (const float*)in[3]; a.rvar = (const float*)in[4];

@@ -130,6 +130,12 @@ struct Kernel {
     virtual void set_staged_output(void* /*nhwc_bf16*/) {}
     virtual bool can_flat() const { return false; }
     virtual void set_flat(bool /*on*/) {}
+    // batch-norm statistics accumulated by the producer of x: a flat batchNormTrain hands out its statistics workspace
+    // (stats_workspace; mode 1 = sums pivoted by pixel 0, the residual add; mode 2 = plain sums, the convolution epilogue) and
+    // skips its own statistics kernel; the producer (can_produce_stats) accumulates into it while it writes x
+    virtual void* stats_workspace(int /*mode*/) { return nullptr; }
+    virtual int can_produce_stats() const { return 0; }   // 0 = no, else the mode it produces
+    virtual void set_stats_workspace(void* /*bn_workspace*/, int /*channels*/) {}
     virtual const void* aux_ptr() const { return nullptr; }
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use

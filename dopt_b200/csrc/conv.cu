@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "tc.cuh"
+#include "flat.cuh"
 
 namespace db {
 namespace {
@@ -47,6 +48,10 @@ struct ConvKernel : Kernel {
     void set_packed_filter(const void* p) override { conv_tc_set_packed_filter(tc, p); }
     bool can_stage_output() const override { return conv_tc_can_stage_output(tc); }
     void set_staged_output(void* p) override { conv_tc_set_staged_output(tc, p); }
+    int can_produce_stats() const override { return (tc && kind == CONV_FWD) ? 2 : 0; }
+    void set_stats_workspace(void* w, int channels) override {
+        if (tc && kind == CONV_FWD && channels == g.K) conv_tc_set_stats_workspace(tc, w);
+    }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == 2, "convolution ops take two inputs");
         const float* a = (const float*)in[0];

@@ -16,19 +16,33 @@
 namespace db {
 
 static constexpr double kFlatEps = 1e-5;   // cudnn7.d:587-636 pass CUDNN_BN_MIN_EPSILON
-static constexpr int kFlatU = 4;           // 16-byte loads in flight per operand per thread
+static constexpr int kFlatU = 4;           // 16-byte loads in flight per operand per thread (apply / add kernels)
 
 namespace {
 
-struct FlatFin {
-    double* acc;          // [C][2], zero between launches
-    unsigned* counter;    // zero between launches
-    float* coef;          // train: [mean | a | b | istd]; grad: [A | B | Cc]
+// per batch-norm kernel object: [epochs (16 B) | sums: 2 buffers x kFlatCopies x 2 * Cp floats | coef: 4 * C floats]
+//   sums   train: sum(x - K), sum((x - K)^2) per channel; grad: sum(g), sum(g * (x - mean)).  Accumulated with fire-and-forget
+//          fp32 atomics by the statistics kernel -- CTA b adds into copy b % kFlatCopies, because atomics on ONE address
+//          serialise at ~25 ns each (profiles/r02_flat_bn.md) -- and summed by the apply kernel's prologue.
+//          Two buffers alternate between launches: the statistics kernel of launch e accumulates into buffer e & 1 and its
+//          first CTA clears the other one (last read by the apply kernel of launch e - 1, long finished).  The launch number
+//          lives in device memory (a CUDA graph replays the same arguments every step): epoch[0] is read by the statistics
+//          kernel and written by the apply kernel, epoch[1] the other way round, so no kernel reads a word it writes.
+//   coef   forward [mean | a | b | istd], written by the first CTA of the forward apply kernel, read by the backward kernels
+static constexpr int kFlatCopies = 8;
+struct FlatWs {
+    unsigned* epoch;
+    float* sums;
+    float* coef;
+};
+struct FlatApplyArgs {
+    FlatWs ws;
     const float* scale; const float* bias; const float* rmean; const float* rvar;
     float* out0; float* out1;       // train: new mean / new var; grad: dscale / dbias
     float* mean2; float* var2;
-    const float* fcoef;             // grad: forward coefficients
+    const float* fcoef;             // grad: forward coefficients [mean | a | b | istd]
     double factor;
+    int pivot_zero;                 // train: the sums are plain sum(x), sum(x^2) (convolution epilogue) instead of pivoted by pixel 0
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
@@ -58,29 +72,59 @@ __device__ __forceinline__ void st16(uint4* p, const uint4& v) {
 // ---- statistics ------------------------------------------------------------------------------------------------------
 // train: per channel sum(x - K), sum((x - K)^2) around the pivot K = x[pixel 0] (keeps E[x^2] - E[x]^2 harmless in fp32)
 // grad:  per channel sum(g), sum(g * (x - mean)) with g = dy gated by the forward relu, mean from the forward pass
-// Per-thread fp32 partials -> shared-memory reduction over the CTA's pixel rows -> one double atomic per (channel, sum) per CTA;
-// the CTA that arrives last turns the sums into the per-channel coefficients and clears the accumulators for the next launch.
-template <bool GRAD, bool GATE>
-__global__ void __launch_bounds__(256) flat_bn_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
-                                                            int64_t P, int G, int C, int R,
-                                                            const __grid_constant__ FlatFin fin) {
-    __shared__ float red[16][256];
-    __shared__ int s_last;
+// Per-thread fp32 partials -> shared-memory reduction over the CTA's pixel rows -> one fire-and-forget fp32 atomic per CTA,
+// channel and sum.  Nothing waits for the result inside this kernel: the apply kernel turns the sums into coefficients in
+// its prologue (profiles/r02_flat_bn.md: a "last CTA finalizes" tail cost more than the streaming of these 10-40 MB tensors).
+// U = independent 16-byte loads in flight per operand per thread.
+// epoch protocol of a statistics producer (see FlatWs): returns this CTA's accumulator copy
+__device__ __forceinline__ float* flat_stats_begin(const FlatWs& ws, int Cp) {
+    const unsigned e = ws.epoch[0];
+    if (blockIdx.x == 0) {
+        float* other = ws.sums + (size_t)((e + 1u) & 1u) * kFlatCopies * 2 * Cp;
+        for (int i = threadIdx.x; i < kFlatCopies * 2 * Cp; i += blockDim.x) other[i] = 0.f;
+        if (threadIdx.x == 0) ws.epoch[1] = e;
+    }
+    return ws.sums + ((size_t)(e & 1u) * kFlatCopies + blockIdx.x % kFlatCopies) * 2 * Cp;
+}
+// per-thread partials (8 channels x 2 sums) -> CTA sums -> one atomic per channel and sum
+__device__ __forceinline__ void flat_stats_end(const float (&s1)[8], const float (&s2)[8], float (&red)[16][256], float* sums, int G,
+                                               int R) {
     const int t = threadIdx.x;
-    const int cg = t % G;
-    const bool active = t < R * G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[j][t] = s1[j];
+        red[8 + j][t] = s2[j];
+    }
+    __syncthreads();
+    const int Cp = G * 8;
+    for (int idx = t; idx < G * 16; idx += blockDim.x) {
+        const int g2 = idx % G, k = idx / G;
+        float v = 0.f;
+        for (int r = 0; r < R; ++r) v += red[k][r * G + g2];
+        atomicAdd(sums + (k >> 3) * Cp + g2 * 8 + (k & 7), v);
+    }
+}
+
+template <bool GRAD, bool GATE, int U>
+__global__ void __launch_bounds__(256) flat_bn_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                                                            int64_t P, int G, int C, int R, const __grid_constant__ FlatWs ws,
+                                                            const float* __restrict__ fcoef) {
+    __shared__ float red[16][256];
+    const int t = threadIdx.x;
+    float* sums = flat_stats_begin(ws, G * 8);
+    const int cg_ = t % G;
     float piv[8], fa[8], fb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) piv[j] = fa[j] = fb[j] = 0.f;
     if (!GRAD) {
-        unpack8(x[cg], piv);   // pixel 0
+        unpack8(x[cg_], piv);   // pixel 0
     } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = cg * 8 + j;
+            const int c = cg_ * 8 + j;
             if (c < C) {
-                piv[j] = fin.fcoef[c];   // the batch mean
-                if (GATE) { fa[j] = fin.fcoef[C + c]; fb[j] = fin.fcoef[2 * C + c]; }
+                piv[j] = fcoef[c];   // the batch mean
+                if (GATE) { fa[j] = fcoef[C + c]; fb[j] = fcoef[2 * C + c]; }
             }
         }
     }
@@ -88,19 +132,19 @@ __global__ void __launch_bounds__(256) flat_bn_stats_kernel(const uint4* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const int64_t trip = (int64_t)R * G, total = P * G;
-    for (int64_t v0 = (int64_t)blockIdx.x * kFlatU * trip; v0 < total; v0 += (int64_t)gridDim.x * kFlatU * trip) {
-        uint4 xv[kFlatU], qv[kFlatU];
-        bool ok[kFlatU];
+    for (int64_t v0 = (int64_t)blockIdx.x * U * trip; v0 < total; v0 += (int64_t)gridDim.x * U * trip) {
+        uint4 xv[U], qv[U];
 #pragma unroll
-        for (int u = 0; u < kFlatU; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t i = v0 + u * trip + t;
-            ok[u] = active && i < total;
-            xv[u] = ok[u] ? ld16(x + i) : make_uint4(0, 0, 0, 0);
-            if (GRAD) qv[u] = ok[u] ? ld16(dy + i) : make_uint4(0, 0, 0, 0);
+            if (i < total) {
+                xv[u] = ld16(x + i);
+                if (GRAD) qv[u] = ld16(dy + i);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < kFlatU; ++u) {
-            if (!ok[u]) continue;
+        for (int u = 0; u < U; ++u) {
+            if (v0 + u * trip + t >= total) continue;
             float xf[8], qf[8];
             unpack8(xv[u], xf);
             if (GRAD) unpack8(qv[u], qf);
@@ -119,89 +163,91 @@ __global__ void __launch_bounds__(256) flat_bn_stats_kernel(const uint4* __restr
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        red[j][t] = active ? s1[j] : 0.f;
-        red[8 + j][t] = active ? s2[j] : 0.f;
-    }
-    __syncthreads();
-    for (int idx = t; idx < G * 16; idx += blockDim.x) {
-        const int g2 = idx % G, k = idx / G;
-        float v = 0.f;
-        for (int r = 0; r < R; ++r) v += red[k][r * G + g2];
-        const int c = g2 * 8 + (k & 7);
-        if (c < C) atomicAdd(&fin.acc[2 * c + (k >> 3)], (double)v);
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1 ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const double M = (double)P;
-    for (int c = t; c < C; c += blockDim.x) {
-        const double a0 = __ldcg(&fin.acc[2 * c]), a1 = __ldcg(&fin.acc[2 * c + 1]);
-        fin.acc[2 * c] = 0.0;
-        fin.acc[2 * c + 1] = 0.0;
-        if (!GRAD) {
-            // same combine as bn_train_finalize_channel (batchnorm.cu)
-            const uint4* x0 = x + c / 8;
-            const uint32_t w = ((const uint32_t*)x0)[(c & 7) >> 1];
-            const double K = (double)__uint_as_float((c & 1) ? (w & 0xffff0000u) : (w << 16));
-            const double d = a0 / M;
-            const double mean = K + d;
-            double var = a1 / M - d * d;
-            if (var < 0) var = 0;
-            const double istd = 1.0 / sqrt(var + kFlatEps);
-            fin.coef[c] = (float)mean;
-            fin.coef[C + c] = (float)((double)fin.scale[c] * istd);
-            fin.coef[2 * C + c] = fin.bias[c];
-            fin.coef[3 * C + c] = (float)istd;
-            const double unbiased = M > 1 ? var * M / (M - 1) : var;
-            const float nm = (float)((double)fin.rmean[c] * (1.0 - fin.factor) + mean * fin.factor);
-            const float nv = (float)((double)fin.rvar[c] * (1.0 - fin.factor) + unbiased * fin.factor);
-            fin.out0[c] = nm;
-            fin.out1[c] = nv;
-            if (fin.mean2) fin.mean2[c] = nm;
-            if (fin.var2) fin.var2[c] = nv;
-        } else {
-            // same algebra as bn_grad_finalize_channel: dx = dy*A + (x - mean)*B + Cc
-            const double istd = (double)fin.fcoef[3 * C + c];
-            const double dbeta = a0, dgamma = a1 * istd;
-            fin.out0[c] = (float)dgamma;
-            fin.out1[c] = (float)dbeta;
-            const double A = (double)fin.scale[c] * istd;
-            fin.coef[c] = (float)A;
-            fin.coef[C + c] = (float)(-A * istd * dgamma / M);
-            fin.coef[2 * C + c] = (float)(-A * dbeta / M);
-        }
-    }
-    if (t == 0) *fin.counter = 0u;
+    flat_stats_end(s1, s2, red, sums, G, R);
 }
 
 // ---- apply -------------------------------------------------------------------------------------------------------------
-// MODE 0: y = relu?((x - mean) * a + b)                                  coef = [mean | a | b | istd]
-// MODE 1: dx = g * A + (x - mean) * B + Cc (+ addend), g = gated dy      coef = [A | B | Cc], fcoef = forward [mean | a | b | istd]
+// Prologue (every CTA, for the 8 channels of each thread): sums -> per-channel coefficients, same algebra as
+// bn_train_finalize_channel / bn_grad_finalize_channel (batchnorm.cu) in fp32.  The first CTA also writes the forward
+// coefficient block, the running statistics (train) or dscale / dbias (grad); the CTA that finishes its prologue last clears
+// the sums for the next launch.
+// MODE 0: y = relu?((x - mean) * a + b)
+// MODE 1: dx = g * A + (x - mean) * B + Cc (+ addend), g = dy gated by the forward relu
 template <int MODE, bool RELU, bool ADDEND>
 __global__ void __launch_bounds__(256) flat_bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                                                             const uint4* __restrict__ addend, uint4* __restrict__ out,
-                                                            int64_t P, int G, int C, int R, const float* __restrict__ coef,
-                                                            const float* __restrict__ fcoef) {
+                                                            int64_t P, int G, int C, int R,
+                                                            const __grid_constant__ FlatApplyArgs a) {
+    __shared__ float ssum[2 * 2048];   // [2][Cp]: the launch's sums, copies added in a fixed order
     const int t = threadIdx.x;
-    const int cg = t % G;
-    if (t >= R * G) return;
+    const int cg_ = t % G;
+    const int Cp = G * 8;
+    const float invM = 1.0f / (float)P;
+    const unsigned e = a.ws.epoch[1];
+    if (t < G) {
+        const float4* src = (const float4*)(a.ws.sums + (size_t)(e & 1u) * kFlatCopies * 2 * Cp);
+        const int q4 = Cp / 4;   // float4 per sum row
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 v[kFlatCopies];
+#pragma unroll
+                for (int k = 0; k < kFlatCopies; ++k) v[k] = __ldcg(src + (size_t)(k * 2 + q) * q4 + cg_ * 2 + h);
+                float4 r = v[0];
+#pragma unroll
+                for (int k = 1; k < kFlatCopies; ++k) { r.x += v[k].x; r.y += v[k].y; r.z += v[k].z; r.w += v[k].w; }
+                *(float4*)&ssum[q * Cp + cg_ * 8 + h * 4] = r;
+            }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && t == 0) a.ws.epoch[0] = e + 1u;   // read by the NEXT statistics kernel only
     float mu[8], ca[8], cb[8], gA[8], gB[8], gC[8];
+    float piv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) piv[j] = 0.f;
+    if (MODE == 0 && !a.pivot_zero) unpack8(x[cg_], piv);   // the statistics producer's pivot: pixel 0
+    const bool writer = blockIdx.x == 0 && t < G;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
+        const int c = cg_ * 8 + j;
         mu[j] = ca[j] = cb[j] = gA[j] = gB[j] = gC[j] = 0.f;
-        if (c < C) {
-            if (MODE == 0) {
-                mu[j] = coef[c]; ca[j] = coef[C + c]; cb[j] = coef[2 * C + c];
-            } else {
-                mu[j] = fcoef[c];
-                if (RELU) { ca[j] = fcoef[C + c]; cb[j] = fcoef[2 * C + c]; }
-                gA[j] = coef[c]; gB[j] = coef[C + c]; gC[j] = coef[2 * C + c];
+        if (c >= C) continue;
+        const float q0 = ssum[c], q1 = ssum[Cp + c];
+        if (MODE == 0) {
+            const float d = q0 * invM;
+            const float mean = piv[j] + d;
+            const float var = fmaxf(fmaf(-d, d, q1 * invM), 0.f);
+            const float istd = 1.0f / sqrtf(var + (float)kFlatEps);
+            mu[j] = mean;
+            ca[j] = a.scale[c] * istd;
+            cb[j] = a.bias[c];
+            if (writer) {
+                a.ws.coef[c] = mean;
+                a.ws.coef[C + c] = ca[j];
+                a.ws.coef[2 * C + c] = cb[j];
+                a.ws.coef[3 * C + c] = istd;
+                const double M = (double)P;
+                const double unbiased = M > 1 ? (double)var * M / (M - 1) : (double)var;
+                const float nm = (float)((double)a.rmean[c] * (1.0 - a.factor) + (double)mean * a.factor);
+                const float nv = (float)((double)a.rvar[c] * (1.0 - a.factor) + unbiased * a.factor);
+                a.out0[c] = nm;
+                a.out1[c] = nv;
+                if (a.mean2) a.mean2[c] = nm;
+                if (a.var2) a.var2[c] = nv;
+            }
+        } else {
+            mu[j] = a.fcoef[c];
+            if (RELU) { ca[j] = a.fcoef[C + c]; cb[j] = a.fcoef[2 * C + c]; }
+            const float istd = a.fcoef[3 * C + c];
+            const float dbeta = q0, dgamma = q1 * istd;
+            const float A = a.scale[c] * istd;
+            gA[j] = A;
+            gB[j] = -A * istd * dgamma * invM;
+            gC[j] = -A * dbeta * invM;
+            if (writer) {
+                a.out0[c] = dgamma;
+                a.out1[c] = dbeta;
             }
         }
     }
@@ -276,6 +322,61 @@ __global__ void __launch_bounds__(256) flat_add_kernel(const uint4* __restrict__
     }
 }
 
+// out = a + b with the batch-norm statistics of `out` (the residual sum feeding the next block's first batch norm) accumulated
+// on the way: same thread <-> channel-group mapping and the same tail as flat_bn_stats_kernel, pivot = out[pixel 0].
+__global__ void __launch_bounds__(256) flat_add_stats_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                             uint4* __restrict__ out, int64_t P, int G, int R,
+                                                             const __grid_constant__ FlatWs ws) {
+    __shared__ float red[16][256];
+    const int t = threadIdx.x;
+    float* sums = flat_stats_begin(ws, G * 8);
+    const int cg_ = t % G;
+    float piv[8];
+    {
+        float af[8], bf[8], r[8];
+        unpack8(a[cg_], af);
+        unpack8(b[cg_], bf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(af[j], bf[j]);
+        unpack8(pack8(r), piv);   // the stored (bf16-rounded) value of pixel 0
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const int64_t trip = (int64_t)R * G, total = P * G;
+    for (int64_t v0 = (int64_t)blockIdx.x * kFlatU * trip; v0 < total; v0 += (int64_t)gridDim.x * kFlatU * trip) {
+        uint4 av[kFlatU], bv[kFlatU];
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) {
+            const int64_t i = v0 + u * trip + t;
+            if (i < total) {
+                av[u] = ld16(a + i);
+                bv[u] = ld16(b + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) {
+            const int64_t i = v0 + u * trip + t;
+            if (i >= total) continue;
+            float af[8], bf[8], r[8];
+            unpack8(av[u], af);
+            unpack8(bv[u], bf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(af[j], bf[j]);
+            const uint4 o = pack8(r);
+            st16(out + i, o);
+            unpack8(o, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = r[j] - piv[j];
+                s1[j] += d;
+                s2[j] = fmaf(d, d, s2[j]);
+            }
+        }
+    }
+    flat_stats_end(s1, s2, red, sums, G, R);
+}
+
 // [N][HW][Cp] bf16 -> [N][C][HW] fp32 through a 16-channel x PX-pixel shared-memory tile: reads are one 32-byte sector per
 // pixel (neighbouring channel groups complete the line in L2), writes PX*4-byte contiguous runs per channel.
 template <int PX>
@@ -313,12 +414,12 @@ __global__ void __launch_bounds__(256) unstage_kernel(const __nv_bfloat16* __res
 struct FlatLaunch {
     int G, R, threads, blocks;
 };
-static FlatLaunch flat_launch(const FlatGeom& g, int ctas_per_sm) {
+static FlatLaunch flat_launch(const FlatGeom& g, int ctas_per_sm, int unroll = kFlatU) {
     FlatLaunch L;
     L.G = g.Cp / 8;
     L.R = std::max(1, 256 / L.G);
     L.threads = L.R * L.G;
-    const int64_t per_block = (int64_t)kFlatU * L.R;   // pixels per CTA trip
+    const int64_t per_block = (int64_t)unroll * L.R;   // pixels per CTA trip
     static int env_ctas = -1;
     if (env_ctas < 0) {
         const char* e = getenv("DOPT_B200_FLAT_CTAS");
@@ -330,58 +431,85 @@ static FlatLaunch flat_launch(const FlatGeom& g, int ctas_per_sm) {
     return L;
 }
 
+static constexpr int kStatsCtasPerSm = 2;
+
 }  // namespace
 
 bool flat_supported(int64_t N, int64_t C, int64_t HW) {
-    return C >= 1 && (C + 7) / 8 <= 256 && N >= 1 && HW >= 1 && N * HW < (1ll << 40);
+    return C >= 1 && (C + 7) / 8 <= 256 && N >= 1 && HW >= 1 && N * HW < (1ll << 31);
 }
-size_t flat_bn_workspace_bytes(int C) { return (size_t)2 * C * sizeof(double) + 16 + (size_t)4 * C * sizeof(float); }
+size_t flat_bn_workspace_bytes(int C) {
+    const int Cp = (C + 7) / 8 * 8;
+    return 16 + (size_t)2 * kFlatCopies * 2 * Cp * sizeof(float) + (size_t)4 * C * sizeof(float);
+}
+static FlatWs flat_ws(void* workspace, int C) {
+    const int Cp = (C + 7) / 8 * 8;
+    FlatWs w;
+    w.epoch = (unsigned*)workspace;
+    w.sums = (float*)((char*)workspace + 16);
+    w.coef = w.sums + (size_t)2 * kFlatCopies * 2 * Cp;
+    return w;
+}
 
 const float* flat_bn_train(const FlatBnTrain& a, const FlatGeom& g, cudaStream_t s) {
-    FlatFin fin{};
-    fin.acc = (double*)a.workspace;
-    fin.counter = (unsigned*)(fin.acc + 2 * g.C);
-    fin.coef = (float*)((char*)fin.counter + 16);
-    fin.scale = a.scale; fin.bias = a.bias; fin.rmean = a.rmean; fin.rvar = a.rvar;
-    fin.out0 = a.new_mean; fin.out1 = a.new_var;
-    fin.mean2 = a.mean2; fin.var2 = a.var2;
-    fin.factor = a.factor;
-    const FlatLaunch Ls = flat_launch(g, 4);
-    flat_bn_stats_kernel<false, false><<<Ls.blocks, Ls.threads, 0, s>>>((const uint4*)a.x, nullptr, g.P, Ls.G, g.C, Ls.R, fin);
-    DB_LAUNCH_CHECK();
+    FlatApplyArgs ap{};
+    ap.ws = flat_ws(a.workspace, g.C);
+    ap.scale = a.scale; ap.bias = a.bias; ap.rmean = a.rmean; ap.rvar = a.rvar;
+    ap.out0 = a.new_mean; ap.out1 = a.new_var;
+    ap.mean2 = a.mean2; ap.var2 = a.var2;
+    ap.factor = a.factor;
+    ap.pivot_zero = a.stats_source == 2 ? 1 : 0;
+    if (a.stats_source == 0) {
+        const FlatLaunch Ls = flat_launch(g, kStatsCtasPerSm, 8);
+        flat_bn_stats_kernel<false, false, 8><<<Ls.blocks, Ls.threads, 0, s>>>((const uint4*)a.x, nullptr, g.P, Ls.G, g.C, Ls.R,
+                                                                             ap.ws, nullptr);
+        DB_LAUNCH_CHECK();
+    }
     const FlatLaunch La = flat_launch(g, 4);
     if (a.relu)
         flat_bn_apply_kernel<0, true, false><<<La.blocks, La.threads, 0, s>>>((const uint4*)a.x, nullptr, nullptr, (uint4*)a.y, g.P,
-                                                                             La.G, g.C, La.R, fin.coef, nullptr);
+                                                                             La.G, g.C, La.R, ap);
     else
         flat_bn_apply_kernel<0, false, false><<<La.blocks, La.threads, 0, s>>>((const uint4*)a.x, nullptr, nullptr, (uint4*)a.y,
-                                                                              g.P, La.G, g.C, La.R, fin.coef, nullptr);
+                                                                              g.P, La.G, g.C, La.R, ap);
     DB_LAUNCH_CHECK();
-    return fin.coef;
+    return ap.ws.coef;
 }
 
 void flat_bn_grad(const FlatBnGrad& a, const FlatGeom& g, cudaStream_t s) {
-    FlatFin fin{};
-    fin.acc = (double*)a.workspace;
-    fin.counter = (unsigned*)(fin.acc + 2 * g.C);
-    fin.coef = (float*)((char*)fin.counter + 16);
-    fin.scale = a.scale;
-    fin.out0 = a.dscale; fin.out1 = a.dbias;
-    fin.fcoef = a.fcoef;
-    const FlatLaunch Ls = flat_launch(g, 3);
-    if (a.gate) flat_bn_stats_kernel<true, true><<<Ls.blocks, Ls.threads, 0, s>>>((const uint4*)a.x, (const uint4*)a.dy, g.P, Ls.G, g.C, Ls.R, fin);
-    else flat_bn_stats_kernel<true, false><<<Ls.blocks, Ls.threads, 0, s>>>((const uint4*)a.x, (const uint4*)a.dy, g.P, Ls.G, g.C, Ls.R, fin);
+    FlatApplyArgs ap{};
+    ap.ws = flat_ws(a.workspace, g.C);
+    ap.scale = a.scale;
+    ap.out0 = a.dscale; ap.out1 = a.dbias;
+    ap.fcoef = a.fcoef;
+    const FlatLaunch Ls = flat_launch(g, kStatsCtasPerSm, 4);
+    const uint4 *x = (const uint4*)a.x, *dy = (const uint4*)a.dy, *ad = (const uint4*)a.addend;
+    if (a.gate) flat_bn_stats_kernel<true, true, 4><<<Ls.blocks, Ls.threads, 0, s>>>(x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef);
+    else flat_bn_stats_kernel<true, false, 4><<<Ls.blocks, Ls.threads, 0, s>>>(x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef);
     DB_LAUNCH_CHECK();
     const FlatLaunch La = flat_launch(g, 2);
-    const uint4 *x = (const uint4*)a.x, *dy = (const uint4*)a.dy, *ad = (const uint4*)a.addend;
     uint4* out = (uint4*)a.dx;
 #define FLAT_GRAD_APPLY(RELU, ADD) \
-    flat_bn_apply_kernel<1, RELU, ADD><<<La.blocks, La.threads, 0, s>>>(x, dy, ad, out, g.P, La.G, g.C, La.R, fin.coef, a.fcoef)
+    flat_bn_apply_kernel<1, RELU, ADD><<<La.blocks, La.threads, 0, s>>>(x, dy, ad, out, g.P, La.G, g.C, La.R, ap)
     if (a.gate && ad) FLAT_GRAD_APPLY(true, true);
     else if (a.gate) FLAT_GRAD_APPLY(true, false);
     else if (ad) FLAT_GRAD_APPLY(false, true);
     else FLAT_GRAD_APPLY(false, false);
 #undef FLAT_GRAD_APPLY
+    DB_LAUNCH_CHECK();
+}
+
+void flat_stats_sink(void* workspace, int C, unsigned** epoch, float** sums, int* copies) {
+    const FlatWs w = flat_ws(workspace, C);
+    *epoch = w.epoch;
+    *sums = w.sums;
+    *copies = kFlatCopies;
+}
+
+void flat_add_stats(const void* a, const void* b, void* out, const FlatGeom& g, void* bn_workspace, cudaStream_t s) {
+    const FlatLaunch L = flat_launch(g, kStatsCtasPerSm);
+    flat_add_stats_kernel<<<L.blocks, L.threads, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, g.P, L.G, L.R,
+                                                       flat_ws(bn_workspace, g.C));
     DB_LAUNCH_CHECK();
 }
 

@@ -28,6 +28,8 @@ struct FlatBnTrain {
     float* mean2; float* var2;               // optional second copy (the caller's return buffers), may alias rmean / rvar
     double factor;                           // 1 - momentum (cudnn7.d:592)
     bool relu;
+    int stats_source;                        // 0: own statistics kernel; the producer of x accumulated them already, pivoted by
+                                             // pixel 0 (1: flat_add_stats) or unpivoted (2: the convolution epilogue)
     void* workspace;                         // flat_bn_workspace_bytes(C), zeroed once by the caller
 };
 // returns the coefficient block [mean | a | b | istd] (4*C floats inside the workspace) the backward pass reads
@@ -45,6 +47,10 @@ struct FlatBnGrad {
 };
 void flat_bn_grad(const FlatBnGrad& a, const FlatGeom& g, cudaStream_t s);
 
+// where a producer of x accumulates the statistics of a flat batchNormTrain (its workspace): see FlatWs in flat.cu
+void flat_stats_sink(void* bn_workspace, int C, unsigned** epoch, float** sums, int* copies);
+// out = a + b plus the batch-norm statistics of out into the workspace of the batchNormTrain that reads it
+void flat_add_stats(const void* a, const void* b, void* out, const FlatGeom& g, void* bn_workspace, cudaStream_t s);
 // out = a + b, all NHWC bf16 of n_elems elements (multiple of 8)
 void flat_add(const void* a, const void* b, void* out, int64_t n_elems, cudaStream_t s);
 // [N][HW][Cp] bf16 -> NCHW fp32 (the inverse of stage_nchw_to_nhwc_bf16), for the few fp32 readers of a bf16-resident value

@@ -1424,7 +1424,32 @@ static void residency(Plan& p) {
         Cn.out_stage = si;
         drop_buffer(Cn);
     }
+    // G: batch-norm statistics accumulated by the producer of x -- the convolution epilogue (x only exists as the staged
+    // result of a tensor-core convolution) or the flat residual add -- instead of a statistics pass of their own
+    int n_stats = 0;
+    if (!getenv("DOPT_B200_NO_PRODUCER_STATS"))
+        for (int i = 0; i < n_nodes; ++i) {
+            Node& B = N[i];
+            if (!B.flat || B.type != "batchNormTrain") continue;
+            int64_t off = 0;
+            const int r = root_of(p, B.deps[0], &off);
+            Node& X = N[r];
+            if (off != 0 || !X.kernel || X.absorbed_by >= 0) continue;
+            const bool conv = X.out_stage >= 0 && X.kernel->can_produce_stats() == 2;
+            const bool add = X.flat && X.type == "add" && X.kernel->can_produce_stats() == 1;
+            if (!conv && !add) continue;
+            // one producer feeds one statistics workspace: the first batch norm reading x gets it (a residual sum has one)
+            bool taken = false;
+            for (int j = 0; j < i; ++j)
+                if (N[j].flat && N[j].type == "batchNormTrain" && root_of(p, N[j].deps[0]) == r) taken = true;
+            if (taken) continue;
+            void* w = B.kernel->stats_workspace(conv ? 2 : 1);
+            if (!w) continue;
+            X.kernel->set_stats_workspace(w, (int)B.op.inputs[0].shape[1]);
+            ++n_stats;
+        }
     if (getenv("DOPT_B200_PLAN_DUMP")) {
+        fprintf(stderr, "PLAN residency: %d batch norms take their statistics from the producer of x\n", n_stats);
         int n_flat = 0, n_conv = 0, n_un = 0;
         for (auto& n : N) {
             n_flat += n.flat ? 1 : 0;

@@ -219,6 +219,9 @@ struct PointwiseKernel : Kernel {
     void set_staged_input(int input, const void* p) override {
         if (input >= 0 && input < 2) staged_in[input] = p;
     }
+    void* bn_ws = nullptr;   // statistics workspace of the batchNormTrain reading the sum (flat mode)
+    int can_produce_stats() const override { return flat ? 1 : 0; }
+    void set_stats_workspace(void* w, int channels) override { bn_ws = channels == (int)aC ? w : nullptr; }
     void set_absorbed(const Absorb& a) override {
         DB_REQUIRE(!a.relu && !a.redirect && (flat || !a.skip_fp32), "pointwise add can only absorb the NHWC staging");
         ab = a;
@@ -244,6 +247,11 @@ struct PointwiseKernel : Kernel {
         DB_REQUIRE(n_in == (unary ? 1 : 2), "pointwise: wrong number of inputs");
         if (flat) {
             DB_REQUIRE(staged_in[0] && staged_in[1] && ab.staged, "add: flat mode needs staged operands and output");
+            if (bn_ws) {
+                FlatGeom fg{aN * aHW, (int)aC, (int)((aC + 7) / 8 * 8)};
+                flat_add_stats(staged_in[0], staged_in[1], ab.staged, fg, bn_ws, s);
+                return;
+            }
             flat_add(staged_in[0], staged_in[1], ab.staged, aN * aHW * ((aC + 7) / 8 * 8), s);
             return;
         }

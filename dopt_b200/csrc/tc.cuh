@@ -27,5 +27,8 @@ void conv_tc_set_packed_filter(ConvTc* c, const void* packed);
 // fwd / dgrad: write the result as [N][H][W][Cp] bf16 into `nhwc_bf16` instead of NCHW fp32 into `out` (nullptr: back to fp32)
 bool conv_tc_can_stage_output(const ConvTc* c);
 void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16);
+// fwd with staged output: also accumulate sum / sum of squares per output channel into the statistics workspace of the flat
+// batchNormTrain that reads the result (flat.cuh: flat_stats_sink)
+void conv_tc_set_stats_workspace(ConvTc* c, void* bn_workspace);
 
 }  // namespace db

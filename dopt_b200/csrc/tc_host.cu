@@ -10,6 +10,7 @@
 //                wgrad      : fp32 atomics into KCRS (split over the pixel dimension)
 #include "common.cuh"
 #include "tc.cuh"
+#include "flat.cuh"
 #include <type_traits>
 #include "tc_kernel.cuh"
 #include <mutex>
@@ -425,6 +426,15 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
                 instr_configured = true;
             }
             DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, true>, tmA, tmB, a));
+        } else if (a.st_cols > 0) {
+            static bool st_configured = false;
+            if (!st_configured) {
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                st_configured = true;
+            }
+            if (a.kbox == 2) DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 2, true>, tmA, tmB, a));
+            else DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, true>, tmA, tmB, a));
         } else if (a.kbox == 2) {
             static bool k2_configured = false;
             if (!k2_configured) {
@@ -442,6 +452,13 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
             instr_configured = true;
         }
         tc_kernel<MODE, false, true><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+    } else if (MODE == TC_MODE_CONV && a.st_cols > 0) {
+        static bool st1_configured = false;
+        if (!st1_configured) {
+            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            st1_configured = true;
+        }
+        tc_kernel<TC_MODE_CONV, false, false, 1, true><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     } else {
         tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
     }
@@ -485,12 +502,13 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
     a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
-    int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - 2048) / L.stage_bytes);
+    const int extra = 2048 + a.st_cols * 32;   // barriers, alignment slack, epilogue statistics
+    int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - extra) / L.stage_bytes);
     if (st > 8) st = 8;
     if (st < 2) {
         // the tile does not fit twice: fall back to one CTA per SM
         a.nacc = 2;
-        st = (int)((225 * 1024 - 2048) / L.stage_bytes);
+        st = (int)((225 * 1024 - extra) / L.stage_bytes);
         if (st > 8) st = 8;
         if (st < 2) st = 2;
     }
@@ -525,8 +543,10 @@ struct TcGemm {
 };
 
 bool tc_gemm_supported(int64_t M, int64_t N, int64_t K) {
-    // worth a 128-row tensor-core tile only when the product is big enough; everything else is latency-bound anyway
-    return M >= 128 && N >= 64 && K >= 64 && M * N * K >= (int64_t)1 << 24 && M < (1 << 30) && N < (1 << 30);
+    // worth a 128-row tensor-core tile only when the product is big enough; everything else is latency-bound anyway.  The
+    // bound admits the dense layer of the WRN configs ([128,640]x[640,100] and its two gradients: 8.2 MFLOP-pairs), which the
+    // fp32 SIMT kernel spent 22 us each on
+    return M >= 128 && N >= 64 && K >= 64 && M * N * K >= (int64_t)1 << 22 && M < (1 << 30) && N < (1 << 30);
 }
 TcGemm* tc_gemm_create(int64_t M, int64_t N, int64_t K) {
     auto* g = new TcGemm;
@@ -612,6 +632,7 @@ struct ConvTc {
     const void* pre[2] = {nullptr, nullptr};   // operands already staged as NHWC bf16 by the plan
     const void* pre_w = nullptr;               // filter already packed by the plan (fwd / dgrad)
     void* out_staged = nullptr;                // fwd / dgrad: write the result as [N][H][W][Cp] bf16 here instead of NCHW fp32
+    void* stats_ws = nullptr;                  // fwd + out_staged: statistics workspace of the batch norm reading the result
 };
 
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
@@ -637,6 +658,9 @@ void conv_tc_set_staged(ConvTc* c, int input, const void* p) {
     if (c && input >= 0 && input < 2) c->pre[input] = p;
 }
 bool conv_tc_can_stage_output(const ConvTc* c) { return c && c->kind != CONV_WGRAD; }
+void conv_tc_set_stats_workspace(ConvTc* c, void* w) {
+    if (c && c->kind == CONV_FWD) c->stats_ws = w;
+}
 void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16) {
     if (c && c->kind != CONV_WGRAD) c->out_staged = nhwc_bf16;
 }
@@ -733,6 +757,11 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
         a.out_kind = TC_OUT_BF16;
         a.o_sn = (long long)g.P * g.Q * c->Kp; a.o_sc = 1; a.o_sh = (long long)g.Q * c->Kp; a.o_sw = c->Kp;
         a.out = c->out_staged;
+        if (c->stats_ws && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) {
+            a.st_cols = a.n_tiles * a.BN;
+            a.st_cp = c->Kp;
+            flat_stats_sink(c->stats_ws, g.K, &a.st_epoch, &a.st_sums, &a.st_copies);
+        }
     }
     a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);

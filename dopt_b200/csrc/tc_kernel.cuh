@@ -75,10 +75,17 @@ struct TcArgs {
     int per_split;      // ceil(iterations / splits), filled by tc_launch
     int kbox;           // CONV pair tiles: (tap, channel block) boxes per pipeline stage (1, or 2 = tc_kernel<.., KBOX = 2>)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
+    // ---- CONV with NHWC bf16 output feeding a flat batchNormTrain (flat.cu): per-channel sum(y), sum(y^2) of the stored
+    // (bf16-rounded) result, reduced in the epilogue -> shared memory -> one fp32 atomic per CTA, channel and sum into the
+    // batch norm's statistics workspace (st_epoch / st_sums = FlatWs::epoch / sums, st_copies = kFlatCopies)
+    int st_cols;              // 0 = off; else n_tiles * BN: columns of the shared-memory accumulator
+    int st_cp, st_copies;     // channels rounded up to 8; accumulator copies per buffer
+    unsigned* st_epoch;
+    float* st_sums;
 };
 
 struct TcSmemLayout {
-    uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total;
+    uint32_t a_bytes, b_bytes, stage_bytes, bar_off, st_off, total;
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     TcSmemLayout L;
@@ -96,7 +103,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     L.b_bytes = (L.b_bytes + 1023u) & ~1023u;
     L.stage_bytes = L.a_bytes + L.b_bytes;
     L.bar_off = L.stage_bytes * (uint32_t)a.stages;
-    L.total = L.bar_off + 1024u /* barriers + tmem slot */ + 1024u /* alignment slack */;
+    L.st_off = L.bar_off + 1024u /* barriers + tmem slot */;
+    L.total = L.st_off + (uint32_t)a.st_cols * 32u /* epilogue statistics: [4 lane quarters][2][st_cols] floats */ + 1024u /* slack */;
     return L;
 }
 
@@ -112,7 +120,44 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
 // single-warp issue loops are sensitive to every extra instruction.
 // KBOX = 2 (CONV pair tiles only): a pipeline stage holds two consecutive (tap, channel block) boxes, so the barrier round
 // trip and the fixed part of the issue loops are paid once per 8 MMAs.
-template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1>
+// sum over the 32 lanes of a warp of 16 per-lane values, transposing as it goes: 16 + 8 + 4 + 2 + 1 shuffles instead of 16 x 5.
+// Lane l returns the total of column (l >> 1) & 15 (lanes l and l ^ 1 hold the same column).
+__device__ __forceinline__ float tc_warp_cols16_sum(const float (&v)[16], int lane) {
+    float w8[8], w4[4], w2[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+            w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? w8[i] : w8[i + 4], keep = up ? w8[i + 4] : w8[i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? w4[i] : w4[i + 2], keep = up ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool up = lane & 2;
+    const float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+    float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    return w1;
+}
+
+// STATS (CONV mode, NHWC bf16 output): the epilogue also reduces per-channel sum / sum of squares of the stored result for the
+// batch norm that follows (TcArgs::st_*).
+template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1, bool STATS = false>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args_) {
@@ -132,6 +177,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = args.BN;
     const int stages = args.stages;
+    // [4 TMEM lane quarters][2 sums][st_cols]: the two epilogue warps of a quarter own disjoint columns, so they update their
+    // quarter's slot with plain read-modify-writes (a shared-memory float atomicAdd is a compare-and-swap loop)
+    float* const st_smem = (float*)(smem + L.st_off);
+    unsigned st_e = 0;
+    if (STATS) {
+        for (int i = threadIdx.x; i < 8 * args.st_cols; i += TC_THREADS) st_smem[i] = 0.f;
+        st_e = *args.st_epoch;
+        if (blockIdx.x == 0) {   // same protocol as flat_bn_stats_kernel: clear the buffer of the next launch, publish the epoch
+            float* other = args.st_sums + (size_t)((st_e + 1u) & 1u) * args.st_copies * 2 * args.st_cp;
+            for (int i = threadIdx.x; i < args.st_copies * 2 * args.st_cp; i += TC_THREADS) other[i] = 0.f;
+            if (threadIdx.x == 0) args.st_epoch[1] = st_e;
+        }
+    }
     constexpr bool pair = PAIR && (MODE == TC_MODE_CONV);
     constexpr int csize = pair ? 2 : 1;
     const uint32_t crank = pair ? tcg::cluster_ctarank() : 0;
@@ -479,6 +537,45 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                     // the tap's plane of the output is selected through tap_bcol[] (set by the host)
                     row_off = args.o_off + (long long)m * args.o_sn + (long long)args.tap_bcol[w.wg_tap];
                 }
+                if (STATS) {
+                    // NHWC bf16 store first (r dies with it), then the statistics of what was stored -- the bf16-rounded
+                    // values -- in place.  Rows outside the tensor and columns beyond Nout add 0.
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        pk[j] = *(uint32_t*)&h;
+                    }
+                    const bool full = col0 + cb + 16 <= args.Nout;
+                    if (row_ok) {
+                        __nv_bfloat16* dst = (__nv_bfloat16*)args.out + row_off + col0 + cb;
+                        if (full) {
+                            ((uint4*)dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            ((uint4*)dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (col0 + cb + j < args.Nout)
+                                    ((unsigned short*)dst)[j] = (unsigned short)((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xffffu));
+                        }
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[2 * j] = (row_ok && (full || col0 + cb + 2 * j < args.Nout)) ? __uint_as_float(pk[j] << 16) : 0.f;
+                        v[2 * j + 1] = (row_ok && (full || col0 + cb + 2 * j + 1 < args.Nout)) ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                    }
+                    const float s1 = tc_warp_cols16_sum(v, lane);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= v[j];
+                    const float s2 = tc_warp_cols16_sum(v, lane);
+                    if (!(lane & 1)) {
+                        float* slot = st_smem + (size_t)quarter * 2 * args.st_cols + col0 + cb + (lane >> 1);
+                        slot[0] += s1;
+                        slot[args.st_cols] += s2;
+                    }
+                    continue;
+                }
                 if (!row_ok || (dbg & 8)) continue;
                 if (args.out_kind == TC_OUT_F32_ATOMIC && !have) continue;
                 if (args.out_kind == TC_OUT_BF16 && args.o_sc == 1 && col0 + cb + 16 <= args.Nout) {
@@ -513,6 +610,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
             }
             if (trace_on && blockIdx.x == 0 && threadIdx.x == 64 && t_done <= 16 && t_done > 0)
                 args.trace[512 + 2 * (t_done - 1) + 1] = clock64();
+        }
+        if (STATS) {
+            // all eight epilogue warps have added their tiles: one fire-and-forget atomic per channel and sum for this CTA
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            float* dst = args.st_sums + ((size_t)(st_e & 1u) * args.st_copies + blockIdx.x % args.st_copies) * 2 * args.st_cp;
+            for (int i = (int)threadIdx.x - 64; i < 2 * args.st_cols; i += 32 * TC_EPI_WARPS) {
+                const int q = i >= args.st_cols ? 1 : 0, c = i - q * args.st_cols;
+                if (c < args.Nout)
+                    atomicAdd(dst + q * args.st_cp + c, (st_smem[i] + st_smem[2 * args.st_cols + i]) +
+                                                          (st_smem[4 * args.st_cols + i] + st_smem[6 * args.st_cols + i]));
+            }
         }
     }
 

@@ -125,6 +125,10 @@ def set_plan_flags(flags):
     _h.dh_set_plan_flags(int(flags))
 
 
+def plan_flags():
+    return int(_h.dh_plan_flags())
+
+
 def set_math(m):
     _h.dh_set_math(int(m))
 

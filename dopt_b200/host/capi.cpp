@@ -76,6 +76,7 @@ void dh_reset() {
     g_ops.clear();
 }
 void dh_set_plan_flags(int f) { cuda::setPlanFlags(f); }
+int dh_plan_flags() { return cuda::planFlags(); }
 void dh_set_math(int m) { cuda::setMath(m); }
 void dh_set_stream(void* s) { cuda::setStream(s); }
 void dh_seed(uint64_t s) { nnet::seedInitializers(s); }

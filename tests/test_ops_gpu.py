@@ -237,7 +237,8 @@ def test_matmul_fp32(M, K, N, math):
     assert rel_err(got, ref) < 1e-5 * max(1.0, np.sqrt(K))
 
 
-@pytest.mark.parametrize("M,K,N", [(256, 512, 256), (1000, 520, 264), (128, 4096, 64), (300, 200, 650)])
+@pytest.mark.parametrize("M,K,N", [(256, 512, 256), (1000, 520, 264), (128, 4096, 64), (300, 200, 650),
+                                   (128, 640, 100), (640, 128, 100), (128, 100, 640)])   # + the WRN dense layer and its gradients
 def test_matmul_tensor_core(M, K, N):
     rng = np.random.RandomState(17)
     a, b = rng.randn(M, K).astype(F), rng.randn(K, N).astype(F)

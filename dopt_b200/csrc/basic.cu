@@ -45,24 +45,29 @@ __global__ void __launch_bounds__(256) map_kernel(const uint32_t* __restrict__ i
 __global__ void __launch_bounds__(256) transpose_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                         int rows_in, int cols_in) {
     // in: [rows_in][cols_in] -> out: [cols_in][rows_in]
+    // the row tiles are on gridDim.x (2^31 - 1 tiles), the column tiles on gridDim.y and looped over when there are more than 65535
     __shared__ uint32_t tile[32][33];
-    int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int by = blockIdx.x * 32;
+    for (int bx = blockIdx.y * 32; bx < cols_in; bx += gridDim.y * 32) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        int r = by + ty + j, c = bx + tx;
-        if (r < rows_in && c < cols_in) tile[ty + j][tx] = in[(int64_t)r * cols_in + c];
-    }
-    __syncthreads();
+        for (int j = 0; j < 32; j += 8) {
+            int r = by + ty + j, c = bx + tx;
+            if (r < rows_in && c < cols_in) tile[ty + j][tx] = in[(int64_t)r * cols_in + c];
+        }
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        int r = bx + ty + j, c = by + tx;   // out row = in col
-        if (r < cols_in && c < rows_in) out[(int64_t)r * rows_in + c] = tile[tx][ty + j];
+        for (int j = 0; j < 32; j += 8) {
+            int r = bx + ty + j, c = by + tx;   // out row = in col
+            if (r < cols_in && c < rows_in) out[(int64_t)r * rows_in + c] = tile[tx][ty + j];
+        }
+        __syncthreads();
     }
 }
 
 void transpose2d_launch(const void* in, void* out, int rows_in, int cols_in, cudaStream_t s) {
-    dim3 grid((unsigned)ceil_div(cols_in, 32), (unsigned)ceil_div(rows_in, 32));
+    if (rows_in <= 0 || cols_in <= 0) return;
+    dim3 grid((unsigned)ceil_div(rows_in, 32), (unsigned)std::min<int64_t>(ceil_div(cols_in, 32), 65535));
     transpose_kernel<<<grid, 256, 0, s>>>((const uint32_t*)in, (uint32_t*)out, rows_in, cols_in);
     DB_LAUNCH_CHECK();
 }

@@ -74,29 +74,33 @@ __global__ void __launch_bounds__(256) colsum_final(const float* __restrict__ pa
 }
 
 // general fp32 GEMM, C = A(MxK) * B(KxN), all row-major.  64x64 CTA tile, 16-deep k slab, 4x4 outputs per thread.
+// blockIdx.z selects a k range of `kchunk` (split-K): slice z writes its partial product to C + z * M * N
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                    float* __restrict__ C, int M, int N, int K) {
+                                                    float* __restrict__ C, int M, int N, int K, int kchunk) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     int tid = threadIdx.x;
-    int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;   // row tiles on gridDim.x: tall operands (M in the millions) are common
     int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    C += (int64_t)blockIdx.z * M * N;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
         // A tile: 64 rows x 16 k -> As[k][m]; 1024 elements, 4 per thread
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int e = tid + i * 256;
             int r = e >> 4, kk = e & 15;
             int gm = m0 + r, gk = k0 + kk;
-            As[kk][r] = (gm < M && gk < K) ? A[(int64_t)gm * K + gk] : 0.f;
+            As[kk][r] = (gm < M && gk < kend) ? A[(int64_t)gm * K + gk] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int e = tid + i * 256;
             int kk = e >> 6, c = e & 63;
             int gk = k0 + kk, gn = n0 + c;
-            Bs[kk][c] = (gk < K && gn < N) ? B[(int64_t)gk * N + gn] : 0.f;
+            Bs[kk][c] = (gk < kend && gn < N) ? B[(int64_t)gk * N + gn] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -125,9 +129,40 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     }
 }
 
-void sgemm_launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, cudaStream_t s) {
-    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-    sgemm_kernel<<<grid, 256, 0, s>>>(A, B, C, (int)M, (int)N, (int)K);
+// sum of `parts` partial products (split-K), in slice order: deterministic
+__global__ void __launch_bounds__(256) sgemm_reduce_kernel(const float* __restrict__ part, float* __restrict__ c, int64_t n,
+                                                           int parts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < parts; ++p) acc += part[(int64_t)p * n + i];
+        c[i] = acc;
+    }
+}
+
+// how many k slices a small-output GEMM is split into (1 = no split): few 64x64 output tiles and a long reduction would leave
+// most SMs idle behind a serial k loop (the dense layer of the WRN configs: 4 tiles x 40 k-slabs took 22 us)
+int sgemm_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ceil_div(N, 64) * ceil_div(M, 64);
+    if (tiles * 2 > sm_count() || K < 64) return 1;
+    int64_t s = std::min<int64_t>(ceil_div(K, 32), std::max<int64_t>(1, sm_count() / tiles));
+    return (int)std::max<int64_t>(1, s);
+}
+
+void sgemm_launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, cudaStream_t s, float* ws = nullptr,
+                  int splits = 1) {
+    if (splits > 1 && ws) {
+        int kchunk = (int)(ceil_div(ceil_div(K, splits), 16) * 16);
+        splits = (int)ceil_div(K, kchunk);
+        dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(N, 64), (unsigned)splits);
+        sgemm_kernel<<<grid, 256, 0, s>>>(A, B, ws, (int)M, (int)N, (int)K, kchunk);
+        DB_LAUNCH_CHECK();
+        sgemm_reduce_kernel<<<stream_grid(M * N, 256, 4), 256, 0, s>>>(ws, C, M * N, splits);
+        DB_LAUNCH_CHECK();
+        return;
+    }
+    DB_REQUIRE(ceil_div(N, 64) <= 65535, "matmul: more than 4.19 M result columns are not supported by the fp32 kernel");
+    dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(N, 64));
+    sgemm_kernel<<<grid, 256, 0, s>>>(A, B, C, (int)M, (int)N, (int)K, (int)K);
     DB_LAUNCH_CHECK();
 }
 
@@ -185,7 +220,9 @@ struct MatmulKernel : Kernel {
         } else if (tc) {
             tc_gemm_run(tc, a, b, c, s);
         } else {
-            sgemm_launch(a, b, c, M, N, K, s);
+            const int splits = sgemm_splits(M, N, K);
+            float* part = splits > 1 ? (float*)ws.get((size_t)splits * M * N * sizeof(float)) : nullptr;
+            sgemm_launch(a, b, c, M, N, K, s, part, splits);
         }
     }
 };

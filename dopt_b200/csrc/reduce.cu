@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) argmin_kernel(const T* __restrict__ in, i
 
 template <typename T, class R>
 static void reduce_axis(const T* in, T* out, int64_t outer, int64_t A, int64_t inner, Scratch& ws, cudaStream_t s) {
+    if (outer * inner == 0) return;   // empty result: nothing to launch (a zero-sized grid is an invalid configuration)
     if (inner == 1) {
         // split long rows over several CTAs so that a full reduction (outer == 1) still fills the chip
         int chunks = 1;

@@ -543,10 +543,11 @@ struct TcGemm {
 };
 
 bool tc_gemm_supported(int64_t M, int64_t N, int64_t K) {
-    // worth a 128-row tensor-core tile only when the product is big enough; everything else is latency-bound anyway.  The
-    // bound admits the dense layer of the WRN configs ([128,640]x[640,100] and its two gradients: 8.2 MFLOP-pairs), which the
-    // fp32 SIMT kernel spent 22 us each on
-    return M >= 128 && N >= 64 && K >= 64 && M * N * K >= (int64_t)1 << 22 && M < (1 << 30) && N < (1 << 30);
+    // worth a 128-row tensor-core tile only when the product is big enough; everything else is latency-bound anyway.
+    // (Measured, profiles/r02_summary.md: the dense layer of the WRN configs, [128,640]x[640,100] and its two gradients, takes
+    // 14.5 us per launch here -- two operand casts + a one-tile launch -- against 22 us on the split-K SIMT kernel's predecessor;
+    // it stays on the fp32 path, which also keeps its results at fp32 accuracy.)
+    return M >= 128 && N >= 64 && K >= 64 && M * N * K >= (int64_t)1 << 24 && M < (1 << 30) && N < (1 << 30);
 }
 TcGemm* tc_gemm_create(int64_t M, int64_t N, int64_t K) {
     auto* g = new TcGemm;

@@ -178,27 +178,33 @@ __global__ void __launch_bounds__(256) flat_bn_apply_kernel(const uint4* __restr
                                                             const uint4* __restrict__ addend, uint4* __restrict__ out,
                                                             int64_t P, int G, int C, int R,
                                                             const __grid_constant__ FlatApplyArgs a) {
-    __shared__ float ssum[2 * 2048];   // [2][Cp]: the launch's sums, copies added in a fixed order
+    __shared__ __align__(16) float ssum[2 * 2048];   // [2][Cp]: the launch's sums, copies added in a fixed order
     const int t = threadIdx.x;
     const int cg_ = t % G;
     const int Cp = G * 8;
     const float invM = 1.0f / (float)P;
-    const unsigned e = a.ws.epoch[1];
-    if (t < G) {
-        const float4* src = (const float4*)(a.ws.sums + (size_t)(e & 1u) * kFlatCopies * 2 * Cp);
-        const int q4 = Cp / 4;   // float4 per sum row
+    // All loads of the prologue are issued back to back (one L2 round trip instead of three): the epoch, BOTH sum buffers
+    // (the current one is selected afterwards), and further down the per-channel parameters.  Thread f < 2*Cp/4 owns float4
+    // column f of the sums and adds its kFlatCopies copies in a fixed order.
+    const unsigned e = __ldcg(a.ws.epoch + 1);
+    const int nf4 = 2 * Cp / 4;
+    for (int f = t; f < nf4; f += blockDim.x) {
+        const float4* b0 = (const float4*)a.ws.sums + f;
+        const float4* b1 = b0 + (size_t)kFlatCopies * nf4;
+        float4 v0[kFlatCopies], v1[kFlatCopies];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int k = 0; k < kFlatCopies; ++k) {
+            v0[k] = __ldcg(b0 + (size_t)k * nf4);
+            v1[k] = __ldcg(b1 + (size_t)k * nf4);
+        }
+        const bool odd = e & 1u;
+        float4 r = odd ? v1[0] : v0[0];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float4 v[kFlatCopies];
-#pragma unroll
-                for (int k = 0; k < kFlatCopies; ++k) v[k] = __ldcg(src + (size_t)(k * 2 + q) * q4 + cg_ * 2 + h);
-                float4 r = v[0];
-#pragma unroll
-                for (int k = 1; k < kFlatCopies; ++k) { r.x += v[k].x; r.y += v[k].y; r.z += v[k].z; r.w += v[k].w; }
-                *(float4*)&ssum[q * Cp + cg_ * 8 + h * 4] = r;
-            }
+        for (int k = 1; k < kFlatCopies; ++k) {
+            const float4 w = odd ? v1[k] : v0[k];
+            r.x += w.x; r.y += w.y; r.z += w.z; r.w += w.w;
+        }
+        *(float4*)&ssum[f * 4] = r;
     }
     __syncthreads();
     if (blockIdx.x == 0 && t == 0) a.ws.epoch[0] = e + 1u;   // read by the NEXT statistics kernel only

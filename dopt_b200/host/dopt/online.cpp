@@ -69,10 +69,16 @@ void loadState(const LastUpdate& u, const std::string& filename) {
     for (size_t i = 0; i < tensors.size(); ++i) tensors[i]->value()->set(data[i].data(), data[i].size() * sizeof(float));
 }
 
-// data-parallel: the mean over ranks of every gradient, as a registered `allreduce` op between grad() and the update rule
+// A "gradient" that is a plain variable / constant is the zero tensor the batch-norm gradient rule hands out for the running
+// mean and variance (core/source/dopt/core/grads/nnet.d:80-81): such parameters are state, moved only by their projection.
+static bool isStateOnly(const Operation& g) { return g->opType() == "variable" || g->opType() == "constant"; }
+
+// data-parallel: the mean over ranks of every gradient, as a registered `allreduce` op between grad() and the update rule.
+// Zero "gradients" of state-only parameters are identical on every rank and are not exchanged.
 static std::vector<Operation> exchange(std::vector<Operation> grads) {
     if (dataParallelWorld() <= 1) return grads;
-    for (auto& g : grads) g = createOperation("allreduce", {g});
+    for (auto& g : grads)
+        if (!isStateOnly(g)) g = createOperation("allreduce", {g});
     return grads;
 }
 
@@ -98,11 +104,16 @@ static Updater finish(const std::vector<Operation>& outputs, std::vector<Operati
     };
 }
 
+// `rawGrads` are the gradients before the exchange.  Data-parallel: the projection of a state-only parameter (the batch-norm
+// running statistics, nnet/layers/batchnorm.d:140-154, computed from the rank's own batch) is averaged over the ranks, so
+// every replica -- and any checkpoint or inference plan made from it -- carries the same running mean / variance.
 static void applyProjections(const std::vector<Operation>& wrt, const std::map<Operation, Projection>& projs,
-                             std::vector<Operation>& newvals) {
+                             std::vector<Operation>& newvals, const std::vector<Operation>& rawGrads) {
     for (size_t i = 0; i < newvals.size(); ++i) {
         auto it = projs.find(wrt[i]);
-        if (it != projs.end() && it->second) newvals[i] = it->second(newvals[i]);
+        if (it == projs.end() || !it->second) continue;
+        newvals[i] = it->second(newvals[i]);
+        if (dataParallelWorld() > 1 && isStateOnly(rawGrads[i])) newvals[i] = createOperation("allreduce", {newvals[i]});
     }
 }
 
@@ -112,7 +123,8 @@ Updater sgd(const std::vector<Operation>& outputs, const std::vector<Operation>&
     if (!learningRate) learningRate = float32({}, {0.01f});
     if (!momentumRate) momentumRate = float32({}, {0.0f});
     auto objective = outputs[0];
-    auto grads = exchange(grad(objective, wrt));
+    auto rawGrads = grad(objective, wrt);
+    auto grads = exchange(rawGrads);
     std::vector<Operation> momentum, newMomentum, newvals;
     for (auto& g : grads) momentum.push_back(float32(g->shape()));
     if (nesterov) {
@@ -123,7 +135,7 @@ Updater sgd(const std::vector<Operation>& outputs, const std::vector<Operation>&
         for (size_t i = 0; i < grads.size(); ++i) newMomentum.push_back(momentum[i] * momentumRate + learningRate * grads[i]);
         for (size_t i = 0; i < grads.size(); ++i) newvals.push_back(wrt[i] - newMomentum[i]);
     }
-    applyProjections(wrt, projs, newvals);
+    applyProjections(wrt, projs, newvals, rawGrads);
     std::vector<Operation> planOutputs(outputs);
     planOutputs.insert(planOutputs.end(), newvals.begin(), newvals.end());
     planOutputs.insert(planOutputs.end(), newMomentum.begin(), newMomentum.end());
@@ -141,7 +153,8 @@ static Updater adamImpl(const std::vector<Operation>& outputs, const std::vector
     if (!beta2) beta2 = float32({}, {0.999f});
     if (!eps) eps = float32({}, {1e-8f});
     auto objective = outputs[0];
-    auto grads = exchange(grad(objective, wrt));
+    auto rawGrads = grad(objective, wrt);
+    auto grads = exchange(rawGrads);
     std::vector<Operation> means, vars, varhats;
     for (auto& w : wrt) means.push_back(float32(w->shape()));
     for (auto& w : wrt) vars.push_back(float32(w->shape()));
@@ -158,7 +171,7 @@ static Updater adamImpl(const std::vector<Operation>& outputs, const std::vector
     if (ams)
         for (size_t i = 0; i < wrt.size(); ++i) newVarhats.push_back(max(varhats[i], vars[i]));   // amsgrad.d:63-66 (survey F11)
     for (size_t i = 0; i < wrt.size(); ++i) newvals.push_back(wrt[i] - eta * (newMeans[i] / (sqrt(newVars[i]) + eps)));
-    applyProjections(wrt, projs, newvals);
+    applyProjections(wrt, projs, newvals, rawGrads);
     std::vector<Operation> planOutputs(outputs);
     planOutputs.insert(planOutputs.end(), newvals.begin(), newvals.end());
     planOutputs.insert(planOutputs.end(), newMeans.begin(), newMeans.end());

@@ -522,6 +522,33 @@ def test_data_parallel_wraps_gradients_in_allreduce():
     assert types(upd.plan_outputs()[0]).count("allreduce") == 0
 
 
+def test_data_parallel_batchnorm_statistics_are_averaged_and_zero_gradients_are_not_exchanged():
+    """A batch-norm layer has two trainable tensors (scale, bias) and two state tensors (running mean / var) whose "gradient"
+    is a zero variable (core/source/dopt/core/grads/nnet.d:80-81) and whose new value is a projection computed from the rank's
+    own batch (nnet/layers/batchnorm.d:140-154).  With a data-parallel world > 1 the real gradients are exchanged, the zero
+    ones are not, and the projected running statistics are averaged over ranks so that all replicas stay identical."""
+    def count(world):
+        H.reset()
+        H.seed(3)
+        H.set_data_parallel_world(world)
+        x, y = H.float32((4, 3, 8, 8)), H.float32((4, 5))
+        out = H.data_source(x).conv2d(8, (3, 3), padding=(1, 1), use_bias=False).batch_norm().relu().dense(5).softmax()
+        net = H.Network([x], [out])
+        loss = H.cross_entropy(out.train_output, y) + net.param_loss
+        upd = H.Updater(H.SGD, [loss], network=net, hyper=[H.float32((), [0.1]), H.float32((), [0.9])])
+        plan_ops, _ = upd.plan_outputs()
+        nodes = H.export(plan_ops)
+        by_id = dict((n["id"], n) for n in nodes)
+        reduced = [by_id[n["deps"][0]] for n in nodes if n["type"] == "allreduce"]
+        return len(net.params), reduced
+    n_params, reduced = count(2)
+    assert n_params == 1 + 4 + 2                                   # conv w | scale, bias, mean, var | dense w, b
+    # 5 real gradients (conv w, scale, bias, dense w, dense b) + the 2 running statistics; never a bare zero variable
+    assert len(reduced) == 5 + 2
+    assert all(r["type"] not in ("variable", "constant") for r in reduced)
+    assert count(1)[1] == []
+
+
 def test_no_backend_means_no_evaluation():
     import torch
     if torch.cuda.is_available():

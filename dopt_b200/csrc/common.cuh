@@ -78,6 +78,16 @@ size_t filter_pack_bytes(const FilterPack& f);
 void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_bytes);
 void filter_pack_launch(const FilterPack* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s);
 
+// one filter gradient to finish: the tensor-core kernel's [tap][C][K] accumulation scratch -> dopt's KCRS (flipped) gradient
+struct WgradFinish {
+    const float* scratch;
+    float* dw;
+    int K, C, RS;
+    int tiles_x, tile0;      // filled by the launcher: 32-wide K tiles, first tile of this row
+};
+void wgrad_finish_layout(WgradFinish* rows, int n, int* total_tiles, size_t* smem_bytes);
+void wgrad_finish_launch(const WgradFinish* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s);
+
 // one row of a batched full reduction (msum.cu): *out = sum_i a[i] * b[i]  (b == nullptr: sum_i a[i])
 struct MsumRow {
     const float* a;
@@ -133,6 +143,10 @@ struct Kernel {
     // batch-norm statistics accumulated by the producer of x: a flat batchNormTrain hands out its statistics workspace
     // (stats_workspace; mode 1 = sums pivoted by pixel 0, the residual add; mode 2 = plain sums, the convolution epilogue) and
     // skips its own statistics kernel; the producer (can_produce_stats) accumulates into it while it writes x
+    // convolutionFiltersGrad on the tensor cores: leave the result in a private [tap][C][K] scratch and let the plan turn the
+    // scratches of many filter gradients into KCRS with ONE multi-tensor launch (28 latency-sized launches per WRN step
+    // otherwise).  deferred_finish fills everything of the row but `dw`.
+    virtual bool deferred_finish(struct WgradFinish* /*row*/) { return false; }
     virtual void* stats_workspace(int /*mode*/) { return nullptr; }
     virtual int can_produce_stats() const { return 0; }   // 0 = no, else the mode it produces
     virtual void set_stats_workspace(void* /*bn_workspace*/, int /*channels*/) {}

@@ -72,6 +72,7 @@ struct Node {
     int gate_from = -1;         // batchNormGrad: batchNormTrain node whose relu gates the incoming gradient (reluGrad absorbed)
     int in_override[DOPT_B200_MAX_INPUTS] = {-1, -1, -1, -1, -1, -1, -1, -1};   // read this node instead of deps[k]
     // bf16-interior activations (pass "residency")
+    int finish_group = -1;      // tensor-core convolutionFiltersGrad whose scratch -> KCRS conversion is done by a multi-tensor launch
     bool flat = false;          // batchNormTrain / batchNormGrad / add working on NHWC bf16 operands and result (flat.cu)
     int out_stage = -1;         // tensor-core convolution whose epilogue writes this stage (NHWC bf16) instead of NCHW fp32
     // runtime
@@ -93,7 +94,7 @@ struct Region {
 };
 
 enum ItemKind { ITEM_KERNEL = 0, ITEM_PW_SCALAR = 1, ITEM_FUSED = 2, ITEM_BUCKET = 3, ITEM_COPY = 4, ITEM_STAGE = 5, ITEM_PACK = 6, ITEM_MSUM = 7,
-                ITEM_UNSTAGE = 8 };
+                ITEM_UNSTAGE = 8, ITEM_WFINISH = 9 };
 struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
@@ -152,6 +153,15 @@ struct dopt_b200_plan_s {
         int64_t chunks = 0;
     };
     std::vector<MsumGroup> msums;
+    // deferred filter-gradient finishes: one multi-tensor launch per gradient bucket (or one for the whole step)
+    struct FinishGroup {
+        std::vector<int> nodes;
+        std::vector<db::WgradFinish> rows;
+        db::WgradFinish* dev = nullptr;
+        int tiles = 0;
+        size_t smem = 0;
+    };
+    std::vector<FinishGroup> finishes;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     int64_t device_bytes = 0;
@@ -185,6 +195,8 @@ struct dopt_b200_plan_s {
             if (m.dev) cudaFree(m.dev);
             if (m.partial) cudaFree(m.partial);
         }
+        for (auto& f : finishes)
+            if (f.dev) cudaFree(f.dev);
         if (packs_dev) cudaFree(packs_dev);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
@@ -750,6 +762,21 @@ static void schedule(Plan& p) {
         item_key.push_back(key_of(st.producer) + 1);
         unstage_item[st.unstage_to] = (int)items.size() - 1;
     }
+    // deferred filter-gradient finishes: the gradient exists once its group's multi-tensor launch has run
+    std::vector<int> finish_item(p.finishes.size(), -1);
+    for (size_t g = 0; g < p.finishes.size(); ++g) {
+        items.push_back({ITEM_WFINISH, (int)g, false});
+        int64_t k = 0;
+        for (int w : p.finishes[g].nodes) k = std::max(k, key_of(w));
+        item_key.push_back(k + 1);
+        finish_item[g] = (int)items.size() - 1;
+    }
+    // the item after which node `id`'s own buffer holds its value
+    auto value_item = [&](int id) {
+        if (unstage_item[id] >= 0) return unstage_item[id];
+        if (N[id].finish_group >= 0) return finish_item[N[id].finish_group];
+        return item_of_node[id];
+    };
     // the item that makes the value read through `d` available: the bucket when the view chain passes an in-place allreduce
     auto producer_item = [&](int d, bool* via_bucket) {
         int id = d;
@@ -764,8 +791,7 @@ static void schedule(Plan& p) {
             if (via_bucket) *via_bucket = true;
             return item_of_bucket[N[id].bucket];
         }
-        if (unstage_item[id] >= 0) return unstage_item[id];
-        return item_of_node[id];
+        return value_item(id);
     };
     std::vector<std::set<int>> succ(items.size());
     std::vector<int> indeg(items.size(), 0);
@@ -796,7 +822,9 @@ static void schedule(Plan& p) {
                 }
     }
     for (size_t b = 0; b < p.buckets.size(); ++b)
-        for (int m : p.buckets[b].members) add_edge(item_of_node[root_of(p, m)], item_of_bucket[b]);
+        for (int m : p.buckets[b].members) add_edge(value_item(root_of(p, m)), item_of_bucket[b]);
+    for (size_t g = 0; g < p.finishes.size(); ++g)
+        for (int w : p.finishes[g].nodes) add_edge(item_of_node[w], finish_item[g]);
     for (size_t si = 0; si < p.stages.size(); ++si) {
         const Stage& st = p.stages[si];
         if (st.unstage_to >= 0 && st.producer >= 0) add_edge(item_of_node[st.producer], unstage_item[st.unstage_to]);
@@ -1560,6 +1588,30 @@ static void build(Plan& p) {
             filter_pack_layout(p.packs.data(), (int)p.packs.size(), &p.pack_tiles, &p.pack_smem);
             DB_CUDA(cudaMalloc(&p.packs_dev, p.packs.size() * sizeof(FilterPack)));
         }
+        // filter gradients of the tensor-core path: one finishing launch per gradient bucket (data-parallel) or per step
+        if (!getenv("DOPT_B200_NO_DEFER_FINISH")) {
+            std::map<int, int> group_of_key;   // bucket id (-1: not exchanged) -> finish group
+            std::vector<int> key(N.size(), -1);
+            for (size_t u = 0; u < N.size(); ++u)
+                if (N[u].needed && N[u].bucket >= 0 && !N[u].deps.empty()) key[root_of(p, N[u].deps[0])] = N[u].bucket;
+            std::set<int> out_roots;
+            for (int o : p.outputs) out_roots.insert(root_of(p, o));
+            for (size_t i = 0; i < N.size(); ++i) {
+                Node& n = N[i];
+                if (!n.needed || n.alias_of >= 0 || !n.kernel || n.type != "convolutionFiltersGrad" || out_roots.count((int)i)) continue;
+                WgradFinish row{};
+                if (!n.kernel->deferred_finish(&row)) continue;
+                auto it = group_of_key.find(key[i]);
+                if (it == group_of_key.end()) {
+                    it = group_of_key.emplace(key[i], (int)p.finishes.size()).first;
+                    p.finishes.emplace_back();
+                }
+                n.finish_group = it->second;
+                p.finishes[it->second].nodes.push_back((int)i);
+                p.finishes[it->second].rows.push_back(row);
+                p.device_bytes += (int64_t)row.RS * row.K * row.C * 4;
+            }
+        }
         if (!getenv("DOPT_B200_NO_ABSORB")) absorb(p);
         if ((p.flags & DOPT_B200_PLAN_BF16_INTERIOR) && !getenv("DOPT_B200_NO_ABSORB") && !getenv("DOPT_B200_NO_RESIDENT")) residency(p);
         for (size_t si = 0; si < p.stages.size(); ++si) {
@@ -1580,7 +1632,7 @@ static void build(Plan& p) {
     p.direct_out.assign(p.outputs.size(), 0);
     if (getenv("DOPT_B200_PLAN_DUMP")) {
         // one line per scheduled item: kind, op type, output volume, the op types of its operands
-        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack", "msum", "unstage"};
+        static const char* kinds[] = {"kernel", "pw_scalar", "fused", "bucket", "copy", "stage", "pack", "msum", "unstage", "wfinish"};
         for (const Item& it : p.order) {
             if (it.kind == ITEM_KERNEL || it.kind == ITEM_PW_SCALAR || it.kind == ITEM_COPY) {
                 const Node& n = N[it.id];
@@ -1778,6 +1830,10 @@ static void run_items(Plan& p, cudaStream_t s) {
             const Stage& st = p.stages[it.id];
             stage_nchw_to_nhwc_bf16((const float*)N[st.src_dep].ptr, st.buf, st.n, st.c, st.hw, s);
             label = "stageNHWC";
+        } else if (it.kind == ITEM_WFINISH) {
+            auto& f = p.finishes[it.id];
+            wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, s);
+            label = "filtersGradFinish";
         } else if (it.kind == ITEM_UNSTAGE) {
             const Stage& st = p.stages[it.id];
             unstage_nhwc_bf16_to_nchw(st.buf, (float*)N[st.unstage_to].ptr, st.n, st.c, st.hw, s);
@@ -1909,6 +1965,12 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
                 DB_CUDA(cudaMalloc(&m.partial, (size_t)m.chunks * sizeof(float)));
             }
             DB_CUDA(cudaMemcpy(m.dev, m.rows.data(), m.rows.size() * sizeof(MsumRow), cudaMemcpyHostToDevice));
+        }
+        for (auto& f : p.finishes) {
+            for (size_t i = 0; i < f.nodes.size(); ++i) f.rows[i].dw = (float*)N[f.nodes[i]].ptr;
+            wgrad_finish_layout(f.rows.data(), (int)f.rows.size(), &f.tiles, &f.smem);
+            if (!f.dev) DB_CUDA(cudaMalloc(&f.dev, f.rows.size() * sizeof(WgradFinish)));
+            DB_CUDA(cudaMemcpy(f.dev, f.rows.data(), f.rows.size() * sizeof(WgradFinish), cudaMemcpyHostToDevice));
         }
         if (!p.packs.empty()) {
             for (size_t i = 0; i < p.packs.size(); ++i) p.packs[i].w = (const float*)N[p.pack_users[i].second].ptr;

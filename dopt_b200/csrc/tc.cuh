@@ -30,5 +30,7 @@ void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16);
 // fwd with staged output: also accumulate sum / sum of squares per output channel into the statistics workspace of the flat
 // batchNormTrain that reads the result (flat.cuh: flat_stats_sink)
 void conv_tc_set_stats_workspace(ConvTc* c, void* bn_workspace);
+// wgrad: accumulate into a private scratch (allocated here) and skip the per-op finish kernel; the caller finishes `row` later
+bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row);
 
 }  // namespace db

@@ -238,11 +238,10 @@ __global__ void __launch_bounds__(256) pack_filters_multi_kernel(const FilterPac
 // convolutionFiltersGrad: the tensor-core kernel accumulates into a scratch laid out [tap][C][K] (K contiguous = the
 // accumulator's lane dimension, so a warp's 32 atomic adds fall into one 128-byte line); this turns it into dopt's KCRS
 // with the filter flip.  grid (ceil(K/32), ceil(C/32)), 256 threads, dynamic smem 32*(32*RS+1) floats.
-__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int K,
-                                                           int C, int RS) {
-    extern __shared__ float pf_tile[];   // [32 k][32 c * RS (+1)]
-    const int ld = 32 * RS + 1;
-    const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+__device__ __forceinline__ void wgrad_finish_tile(const float* __restrict__ scratch, float* __restrict__ dw, int K, int C, int RS,
+                                                  int bx, int by, float* pf_tile) {
+    const int ld = 32 * RS + 1;          // pf_tile: [32 k][32 c * RS (+1)]
+    const int k0 = bx * 32, c0 = by * 32;
     const int kk = threadIdx.x & 31, k = k0 + kk;
     // rows (tap, c) of 32 consecutive k; 4 * RS rows per warp, loaded four at a time into registers before they are stored
     for (int row0 = threadIdx.x >> 5; row0 < 32 * RS; row0 += 32) {
@@ -269,6 +268,49 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
         float* dst = dw + ((int64_t)kr * C + c0) * RS;
         for (int j = threadIdx.x & 31; j < run; j += 32) dst[j] = pf_tile[r * ld + j];
     }
+}
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int K,
+                                                           int C, int RS) {
+    extern __shared__ float pf_tile[];
+    wgrad_finish_tile(scratch, dw, K, C, RS, blockIdx.x, blockIdx.y, pf_tile);
+}
+// every deferred filter gradient of a plan (or of one gradient bucket) in one launch: block -> (row, tile) through the rows'
+// tile prefix, like pack_filters_multi_kernel
+__global__ void __launch_bounds__(256) wgrad_finish_multi_kernel(const WgradFinish* __restrict__ rows, int n_rows) {
+    extern __shared__ float pf_tile[];
+    int lo = 0, hi = n_rows - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (rows[mid].tile0 <= (int)blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const WgradFinish r = rows[lo];
+    const int t = (int)blockIdx.x - r.tile0;
+    wgrad_finish_tile(r.scratch, r.dw, r.K, r.C, r.RS, t % r.tiles_x, t / r.tiles_x, pf_tile);
+}
+void wgrad_finish_layout(WgradFinish* rows, int n, int* total_tiles, size_t* smem_bytes) {
+    int tiles = 0;
+    size_t smem = 0;
+    for (int i = 0; i < n; ++i) {
+        WgradFinish& f = rows[i];
+        f.tiles_x = (int)ceil_div(f.K, 32);
+        f.tile0 = tiles;
+        tiles += f.tiles_x * (int)ceil_div(f.C, 32);
+        smem = std::max(smem, (size_t)32 * (32 * f.RS + 1) * sizeof(float));
+    }
+    *total_tiles = tiles;
+    *smem_bytes = smem;
+}
+void wgrad_finish_launch(const WgradFinish* dev_rows, int n, int total_tiles, size_t smem_bytes, cudaStream_t s) {
+    if (n <= 0 || total_tiles <= 0) return;
+    DB_REQUIRE(smem_bytes <= 200 * 1024, "filter window too large for the wgrad finish kernel");
+    static size_t configured = 48 * 1024;
+    if (smem_bytes > configured) {
+        DB_CUDA(cudaFuncSetAttribute(wgrad_finish_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    wgrad_finish_multi_kernel<<<(unsigned)total_tiles, 256, smem_bytes, s>>>(dev_rows, n);
+    DB_LAUNCH_CHECK();
 }
 
 static void pack_filters(const float* w, __nv_bfloat16* out, int K, int C, int RS, int Kp, int Cp, int mode, cudaStream_t s) {
@@ -634,6 +676,7 @@ struct ConvTc {
     const void* pre_w = nullptr;               // filter already packed by the plan (fwd / dgrad)
     void* out_staged = nullptr;                // fwd / dgrad: write the result as [N][H][W][Cp] bf16 here instead of NCHW fp32
     void* stats_ws = nullptr;                  // fwd + out_staged: statistics workspace of the batch norm reading the result
+    float* acc_private = nullptr;              // wgrad: private accumulation scratch, finished later by the plan (deferred)
 };
 
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
@@ -704,7 +747,21 @@ ConvTc* conv_tc_create(const ConvGeom& g, int kind) {
     DB_REQUIRE(ok, "conv_tc_create: unsupported geometry");
     return c;
 }
-void conv_tc_destroy(ConvTc* c) { delete c; }
+void conv_tc_destroy(ConvTc* c) {
+    if (c && c->acc_private) cudaFree(c->acc_private);
+    delete c;
+}
+bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row) {
+    if (!c || c->kind != CONV_WGRAD) return false;
+    const ConvGeom& g = c->g;
+    const size_t bytes = (size_t)g.R * g.S * g.K * g.C * sizeof(float);
+    if (!c->acc_private) DB_CUDA(cudaMalloc((void**)&c->acc_private, std::max<size_t>(bytes, 16)));
+    row->scratch = c->acc_private;
+    row->dw = nullptr;
+    row->K = g.K; row->C = g.C; row->RS = g.R * g.S;
+    row->tiles_x = row->tile0 = 0;
+    return true;
+}
 
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int pos_mod(int a, int b) { return ((a % b) + b) % b; }
@@ -882,8 +939,8 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     const int RS = g.R * g.S, Kp = c->Kp, Cp = c->Cp;
     size_t yb = align_up((size_t)g.N * g.P * g.Q * Kp * 2, 1024), xb = align_up((size_t)g.N * g.H * g.W * Cp * 2, 1024);
     const size_t sb = align_up((size_t)RS * g.K * g.C * sizeof(float), 1024);   // [tap][C][K] accumulation scratch
-    uint8_t* st = stage_get(yb + xb + sb);
-    float* acc = (float*)(st + yb + xb);
+    uint8_t* st = stage_get(yb + xb + (c->acc_private ? 0 : sb));
+    float* acc = c->acc_private ? c->acc_private : (float*)(st + yb + xb);
     auto* dyh = (__nv_bfloat16*)st;
     auto* xh = (__nv_bfloat16*)(st + yb);
     if (c->pre[0]) dyh = (__nv_bfloat16*)c->pre[0];
@@ -966,7 +1023,7 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     a.cluster = 1;
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, tiles * a.splits, s);
-    {
+    if (!c->acc_private) {
         const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);
         DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the wgrad finish kernel");
         static size_t configured = 48 * 1024;

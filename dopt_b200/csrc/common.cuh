@@ -67,11 +67,15 @@ inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
 
 // A kernel object == dopt's CUDAKernel (cuda/source/dopt/cuda/package.d:68-79).
 // one filter to pack: KCRS fp32 -> bf16, mode 0 = forward layout [K][RS][Cp], mode 1 = feature-gradient layout [C][RS][Kp]
+// mode 2 = both layouts from one read of w (`out`/Kp/Cp describe the forward layout, `out2`/Kp2 the feature-gradient one);
+// mode -1 = row merged into another one (kept so that row indices stay stable), nothing to do
 struct FilterPack {
     const float* w;
     void* out;
     int K, C, RS, Kp, Cp, mode;
     int tiles_x, tile0;      // filled by the launcher: tiles along the first grid dimension, first tile of this row
+    void* out2;
+    int Kp2;
 };
 size_t filter_pack_bytes(const FilterPack& f);
 // packs rows[0..n) (device copy of the table in dev_rows); total_tiles and smem_bytes come from filter_pack_layout

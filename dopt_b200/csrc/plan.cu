@@ -1584,6 +1584,24 @@ static void build(Plan& p) {
                     n.kernel->set_packed_filter(buf);
                 }
             }
+        // a parameter packed for its convolution (forward layout) AND for the feature gradient of the same layer: one row that
+        // reads the filter once and writes both layouts
+        if (!getenv("DOPT_B200_NO_PACK_MERGE"))
+            for (size_t i = 0; i < p.packs.size(); ++i) {
+                FilterPack& f = p.packs[i];
+                if (f.mode != 0) continue;
+                for (size_t j = 0; j < p.packs.size(); ++j) {
+                    FilterPack& d = p.packs[j];
+                    if (d.mode != 1 || root_of(p, p.pack_users[j].second) != root_of(p, p.pack_users[i].second) || d.K != f.K || d.C != f.C || d.RS != f.RS ||
+                        f.Kp != f.K || d.Cp != d.C)
+                        continue;
+                    f.mode = 2;
+                    f.out2 = d.out;
+                    f.Kp2 = d.Kp;
+                    d.mode = -1;
+                    break;
+                }
+            }
         if (!p.packs.empty()) {
             filter_pack_layout(p.packs.data(), (int)p.packs.size(), &p.pack_tiles, &p.pack_smem);
             DB_CUDA(cudaMalloc(&p.packs_dev, p.packs.size() * sizeof(FilterPack)));

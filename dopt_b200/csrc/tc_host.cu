@@ -207,6 +207,58 @@ __device__ __forceinline__ void pack_filters_tile(const float* __restrict__ w, _
         }
     }
 }
+// Both layouts from ONE read of the filter (a parameter is packed for its convolution and for the feature gradient of the
+// same layer every step): tile 16 k x 64 c -- 37 KB of fp32 per CTA for a 3x3 filter, read as runs of 64*RS floats, written
+// as 128-byte rows of 64 channels (forward layout) and 32-byte rows of 16 output channels (feature-gradient layout).
+template <bool RS9>
+__device__ __forceinline__ void pack_filters_both_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ out_f,
+                                                       __nv_bfloat16* __restrict__ out_d, int K, int C, int RS_, int Cp, int Kp2,
+                                                       int bx, int by, float* pf_tile) {
+    const int RS = RS9 ? 9 : RS_;
+    constexpr int TK = 16, TCc = 64;
+    const int ld = TCc * RS + 1;
+    const int k0 = bx * TK, c0 = by * TCc;
+    const int run = min(TCc, C - c0) * RS;
+    const int row_len = TCc * RS;
+    const int total = TK * row_len;
+    // the tile has 4 * RS elements per thread; four loads in flight per trip
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * 256) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256;
+            const int kk = e / row_len, j = e - kk * row_len;
+            v[u] = (e < total && k0 + kk < K && j < run) ? w[((int64_t)(k0 + kk) * C + c0) * RS + j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256;
+            const int kk = e / row_len, j = e - kk * row_len;
+            if (e < total) pf_tile[kk * ld + j] = v[u];
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // forward layout: out_f[k][(tap)*Cp + c], one (k, tap) row of 64 channels per warp trip
+    for (int row = wid; row < TK * RS; row += 8) {
+        const int kk = row / RS, t = row - kk * RS;
+        const int k = k0 + kk, c = c0 + lane * 2;
+        if (k < K && c < Cp) {
+            const float* src = pf_tile + kk * ld + (RS - 1 - t);
+            *(__nv_bfloat162*)(out_f + ((int64_t)k * RS + t) * Cp + c) = __floats2bfloat162_rn(src[(lane * 2) * RS], src[(lane * 2 + 1) * RS]);
+        }
+    }
+    // feature-gradient layout: out_d[c][(tap)*Kp2 + k], rows (c, tap) of 16 output channels, two per thread
+    for (int item = threadIdx.x; item < TCc * RS * (TK / 2); item += 256) {
+        const int row = item / (TK / 2), kp = item - row * (TK / 2);
+        const int cc = row / RS, t = row - cc * RS;
+        const int c = c0 + cc, k = k0 + kp * 2;
+        if (c < C && k < Kp2) {
+            const float* src = pf_tile + cc * RS + (RS - 1 - t);
+            *(__nv_bfloat162*)(out_d + ((int64_t)c * RS + t) * Kp2 + k) = __floats2bfloat162_rn(src[(kp * 2) * ld], src[(kp * 2 + 1) * ld]);
+        }
+    }
+}
 template <int MODE>
 __global__ void __launch_bounds__(256) pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int K, int C, int RS, int Kp, int Cp) {
@@ -225,7 +277,10 @@ __global__ void __launch_bounds__(256) pack_filters_multi_kernel(const FilterPac
     const FilterPack r = rows[lo];
     const int t = (int)blockIdx.x - r.tile0;
     const int bx = t % r.tiles_x, by = t / r.tiles_x;
-    if (r.RS == 9) {
+    if (r.mode == 2) {
+        if (r.RS == 9) pack_filters_both_tile<true>(r.w, (__nv_bfloat16*)r.out, (__nv_bfloat16*)r.out2, r.K, r.C, 9, r.Cp, r.Kp2, bx, by, pf_tile);
+        else pack_filters_both_tile<false>(r.w, (__nv_bfloat16*)r.out, (__nv_bfloat16*)r.out2, r.K, r.C, r.RS, r.Cp, r.Kp2, bx, by, pf_tile);
+    } else if (r.RS == 9) {
         if (r.mode == 0) pack_filters_tile<0, true>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, 9, r.Kp, r.Cp, bx, by, pf_tile);
         else pack_filters_tile<1, true>(r.w, (__nv_bfloat16*)r.out, r.K, r.C, 9, r.Kp, r.Cp, bx, by, pf_tile);
     } else if (r.mode == 0) {
@@ -339,9 +394,11 @@ void filter_pack_layout(FilterPack* rows, int n, int* total_tiles, size_t* smem_
     size_t smem = 0;
     for (int i = 0; i < n; ++i) {
         FilterPack& f = rows[i];
-        const int TK = f.mode == 0 ? 4 : 16, TCc = f.mode == 0 ? 64 : 16;
-        f.tiles_x = (int)ceil_div(f.Kp, TK);
         f.tile0 = tiles;
+        f.tiles_x = 1;
+        if (f.mode < 0) continue;   // merged into another row
+        const int TK = f.mode == 0 ? 4 : 16, TCc = f.mode == 1 ? 16 : 64;
+        f.tiles_x = (int)ceil_div(f.mode == 2 ? std::max(f.Kp, f.Kp2) : f.Kp, TK);
         tiles += f.tiles_x * (int)ceil_div(f.Cp, TCc);
         smem = std::max(smem, (size_t)TK * (TCc * f.RS + 1) * sizeof(float));
     }
@@ -693,6 +750,8 @@ bool conv_tc_filter_pack(const ConvTc* c, int input, FilterPack* d) {
     d->Kp = c->kind == CONV_FWD ? g.K : c->Kp;
     d->Cp = c->kind == CONV_FWD ? c->Cp : g.C;
     d->tiles_x = d->tile0 = 0;
+    d->out2 = nullptr;
+    d->Kp2 = 0;
     return true;
 }
 void conv_tc_set_packed_filter(ConvTc* c, const void* packed) {

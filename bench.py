@@ -32,6 +32,11 @@ LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 RANK = int(os.environ.get("RANK", "0"))
 if WORLD > 1:
+    # the gradient all-reduces get a fixed, small number of CTAs and the tensor-core kernels leave exactly those SMs free while
+    # a bucket is in flight (dopt_b200/csrc/comm.cu, tc_host.cu); NCCL reads the variable when the process creates its first
+    # communicator -- torch.distributed's, below -- so it has to be in the environment now
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "4"))
+    os.environ.setdefault("NCCL_MIN_NCHANNELS", os.environ["NCCL_MAX_NCHANNELS"])
     # one process per GPU, each seeing exactly its own device as ordinal 0 -- the reference hard-codes ordinal 0
     # (cuda/source/dopt/cuda/package.d:44), so this is also how the D host would be launched
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")

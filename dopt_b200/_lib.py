@@ -66,7 +66,7 @@ SYMBOLS = [
     "dopt_b200_plan_create", "dopt_b200_plan_add_node", "dopt_b200_plan_set_outputs", "dopt_b200_plan_finalize",
     "dopt_b200_plan_execute", "dopt_b200_plan_stats", "dopt_b200_plan_profile", "dopt_b200_plan_destroy",
     "dopt_b200_comm_unique_id", "dopt_b200_comm_init", "dopt_b200_comm_world_size", "dopt_b200_comm_rank",
-    "dopt_b200_allreduce", "dopt_b200_comm_destroy",
+    "dopt_b200_allreduce", "dopt_b200_comm_check", "dopt_b200_comm_destroy",
 ]
 
 

@@ -7,6 +7,8 @@
 // libnccl (PyTorch bundles one) shares it instead of loading a second copy.
 #include "common.cuh"
 #include <dlfcn.h>
+#include <algorithm>
+#include <cstdlib>
 
 namespace db {
 namespace {
@@ -22,11 +24,17 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static Nccl g_nccl;
 static ncclComm_t g_comm = nullptr;
 static int g_rank = 0, g_world = 1;
+// CTAs (channels) the all-reduce kernels may use = SMs the tensor-core kernels leave free while a bucket is in flight.
+// NCCL reads NCCL_MAX_NCHANNELS once per process, when its first communicator is created: a host that creates NCCL
+// communicators of its own first (bench.py: torch.distributed) must export the variable before that.
+static int g_channels = 0;
 
 static void load_nccl() {
     if (g_nccl.h) return;
@@ -43,11 +51,45 @@ static void load_nccl() {
     SYM(CommInitRank, "ncclCommInitRank")
     SYM(AllReduce, "ncclAllReduce")
     SYM(CommDestroy, "ncclCommDestroy")
+    SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+    SYM(CommAbort, "ncclCommAbort")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
 }
+static void pick_channels() {
+    int k = 4;
+    if (const char* e = getenv("DOPT_B200_COMM_CHANNELS")) k = atoi(e);
+    if (k <= 0) {   // 0: NCCL's own choice, no SM reservation
+        g_channels = 0;
+        return;
+    }
+    if (const char* e = getenv("NCCL_MAX_NCHANNELS")) {
+        g_channels = std::max(1, std::min(atoi(e), 32));
+        return;
+    }
+    char buf[16];
+    snprintf(buf, sizeof(buf), "%d", k);
+    setenv("NCCL_MAX_NCHANNELS", buf, 0);
+    setenv("NCCL_MIN_NCHANNELS", buf, 0);
+    g_channels = k;
+}
 static void nccl_check(ncclResult_t r, const char* what) {
     if (r != 0) throw Error(std::string("NCCL error in ") + what + ": " + g_nccl.GetErrorString(r));
+}
+
+// Collectives are enqueued asynchronously (inside a CUDA graph, even): a failure of a peer or of the fabric only shows up as
+// the communicator's asynchronous error state.  It is polled before every enqueue and through dopt_b200_comm_check(); a
+// communicator in error is aborted so that no rank keeps waiting in a kernel that can never finish.
+static void poll_async_error(const char* where) {
+    if (!g_comm) return;
+    ncclResult_t async = 0;
+    nccl_check(g_nccl.CommGetAsyncError(g_comm, &async), "ncclCommGetAsyncError");
+    if (async != 0 && async != 7 /* ncclInProgress */) {
+        std::string msg = std::string("NCCL asynchronous error (") + where + "): " + g_nccl.GetErrorString(async);
+        g_nccl.CommAbort(g_comm);
+        g_comm = nullptr;
+        throw Error(msg);
+    }
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, int64_t n, float s) {
@@ -57,13 +99,18 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, int64
 }  // namespace
 
 int comm_world() { return g_world; }
+int comm_reserved_sms() { return g_world > 1 ? g_channels : 0; }
 
 // mean over ranks, in place, one NCCL call (ncclAvg); used by the plan's gradient buckets
 void allreduce_mean(float* buf, int64_t n, cudaStream_t s) {
     if (n <= 0 || g_world <= 1) return;
     DB_REQUIRE(g_comm != nullptr, "allreduce: communicator not initialised (dopt_b200_comm_init)");
+    poll_async_error("before a gradient-bucket all-reduce");
     nccl_check(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclAvg, g_comm, s), "ncclAllReduce");
     count_launch();
+}
+void comm_check() {
+    if (g_world > 1) poll_async_error("dopt_b200_comm_check");
 }
 
 namespace {
@@ -79,6 +126,7 @@ struct AllreduceKernel : Kernel {
 };
 }  // namespace
 void allreduce(float* buf, int64_t n, float scale, cudaStream_t s);
+void comm_check();
 void AllreduceKernel::run(const void* const* in, int n_in, void* out, cudaStream_t s) {
     DB_REQUIRE(n_in == 1, "allreduce: one input");
     if (n == 0) return;
@@ -96,6 +144,7 @@ void allreduce(float* buf, int64_t n, float scale, cudaStream_t s) {
     if (n <= 0) return;
     if (g_world > 1) {
         DB_REQUIRE(g_comm != nullptr, "allreduce: communicator not initialised (dopt_b200_comm_init)");
+        poll_async_error("before an all-reduce");
         nccl_check(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, g_comm, s), "ncclAllReduce");
         count_launch();
     }
@@ -128,6 +177,7 @@ int dopt_b200_comm_init(int rank, int world_size, const void* id128) {
         if (world_size == 1) return 0;
         DB_REQUIRE(id128, "null id");
         db::require_device();
+        db::pick_channels();
         db::load_nccl();
         db::ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
@@ -144,6 +194,15 @@ int dopt_b200_allreduce(float* buf, int64_t n, float scale, void* stream) {
     try {
         db::require_device();
         db::allreduce(buf, n, scale, (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        db::set_last_error(e.what());
+        return 1;
+    }
+    return 0;
+}
+int dopt_b200_comm_check(void) {
+    try {
+        db::comm_check();
     } catch (const std::exception& e) {
         db::set_last_error(e.what());
         return 1;

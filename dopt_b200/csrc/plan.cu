@@ -38,6 +38,8 @@ void tc_prof_enable(bool on);
 void tc_prof_read(double* us, int64_t* launches);
 void allreduce_mean(float* buf, int64_t n, cudaStream_t s);
 int comm_world();
+int comm_reserved_sms();
+void tc_set_reserved_sms(int k);
 
 namespace {
 
@@ -1818,6 +1820,7 @@ static void run_items(Plan& p, cudaStream_t s) {
             DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
             DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
             comm_pending = false;
+            tc_set_reserved_sms(0);
         }
         if (it.kind == ITEM_BUCKET) {
             // one all-reduce for the whole bucket, on the communication stream so that it overlaps the rest of backward
@@ -1831,10 +1834,12 @@ static void run_items(Plan& p, cudaStream_t s) {
             DB_CUDA(cudaStreamWaitEvent(p.comm_stream, p.comm_fork, 0));
             allreduce_mean((float*)b.arena, b.bytes / 4, p.comm_stream);
             comm_pending = true;
+            tc_set_reserved_sms(comm_reserved_sms());   // the tensor-core launches that follow leave SMs to the collective
             if (p.profiling) {   // serialise so that the profile attributes the time
                 DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
                 DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
                 comm_pending = false;
+                tc_set_reserved_sms(0);
             }
             label = "allreduceBucket";
         } else if (it.kind == ITEM_MSUM) {
@@ -1900,6 +1905,7 @@ static void run_items(Plan& p, cudaStream_t s) {
             p.prof_cnt[labels[i]] += 1;
         }
     }
+    tc_set_reserved_sms(0);
     if (comm_pending) {   // nothing may be left running on the side stream when the step (or the capture) ends
         DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
         DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));

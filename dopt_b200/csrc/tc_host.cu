@@ -462,6 +462,14 @@ void tc_prof_read(double* us, int64_t* launches) {
     *launches = (int64_t)g_tc_ev_used;
 }
 
+// SMs left to a collective that runs beside the tensor-core kernels (plan.cu sets it while a gradient-bucket all-reduce may be
+// in flight).  The persistent grid is statically scheduled -- every CTA owns a fixed share of the tiles -- so one CTA that
+// shares its SM with an NCCL channel stretches the whole launch (8 % per convolution, profiles/r01c_conv_bisect.md section 7).
+// With k SMs reserved the grid shrinks to 148 - k CTAs, each asking for the full 227 KB of shared memory so that it cannot
+// be placed next to an NCCL CTA: the two kernels then run on disjoint SMs.
+static int g_reserved_sms = 0;
+void tc_set_reserved_sms(int k) { g_reserved_sms = k < 0 ? 0 : k; }
+
 template <int MODE>
 static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, int n_ctas, cudaStream_t s) {
     // n_ctas on entry = number of work items (m_tiles * n_tiles * splits)
@@ -484,6 +492,7 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         configured = 227 * 1024;
     }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
+    if (g_reserved_sms > 0 && a.nacc == 2) L.total = 227 * 1024;   // one CTA per SM: keep the SM to itself
     if (g_tc_prof) {
         if (g_tc_ev_used == g_tc_ev.size()) {
             cudaEvent_t e0, e1;
@@ -496,7 +505,8 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     // persistent grid: one CTA (pair) per SM, each looping over its share of the n_ctas work items
     {
         const int cs = a.pair ? 2 : 1;
-        int clusters = std::min(n_ctas / cs, (a.nacc == 2 ? 1 : 2) * sm_count() / cs);
+        const int sms = std::max(2, sm_count() - std::min(g_reserved_sms, sm_count() / 2));
+        int clusters = std::min(n_ctas / cs, (a.nacc == 2 ? 1 : 2) * (sms / cs * cs) / cs);
         if (clusters < 1) clusters = 1;
         n_ctas = clusters * cs;
     }

@@ -292,6 +292,9 @@ void B200Plan::executeRaw(const std::vector<Operation>& argOps, const std::vecto
     }
     abiEnforce(dopt_b200_plan_execute((dopt_b200_plan_t)mPlan, ids.data(), ptrs.data(), onHost.data(), (int)ids.size(),
                                       rets.data(), (int)rets.size(), g_stream));
+    // data-parallel: the collectives inside the (replayed) step are asynchronous; surface a failed peer / link as an exception
+    // at the next step instead of a hang (one host call, no synchronisation)
+    if (dopt_b200_comm_world_size() > 1) abiEnforce(dopt_b200_comm_check());
 }
 
 void B200Plan::executeImpl(const std::map<Operation, Buffer>& args, std::vector<Buffer>& rets) {

@@ -196,6 +196,10 @@ int dopt_b200_comm_world_size(void);
 int dopt_b200_comm_rank(void);
 /* in-place sum over ranks of a float buffer, then multiply by `scale` (1/world for a mean) */
 int dopt_b200_allreduce(float* buf, int64_t n, float scale, void* stream);
+/* polls the communicator's asynchronous error state (ncclCommGetAsyncError): collectives are enqueued without waiting, so a
+ * failed peer or link only shows up here.  Non-zero = the communicator was aborted; dopt_b200_last_error() says why.
+ * (The same poll runs before every all-reduce the library enqueues.)  Call it after synchronising a step. */
+int dopt_b200_comm_check(void);
 int dopt_b200_comm_destroy(void);
 
 #ifdef __cplusplus

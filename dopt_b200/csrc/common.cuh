@@ -151,6 +151,9 @@ struct Kernel {
     // scratches of many filter gradients into KCRS with ONE multi-tensor launch (28 latency-sized launches per WRN step
     // otherwise).  deferred_finish fills everything of the row but `dw`.
     virtual bool deferred_finish(struct WgradFinish* /*row*/) { return false; }
+    // true when run() touches no workspace shared with other ops (only its operands, its result and private scratch): the
+    // plan may then issue it on a side stream, concurrently with the ops that follow it in the order
+    virtual bool side_stream_safe() const { return false; }
     virtual void* stats_workspace(int /*mode*/) { return nullptr; }
     virtual int can_produce_stats() const { return 0; }   // 0 = no, else the mode it produces
     virtual void set_stats_workspace(void* /*bn_workspace*/, int /*channels*/) {}

@@ -166,6 +166,9 @@ struct dopt_b200_plan_s {
     std::vector<FinishGroup> finishes;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
+    // side stream: filter gradients whose only reader is a deferred finish launch run here, beside the feature-gradient chain
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
     int64_t device_bytes = 0;
     int64_t launches_per_exec = 0;
     std::unordered_map<int, void*> var_stage;   // device staging for variables passed as host pointers
@@ -203,6 +206,9 @@ struct dopt_b200_plan_s {
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
         if (comm_join) cudaEventDestroy(comm_join);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (side_fork) cudaEventDestroy(side_fork);
+        if (side_join) cudaEventDestroy(side_join);
         for (auto& kv : var_stage) cudaFree(kv.second);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -349,7 +355,7 @@ static void lower_views(Plan& p) {
         Node& c = N[i];
         if (c.alias_of >= 0 || c.op.output.dtype != DOPT_B200_FLOAT32) continue;
         int op = pointwise_op_id(c.type.c_str());
-        if (op < 0) continue;
+        if (!pointwise_fusable(op)) continue;   // (sin ... atanh run as plain kernel launches)
         c.pw_op = op;
         c.pw_unary = pointwise_is_unary(op);
         c.eff_in[0] = c.deps[0];
@@ -1800,6 +1806,19 @@ static void bind_bn_stats(Plan& p, void* const* rets) {
 static void run_items(Plan& p, cudaStream_t s) {
     auto& N = p.nodes;
     bool comm_pending = false;
+    // Side stream.  A tensor-core filter gradient with a deferred finish reads two staged activations nothing overwrites and
+    // accumulates into a private scratch only the finish launch reads, and nothing on the feature-gradient chain
+    // (batchNormGrad -> convolutionFeaturesGrad -> ...) waits for it.  Issued on a second stream (a parallel branch of the
+    // captured graph) it fills the SMs while the memory-bound batch-norm passes of the chain run and while the chain sits in
+    // the gaps between dependent launches.  The chain joins before the first finish launch.  Profiling serialises everything.
+    static const bool side_on = !getenv("DOPT_B200_NO_SIDE_STREAM");
+    bool side_pending = false;
+    auto side_join_now = [&]() {
+        if (!side_pending) return;
+        DB_CUDA(cudaEventRecord(p.side_join, p.side_stream));
+        DB_CUDA(cudaStreamWaitEvent(s, p.side_join, 0));
+        side_pending = false;
+    };
     // profiling: an event between every two items, read back after the whole step -- no host synchronisation inside the
     // step, so small kernels are charged their device time and the launch gap, not a host round trip
     std::vector<const char*> labels;
@@ -1855,6 +1874,7 @@ static void run_items(Plan& p, cudaStream_t s) {
             label = "stageNHWC";
         } else if (it.kind == ITEM_WFINISH) {
             auto& f = p.finishes[it.id];
+            side_join_now();
             wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, s);
             label = "filtersGradFinish";
         } else if (it.kind == ITEM_UNSTAGE) {
@@ -1882,7 +1902,22 @@ static void run_items(Plan& p, cudaStream_t s) {
                 ab.staged = n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr;
                 n.kernel->set_absorbed(ab);
             }
-            n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
+            if (side_on && !p.profiling && n.finish_group >= 0 && n.kernel->side_stream_safe()) {
+                if (!p.side_stream) {
+                    // lowest priority: when both streams have CTAs waiting for an SM, the chain's go first
+                    int prio_lo = 0, prio_hi = 0;
+                    DB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                    DB_CUDA(cudaStreamCreateWithPriority(&p.side_stream, cudaStreamNonBlocking, prio_lo));
+                    DB_CUDA(cudaEventCreateWithFlags(&p.side_fork, cudaEventDisableTiming));
+                    DB_CUDA(cudaEventCreateWithFlags(&p.side_join, cudaEventDisableTiming));
+                }
+                DB_CUDA(cudaEventRecord(p.side_fork, s));
+                DB_CUDA(cudaStreamWaitEvent(p.side_stream, p.side_fork, 0));
+                n.kernel->run(in, (int)n.deps.size(), n.ptr, p.side_stream);
+                side_pending = true;
+            } else {
+                n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
+            }
             label = n.type.c_str();
         } else if (it.kind == ITEM_PW_SCALAR) {
             Node& n = N[it.id];
@@ -1906,6 +1941,7 @@ static void run_items(Plan& p, cudaStream_t s) {
         }
     }
     tc_set_reserved_sms(0);
+    side_join_now();
     if (comm_pending) {   // nothing may be left running on the side stream when the step (or the capture) ends
         DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
         DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
@@ -2040,7 +2076,12 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
         cudaGraphExecDestroy(p.graph_exec);
         p.graph_exec = nullptr;
     }
-    if (!p.cap_stream) DB_CUDA(cudaStreamCreateWithFlags(&p.cap_stream, cudaStreamNonBlocking));
+    if (!p.cap_stream) {
+        // highest priority (captured into the kernel nodes): the side stream's filter gradients yield to the chain
+        int prio_lo = 0, prio_hi = 0;
+        DB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DB_CUDA(cudaStreamCreateWithPriority(&p.cap_stream, cudaStreamNonBlocking, prio_hi));
+    }
     DB_CUDA(cudaStreamSynchronize(s));
     cudaGraph_t graph = nullptr;
     DB_CUDA(cudaStreamBeginCapture(p.cap_stream, cudaStreamCaptureModeThreadLocal));

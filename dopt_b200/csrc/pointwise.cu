@@ -1,4 +1,5 @@
-// pointwise.cu -- the 19 elementwise ops of dopt.cuda.math (cuda/source/dopt/cuda/math.d:79-207).
+// pointwise.cu -- the 19 elementwise ops of dopt.cuda.math (cuda/source/dopt/cuda/math.d:79-207) and the 12 unary functions
+// (sin ... atanh) the reference evaluates on the host for the CUDA backend (cuda/source/dopt/cuda/package.d:81-119).
 //
 // Reference: one NVRTC template `out[i] = a[i] OP b[i]` / `out[i] = f(a[i])`, T in {float,int}, 512 threads, scalar 4-byte
 // accesses, cuCtxSynchronize after every launch (math.d:129-170,199-201; nvrtc.d:111).
@@ -113,6 +114,8 @@ static void launch_pw_op(int op, int bmode, const void* a, const void* b, void* 
 #undef C
 #define C(OP) case dbk::OP: launch_pw<dbk::OP, T, dbk::B_SCALAR_B>(a, a, o, n, s); break;   /* unary: b unused */
         C(OP_NEG) C(OP_ABS) C(OP_SGN) C(OP_EXP) C(OP_LOG) C(OP_SQRT)
+        C(OP_SIN) C(OP_COS) C(OP_TAN) C(OP_ASIN) C(OP_ACOS) C(OP_ATAN) C(OP_SINH) C(OP_COSH) C(OP_TANH) C(OP_ASINH) C(OP_ACOSH)
+        C(OP_ATANH)
 #undef C
         default: throw Error("pointwise: unknown op");
     }
@@ -125,7 +128,8 @@ void pointwise_launch(int op, int dtype, int bmode, const void* a, const void* b
 }
 
 static const char* kNames[] = {"add", "sub", "mul", "div", "lt",  "lte", "gt",  "gte", "eq",  "neq",
-                               "max", "min", "pow", "neg", "abs", "sgn", "exp", "log", "sqrt"};
+                               "max", "min", "pow", "neg", "abs", "sgn", "exp", "log", "sqrt",
+                               "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh"};
 
 int pointwise_op_id(const char* name) {
     for (int i = 0; i < dbk::OP_COUNT; ++i)

@@ -6,8 +6,14 @@ namespace dbk {
 
 enum PwOp {
     OP_ADD = 0, OP_SUB, OP_MUL, OP_DIV, OP_LT, OP_LTE, OP_GT, OP_GTE, OP_EQ, OP_NEQ, OP_MAX, OP_MIN, OP_POW,
-    OP_NEG, OP_ABS, OP_SGN, OP_EXP, OP_LOG, OP_SQRT, OP_COUNT
+    OP_NEG, OP_ABS, OP_SGN, OP_EXP, OP_LOG, OP_SQRT,
+    // unary functions the reference only has CPU kernels for (cpu/source/dopt/cpu/math.d:323-324: `op(cast(float)x)`) and
+    // reaches from the CUDA backend through the CUDACPUKernel round trip (cuda/source/dopt/cuda/package.d:81-119)
+    OP_SIN, OP_COS, OP_TAN, OP_ASIN, OP_ACOS, OP_ATAN, OP_SINH, OP_COSH, OP_TANH, OP_ASINH, OP_ACOSH, OP_ATANH,
+    OP_COUNT
 };
+// ops below this id can be instructions of a fused pointwise region (fused.cu); the transcendental tail runs as plain launches
+static constexpr int OP_FUSABLE_END = OP_SIN;
 enum PwBroadcast { B_TENSOR = 0, B_SCALAR_B = 1, B_SCALAR_A = 2 };
 
 template <typename T> struct Vec4;
@@ -55,6 +61,18 @@ template <int OP> struct Apply<OP, float> {
             case OP_EXP: return expf(a);
             case OP_LOG: return logf(a);
             case OP_SQRT: return __fsqrt_rn(a);
+            case OP_SIN: return sinf(a);
+            case OP_COS: return cosf(a);
+            case OP_TAN: return tanf(a);
+            case OP_ASIN: return asinf(a);
+            case OP_ACOS: return acosf(a);
+            case OP_ATAN: return atanf(a);
+            case OP_SINH: return sinhf(a);
+            case OP_COSH: return coshf(a);
+            case OP_TANH: return tanhf(a);
+            case OP_ASINH: return asinhf(a);
+            case OP_ACOSH: return acoshf(a);
+            case OP_ATANH: return atanhf(a);
         }
         return 0.0f;
     }
@@ -92,6 +110,19 @@ template <int OP> struct Apply<OP, int> {
             case OP_EXP: return (int)exp((double)a);
             case OP_LOG: return (int)log((double)a);
             case OP_SQRT: return (int)sqrt((double)a);
+            // cast(int)(f(cast(float)a)), cpu/source/dopt/cpu/math.d:416-423
+            case OP_SIN: return (int)sinf((float)a);
+            case OP_COS: return (int)cosf((float)a);
+            case OP_TAN: return (int)tanf((float)a);
+            case OP_ASIN: return (int)asinf((float)a);
+            case OP_ACOS: return (int)acosf((float)a);
+            case OP_ATAN: return (int)atanf((float)a);
+            case OP_SINH: return (int)sinhf((float)a);
+            case OP_COSH: return (int)coshf((float)a);
+            case OP_TANH: return (int)tanhf((float)a);
+            case OP_ASINH: return (int)asinhf((float)a);
+            case OP_ACOSH: return (int)acoshf((float)a);
+            case OP_ATANH: return (int)atanhf((float)a);
         }
         return 0;
     }
@@ -105,4 +136,5 @@ namespace db {
 void pointwise_launch(int op, int dtype, int bmode, const void* a, const void* b, void* o, int64_t n, cudaStream_t s);
 int pointwise_op_id(const char* name);
 bool pointwise_is_unary(int op);
+inline bool pointwise_fusable(int op) { return op >= 0 && op < dbk::OP_FUSABLE_END; }
 }  // namespace db

@@ -32,5 +32,8 @@ void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16);
 void conv_tc_set_stats_workspace(ConvTc* c, void* bn_workspace);
 // wgrad: accumulate into a private scratch (allocated here) and skip the per-op finish kernel; the caller finishes `row` later
 bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row);
+// wgrad that reads only plan-staged operands and writes only its private scratch: it shares no workspace with any other op, so
+// the plan may run it on a second stream beside the feature-gradient chain
+bool conv_tc_side_stream_safe(const ConvTc* c);
 
 }  // namespace db

@@ -832,6 +832,10 @@ bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row) {
     return true;
 }
 
+bool conv_tc_side_stream_safe(const ConvTc* c) {
+    return c && c->kind == CONV_WGRAD && c->pre[0] && c->pre[1] && c->acc_private;
+}
+
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int pos_mod(int a, int b) { return ((a % b) + b) % b; }
 
@@ -1008,7 +1012,10 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     const int RS = g.R * g.S, Kp = c->Kp, Cp = c->Cp;
     size_t yb = align_up((size_t)g.N * g.P * g.Q * Kp * 2, 1024), xb = align_up((size_t)g.N * g.H * g.W * Cp * 2, 1024);
     const size_t sb = align_up((size_t)RS * g.K * g.C * sizeof(float), 1024);   // [tap][C][K] accumulation scratch
-    uint8_t* st = stage_get(yb + xb + (c->acc_private ? 0 : sb));
+    // with both operands staged by the plan and a private accumulator the shared arena is not touched at all -- which is what
+    // lets the plan run this op on its side stream next to other convolutions (conv_tc_side_stream_safe)
+    const bool own = c->pre[0] && c->pre[1] && c->acc_private;
+    uint8_t* st = own ? nullptr : stage_get(yb + xb + (c->acc_private ? 0 : sb));
     float* acc = c->acc_private ? c->acc_private : (float*)(st + yb + xb);
     auto* dyh = (__nv_bfloat16*)st;
     auto* xh = (__nv_bfloat16*)(st + yb);

@@ -333,6 +333,8 @@ DOPT_DEF_BIN(add) DOPT_DEF_BIN(sub) DOPT_DEF_BIN(mul) DOPT_DEF_BIN(div)
 DOPT_DEF_BIN(lt) DOPT_DEF_BIN(lte) DOPT_DEF_BIN(gt) DOPT_DEF_BIN(gte) DOPT_DEF_BIN(eq) DOPT_DEF_BIN(neq)
 DOPT_DEF_BIN(max) DOPT_DEF_BIN(min) DOPT_DEF_BIN(pow)
 DOPT_DEF_UN(neg) DOPT_DEF_UN(abs) DOPT_DEF_UN(sgn) DOPT_DEF_UN(exp) DOPT_DEF_UN(log) DOPT_DEF_UN(sqrt)
+DOPT_DEF_UN(sin) DOPT_DEF_UN(cos) DOPT_DEF_UN(tan) DOPT_DEF_UN(asin) DOPT_DEF_UN(acos) DOPT_DEF_UN(atan)
+DOPT_DEF_UN(sinh) DOPT_DEF_UN(cosh) DOPT_DEF_UN(tanh) DOPT_DEF_UN(asinh) DOPT_DEF_UN(acosh) DOPT_DEF_UN(atanh)
 #undef DOPT_DEF_BIN
 #undef DOPT_DEF_UN
 

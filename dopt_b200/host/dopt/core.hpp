@@ -158,6 +158,8 @@ DOPT_DECL_BIN(add) DOPT_DECL_BIN(sub) DOPT_DECL_BIN(mul) DOPT_DECL_BIN(div)
 DOPT_DECL_BIN(lt) DOPT_DECL_BIN(lte) DOPT_DECL_BIN(gt) DOPT_DECL_BIN(gte) DOPT_DECL_BIN(eq) DOPT_DECL_BIN(neq)
 DOPT_DECL_BIN(max) DOPT_DECL_BIN(min) DOPT_DECL_BIN(pow)
 DOPT_DECL_UN(neg) DOPT_DECL_UN(abs) DOPT_DECL_UN(sgn) DOPT_DECL_UN(exp) DOPT_DECL_UN(log) DOPT_DECL_UN(sqrt)
+DOPT_DECL_UN(sin) DOPT_DECL_UN(cos) DOPT_DECL_UN(tan) DOPT_DECL_UN(asin) DOPT_DECL_UN(acos) DOPT_DECL_UN(atan)
+DOPT_DECL_UN(sinh) DOPT_DECL_UN(cosh) DOPT_DECL_UN(tanh) DOPT_DECL_UN(asinh) DOPT_DECL_UN(acosh) DOPT_DECL_UN(atanh)
 #undef DOPT_DECL_BIN
 #undef DOPT_DECL_UN
 Operation matmul(Operation lhs, Operation rhs);

@@ -97,6 +97,25 @@ POINTWISE_UNARY = {
 }
 
 
+def _via_float32(fn):
+    """`cast(T)(op(cast(float)x))`, cpu/source/dopt/cpu/math.d:416-423: std.math evaluates the float argument in extended
+    precision, so the result is the correctly rounded function of the float32 value (float64 here), then cast to T --
+    truncation toward zero for int32."""
+    def f(a):
+        with np.errstate(all="ignore"):
+            r = fn(a.astype(np.float32).astype(np.float64))
+            if a.dtype == np.int32:
+                return np.trunc(np.nan_to_num(r.astype(np.float32))).astype(np.int32)
+            return r.astype(a.dtype)
+    return f
+
+
+for _name, _fn in (("sin", np.sin), ("cos", np.cos), ("tan", np.tan), ("asin", np.arcsin), ("acos", np.arccos),
+                   ("atan", np.arctan), ("sinh", np.sinh), ("cosh", np.cosh), ("tanh", np.tanh), ("asinh", np.arcsinh),
+                   ("acosh", np.arccosh), ("atanh", np.arctanh)):
+    POINTWISE_UNARY[_name] = _via_float32(_fn)
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # matmul / reductions -- cpu/source/dopt/cpu/math.d:70-310
 # --------------------------------------------------------------------------------------------------------------------

@@ -14,12 +14,18 @@ import numpy as np
 from . import dopt_ref as R
 
 
-def evaluate(nodes, outputs_ids, values, args=None):
-    """nodes: dopt_b200.host.export() result; values: {node id: ndarray} for variables / constants; args override."""
+def evaluate(nodes, outputs_ids, values, args=None, overrides=None):
+    """nodes: dopt_b200.host.export() result; values: {node id: ndarray} for variables / constants; args override.
+    overrides: {node id: ndarray} fixes the value of any other node -- used for `uniform` nodes (the reference draws them
+    unseeded, cuda/source/dopt/cuda/random.d:56-83, so a comparison has to share the draw)."""
     env = {}
     args = args or {}
+    overrides = overrides or {}
     for n in nodes:
         t = n["type"]
+        if n["id"] in overrides:
+            env[n["id"]] = np.asarray(overrides[n["id"]], dtype=n["dtype"]).reshape(n["shape"])
+            continue
         if t in ("variable", "constant"):
             v = args.get(n["id"], values.get(n["id"]))
             if v is None:
@@ -60,9 +66,10 @@ class UpdaterOracle(object):
         self.out_ids = [o.serial for o in self.plan_ops]
         self.dest_ids = [d.serial if d is not None else None for d in self.dest_ops]
 
-    def step(self, args):
+    def step(self, args, overrides=None):
         a = dict((k.serial, v) for k, v in args.items())
-        outs = evaluate(self.nodes, self.out_ids, self.values, a)
+        o = dict((k.serial, v) for k, v in (overrides or {}).items())
+        outs = evaluate(self.nodes, self.out_ids, self.values, a, o)
         # all reads happen before any write-back, like the D2D copies after the last node (package.d:419-422)
         for val, dest in zip(outs, self.dest_ids):
             if dest is not None:

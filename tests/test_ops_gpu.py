@@ -87,6 +87,25 @@ def test_pointwise_unary_transcendental(op):
     np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7)
 
 
+# the 12 unary functions the reference's CUDA backend evaluates on the host (cuda/source/dopt/cuda/package.d:81-119,
+# cpu/source/dopt/cpu/math.d:323-324): CUDA's single-precision functions are within 2 ulp of the correctly rounded value
+@pytest.mark.parametrize("op", ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh"])
+def test_pointwise_unary_trigonometric(op):
+    rng = np.random.RandomState(9)
+    a = (rng.rand(100003).astype(F) * 2 - 1) * F(0.98)          # (-0.98, 0.98): inside every domain but acosh's
+    if op == "acosh":
+        a = np.abs(a) * 5 + F(1.01)
+    elif op in ("sin", "cos", "tan", "atan", "sinh", "cosh", "tanh", "asinh"):
+        a = a * F(1.5)                                          # tan stays away from its poles
+    got, ref = run(op, [a])
+    np.testing.assert_allclose(got, ref, rtol=4e-6, atol=2e-7)
+    ai = np.arange(-3, 4, dtype=np.int32) if op != "acosh" else np.arange(1, 8, dtype=np.int32)
+    if op in ("asin", "acos", "atanh"):
+        ai = np.array([0, 0, 0], np.int32)
+    got, ref = run(op, [ai])
+    np.testing.assert_array_equal(got, ref)
+
+
 def test_pointwise_pow_float():
     rng = np.random.RandomState(8)
     a = rng.rand(5000).astype(F) * 3 + 0.1

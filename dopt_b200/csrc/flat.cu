@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(256) flat_bn_stats_kernel(const uint4* __restr
                                                             const float* __restrict__ fcoef) {
     __shared__ float red[16][256];
     const int t = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float* sums = flat_stats_begin(ws, G * 8);
     const int cg_ = t % G;
     float piv[8], fa[8], fb[8];
@@ -183,6 +185,8 @@ __global__ void __launch_bounds__(256) flat_bn_apply_kernel(const uint4* __restr
     const int cg_ = t % G;
     const int Cp = G * 8;
     const float invM = 1.0f / (float)P;
+    pdl_trigger();
+    pdl_wait();
     // All loads of the prologue are issued back to back (one L2 round trip instead of three): the epoch, BOTH sum buffers
     // (the current one is selected afterwards), and further down the per-channel parameters.  Thread f < 2*Cp/4 owns float4
     // column f of the sums and adds its kFlatCopies copies in a fixed order.
@@ -258,6 +262,8 @@ __global__ void __launch_bounds__(256) flat_bn_apply_kernel(const uint4* __restr
         }
     }
     const int64_t trip = (int64_t)R * G, total = P * G;
+    // (L2 residency hints -- evict_last in the statistics pass, evict_first here -- and walking the tensor from its end were
+    // measured: no net gain, profiles/r02_summary.md)
     for (int64_t v0 = (int64_t)blockIdx.x * kFlatU * trip; v0 < total; v0 += (int64_t)gridDim.x * kFlatU * trip) {
         uint4 xv[kFlatU], qv[kFlatU], ev[kFlatU];
 #pragma unroll
@@ -299,6 +305,8 @@ __global__ void __launch_bounds__(256) flat_bn_apply_kernel(const uint4* __restr
 
 __global__ void __launch_bounds__(256) flat_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                        uint4* __restrict__ out, int64_t nvec) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + (kFlatU - 1) * stride < nvec; i += kFlatU * stride) {
@@ -335,6 +343,8 @@ __global__ void __launch_bounds__(256) flat_add_stats_kernel(const uint4* __rest
                                                              const __grid_constant__ FlatWs ws) {
     __shared__ float red[16][256];
     const int t = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float* sums = flat_stats_begin(ws, G * 8);
     const int cg_ = t % G;
     float piv[8];
@@ -467,18 +477,19 @@ const float* flat_bn_train(const FlatBnTrain& a, const FlatGeom& g, cudaStream_t
     ap.pivot_zero = a.stats_source == 2 ? 1 : 0;
     if (a.stats_source == 0) {
         const FlatLaunch Ls = flat_launch(g, kStatsCtasPerSm, 8);
-        flat_bn_stats_kernel<false, false, 8><<<Ls.blocks, Ls.threads, 0, s>>>((const uint4*)a.x, nullptr, g.P, Ls.G, g.C, Ls.R,
-                                                                             ap.ws, nullptr);
-        DB_LAUNCH_CHECK();
+        DB_CUDA(launch_pdl(flat_bn_stats_kernel<false, false, 8>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, (const uint4*)a.x,
+                           (const uint4*)nullptr, g.P, Ls.G, g.C, Ls.R, ap.ws, (const float*)nullptr));
+        count_launch();
     }
     const FlatLaunch La = flat_launch(g, 4);
+    const uint4* none = nullptr;
     if (a.relu)
-        flat_bn_apply_kernel<0, true, false><<<La.blocks, La.threads, 0, s>>>((const uint4*)a.x, nullptr, nullptr, (uint4*)a.y, g.P,
-                                                                             La.G, g.C, La.R, ap);
+        DB_CUDA(launch_pdl(flat_bn_apply_kernel<0, true, false>, dim3(La.blocks), dim3(La.threads), 0, s, (const uint4*)a.x, none, none,
+                           (uint4*)a.y, g.P, La.G, g.C, La.R, ap));
     else
-        flat_bn_apply_kernel<0, false, false><<<La.blocks, La.threads, 0, s>>>((const uint4*)a.x, nullptr, nullptr, (uint4*)a.y,
-                                                                              g.P, La.G, g.C, La.R, ap);
-    DB_LAUNCH_CHECK();
+        DB_CUDA(launch_pdl(flat_bn_apply_kernel<0, false, false>, dim3(La.blocks), dim3(La.threads), 0, s, (const uint4*)a.x, none, none,
+                           (uint4*)a.y, g.P, La.G, g.C, La.R, ap));
+    count_launch();
     return ap.ws.coef;
 }
 
@@ -490,19 +501,19 @@ void flat_bn_grad(const FlatBnGrad& a, const FlatGeom& g, cudaStream_t s) {
     ap.fcoef = a.fcoef;
     const FlatLaunch Ls = flat_launch(g, kStatsCtasPerSm, 4);
     const uint4 *x = (const uint4*)a.x, *dy = (const uint4*)a.dy, *ad = (const uint4*)a.addend;
-    if (a.gate) flat_bn_stats_kernel<true, true, 4><<<Ls.blocks, Ls.threads, 0, s>>>(x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef);
-    else flat_bn_stats_kernel<true, false, 4><<<Ls.blocks, Ls.threads, 0, s>>>(x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef);
-    DB_LAUNCH_CHECK();
+    if (a.gate) DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, true, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
+    else DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, false, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
+    count_launch();
     const FlatLaunch La = flat_launch(g, 2);
     uint4* out = (uint4*)a.dx;
 #define FLAT_GRAD_APPLY(RELU, ADD) \
-    flat_bn_apply_kernel<1, RELU, ADD><<<La.blocks, La.threads, 0, s>>>(x, dy, ad, out, g.P, La.G, g.C, La.R, ap)
+    DB_CUDA(launch_pdl(flat_bn_apply_kernel<1, RELU, ADD>, dim3(La.blocks), dim3(La.threads), 0, s, x, dy, ad, out, g.P, La.G, g.C, La.R, ap))
     if (a.gate && ad) FLAT_GRAD_APPLY(true, true);
     else if (a.gate) FLAT_GRAD_APPLY(true, false);
     else if (ad) FLAT_GRAD_APPLY(false, true);
     else FLAT_GRAD_APPLY(false, false);
 #undef FLAT_GRAD_APPLY
-    DB_LAUNCH_CHECK();
+    count_launch();
 }
 
 void flat_stats_sink(void* workspace, int C, unsigned** epoch, float** sums, int* copies) {
@@ -514,17 +525,18 @@ void flat_stats_sink(void* workspace, int C, unsigned** epoch, float** sums, int
 
 void flat_add_stats(const void* a, const void* b, void* out, const FlatGeom& g, void* bn_workspace, cudaStream_t s) {
     const FlatLaunch L = flat_launch(g, kStatsCtasPerSm);
-    flat_add_stats_kernel<<<L.blocks, L.threads, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, g.P, L.G, L.R,
-                                                       flat_ws(bn_workspace, g.C));
-    DB_LAUNCH_CHECK();
+    DB_CUDA(launch_pdl(flat_add_stats_kernel, dim3(L.blocks), dim3(L.threads), 0, s, (const uint4*)a, (const uint4*)b, (uint4*)out,
+                       g.P, L.G, L.R, flat_ws(bn_workspace, g.C)));
+    count_launch();
 }
 
 void flat_add(const void* a, const void* b, void* out, int64_t n_elems, cudaStream_t s) {
     DB_REQUIRE(n_elems % 8 == 0, "flat_add: element count must be a multiple of 8");
     const int64_t nvec = n_elems / 8;
     if (nvec == 0) return;
-    flat_add_kernel<<<stream_grid(ceil_div(nvec, kFlatU), 256, 6), 256, 0, s>>>((const uint4*)a, (const uint4*)b, (uint4*)out, nvec);
-    DB_LAUNCH_CHECK();
+    DB_CUDA(launch_pdl(flat_add_kernel, dim3(stream_grid(ceil_div(nvec, kFlatU), 256, 6)), dim3(256), 0, s, (const uint4*)a,
+                       (const uint4*)b, (uint4*)out, nvec));
+    count_launch();
 }
 
 void unstage_nhwc_bf16_to_nchw(const void* in, float* out, int N, int C, int64_t HW, cudaStream_t s) {

@@ -534,13 +534,15 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = L.total;
         cfg.stream = s;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2;
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         static bool pair_configured = false;
         if (!pair_configured) {
             DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -587,16 +589,23 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
             DB_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             instr_configured = true;
         }
-        tc_kernel<MODE, false, true><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+        DB_CUDA(launch_pdl(tc_kernel<MODE, false, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
     } else if (MODE == TC_MODE_CONV && a.st_cols > 0) {
         static bool st1_configured = false;
         if (!st1_configured) {
             DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             st1_configured = true;
         }
-        tc_kernel<TC_MODE_CONV, false, false, 1, true><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+        DB_CUDA(launch_pdl(tc_kernel<TC_MODE_CONV, false, false, 1, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
+    } else if (MODE == TC_MODE_WGRAD && a.halo) {
+        static bool wh_configured = false;
+        if (!wh_configured) {
+            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_WGRAD, false, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            wh_configured = true;
+        }
+        DB_CUDA(launch_pdl(tc_kernel<TC_MODE_WGRAD, false, false, 1, false, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
     } else {
-        tc_kernel<MODE><<<n_ctas, TC_THREADS, L.total, s>>>(tmA, tmB, a);
+        DB_CUDA(launch_pdl(tc_kernel<MODE>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
     }
     {
         cudaError_t e = cudaGetLastError();
@@ -1122,6 +1131,46 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     a.o_sc = g.K;      // per Cin column
     a.out = acc;
     int mt = (int)ceil_div(g.K, TC_BM);
+    // Halo variant (3 x 3, unit stride, one image per pixel box): an item = (filter COLUMN, one Kout tile, Cin tile, pixel split);
+    // its three vertical taps keep their accumulators side by side in TMEM and share both the dy tile and ONE x box that
+    // carries a halo row above and below.  L2 -> SM bytes per MAC drop by a third (profiles/r02_summary.md).
+    static const int wg_halo = getenv("DOPT_B200_WG_HALO") ? atoi(getenv("DOPT_B200_WG_HALO")) : 1;
+    if (wg_halo && g.R == 3 && g.S == 3 && g.u == 1 && g.v == 1 && b.bn == 1 && b.bw % 8 == 0 && b.bw == g.Q && 3 * a.BN <= 512 &&
+        !getenv("DOPT_B200_DBG")) {
+        uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
+        uint64_t st[3] = {(uint64_t)Cp * 2, (uint64_t)g.W * Cp * 2, (uint64_t)g.H * g.W * Cp * 2};
+        uint32_t box[4] = {64, (uint32_t)b.bw, (uint32_t)(b.bh + 2), 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xh, dims, st, box, es, CU_TENSOR_MAP_SWIZZLE_128B) == CUDA_SUCCESS)
+            a.halo = 1;
+    }
+    if (a.halo) {
+        a.wg_nm = 1;
+        const int sms = sm_count();
+        const double pix = a.kmma * 16.0, nblk = (a.BN + 63) / 64, pixh = (double)(b.bh + 2) * b.bw;
+        const double mma = 3.0 * a.kmma * 115.0 * a.BN / 160.0;
+        const double copy = (2.0 * pix + nblk * pixh) * 128.0 / 42.0;   // ~42 B/clk per SM out of L2 with every SM pulling
+        const double iter = std::max(mma, copy) + 100.0, fixed = 4000.0 + 3.0 * 4000.0 * a.BN / 160.0;
+        const int64_t tiles_ = (int64_t)g.S * mt * a.n_tiles;
+        double best_t = 1e300;
+        int best_sp = 1;
+        for (int sp = 1; sp <= a.pix_tiles && tiles_ * sp <= (int64_t)16 * sms; ++sp) {
+            const int64_t per = ceil_div((int64_t)a.pix_tiles, (int64_t)sp);
+            if (per < 4 && sp > 1) break;
+            const int64_t rounds = ceil_div(tiles_ * sp, (int64_t)sms);
+            const double t = (double)rounds * ((double)per * iter + fixed);
+            if (t < best_t * 0.98) {
+                best_t = t;
+                best_sp = sp;
+            }
+        }
+        a.splits = best_sp;
+        if (const char* e = getenv("DOPT_B200_WG_SPLITS")) a.splits = std::max(1, std::min(a.pix_tiles, atoi(e)));
+        a.stages = pick_stages(a);
+        a.m_tiles = g.S * mt;
+        a.cluster = 1;
+        tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, (int)tiles_ * a.splits, s);
+    } else {
     // Work decomposition.  An item = (tap, group of wg_nm Kout tiles, Cin tile, pixel split).  The Kout tiles of a group share
     // the x tile of every stage, which is what keeps the kernel off the L2 -> SM bandwidth limit
     // (profiles/r01c_conv_bisect.md); wg_nm is bounded by the 512 TMEM columns and the shared-memory ring.  The pixel range
@@ -1166,6 +1215,7 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     a.cluster = 1;
     if (const char* e = getenv("DOPT_B200_DBG")) a.dbg = atoi(e);
     tc_launch<TC_MODE_WGRAD>(tmA, tmB, a, tiles * a.splits, s);
+    }
     if (!c->acc_private) {
         const size_t smem = (size_t)32 * (32 * RS + 1) * sizeof(float);
         DB_REQUIRE(smem <= 200 * 1024, "filter window too large for the wgrad finish kernel");

@@ -57,8 +57,9 @@ TRAIN_GFLOP_PER_IMAGE = 31.459
 # images per step of the bounded CPU sample (cpu_baseline and --impl reference): about 10 s of host work per step
 CPU_SAMPLE = 16
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, round 1 final)
-TC_DRAM_BYTES_PER_STEP = 3106400512 + 557725696
+# dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, profiles/r02_tc_dram.csv;
+# the NHWC bf16 results mostly stay in L2 until a later kernel evicts them, hence the small write figure)
+TC_DRAM_BYTES_PER_STEP = 2929168640 + 3014656
 
 
 def workload_name(depth=MODEL["depth"], width=MODEL["width"], batch=MODEL["batch"]):
@@ -100,6 +101,9 @@ def synthetic_batch(batch, seed):
 # ---------------------------------------------------------------------------------------------------------------------
 # per-kernel-class rooflines (the north star asks for the memory-bound classes as a fraction of HBM bandwidth)
 # ---------------------------------------------------------------------------------------------------------------------
+CONV_OPS = "convolution,convolutionFeaturesGrad,convolutionFiltersGrad"
+
+
 def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs, elem=4):
     """ALGORITHMIC bytes per step of the memory-bound op classes, from the exported dopt graph and SURVEY.md section 8(d)'s
     per-element figures (batchNormTrain 2V*s, batchNormGrad 3V*s -- the relu / reluGrad / NHWC staging the plan folds into
@@ -390,7 +394,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = float(t[0]), float(t[1])
 
-    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of the tcgen05 kernel inside the same step ----
+    # ---- per-op device times: every plan item between two CUDA events (serialised, eager; includes the launch latency the
+    # captured graph hides, so it is an upper bound per op type) ----
     roof = None
     # every rank runs the profiled steps (the plan contains the gradient all-reduce); rank 0 reports
     upd.profile(True)
@@ -398,9 +403,26 @@ def main():
         step_dev(i)
     torch.cuda.synchronize()
     prof = upd.profile(False)
+    # ---- rooflines: the launches of ONE kernel class re-issued back to back with the operands of the last step, between one
+    # pair of CUDA events (dopt_b200_plan_replay_class) -- the class's device time without an event bracket around every
+    # launch.  This scrambles the plan's accumulating state, so it is the last thing this process does with the updater. ----
+    replay = {}
+    if world == 1:
+        for name, ops in (("tc", CONV_OPS), ("batchNormTrain", "batchNormTrain"), ("batchNormGrad", "batchNormGrad"),
+                          ("add", "add"), ("fusedRegion", "fusedRegion")):
+            try:
+                replay[name] = upd.replay_class(ops, 3)
+            except Exception as e:   # diagnostics: never lose the bench line over it
+                replay[name + "_error"] = repr(e)
+        torch.cuda.synchronize()
     if RANK == 0:
         pk = peaks()
         tc_us = prof.get("tc_kernel", 0) / 2.0
+        tc_us_events = tc_us
+        if "tc" in replay:
+            # the three convolution ops of the step: 88 tcgen05 launches + the 3-channel stem's direct kernel + the memsets of
+            # the filter-gradient accumulators (part of those ops), against the same algorithmic FLOPs
+            tc_us = replay["tc"][0]
         conv_flops = TRAIN_GFLOP_PER_IMAGE * 1e9 * B if (args.depth, args.width) == (28, 10) else None
         if tc_us > 0 and conv_flops:
             achieved = conv_flops / (tc_us * 1e-6) / 1e12
@@ -415,10 +437,14 @@ def main():
                     "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                     "traffic": TC_DRAM_BYTES_PER_STEP if (args.depth, args.width) == (28, 10) else None,
                     "traffic_source": "ncu dram__bytes_read+write summed over the step's tc_kernel launches "
-                                      "(profiles/r01_final_tc_dram.csv), per step like `achieved`",
+                                      "(profiles/r02j_tc_dram.csv), per step like `achieved`",
                     "peak_source": pk["source"] + (" (burst: SM clock at max, no power cap during the timed region)" if burst
                                                    else " (sustained: SM clock below max or power-capped during the timed region)"),
-                    "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3}
+                    "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3,
+                    "how": ("the step's convolution launches re-issued back to back between one CUDA-event pair "
+                            "(dopt_b200_plan_replay_class; includes the stem's direct kernel and the accumulator memsets)"
+                            if "tc" in replay else "sum of per-launch CUDA-event brackets around the tcgen05 kernel"),
+                    "kernel_ms_per_step_event_brackets": tc_us_events / 1e3}
     classes = None
     if RANK == 0:
         try:
@@ -427,6 +453,9 @@ def main():
             loss_id = [n["id"] for n in nodes if n["op"].h == plan_outs[0].h][0]
             per_us = dict((k, v / 2.0) for k, v in prof.items() if "#" not in k)
             per_n = dict((k[:-2], v / 2.0) for k, v in prof.items() if k.endswith("#n"))
+            for name in ("batchNormTrain", "batchNormGrad", "add", "fusedRegion"):
+                if name in replay:      # class replay (one event pair per class) instead of per-launch event brackets
+                    per_us[name] = replay[name][0]
             interior = bool(H.plan_flags() & db._lib.PLAN_BF16_INTERIOR)
             classes = class_rooflines(nodes, loss_id, per_us, per_n, n_params, peaks()["hbm_gbs"], elem=2 if interior else 4)
         except Exception as e:  # diagnostics only: never lose the bench line over it

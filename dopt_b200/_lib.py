@@ -64,7 +64,7 @@ SYMBOLS = [
     "dopt_b200_sgd_update", "dopt_b200_adam_update",
     "dopt_b200_image_transform_u8", "dopt_b200_image_transform_f32", "dopt_b200_one_hot_u8", "dopt_b200_jitter_sample",
     "dopt_b200_plan_create", "dopt_b200_plan_add_node", "dopt_b200_plan_set_outputs", "dopt_b200_plan_finalize",
-    "dopt_b200_plan_execute", "dopt_b200_plan_stats", "dopt_b200_plan_profile", "dopt_b200_plan_destroy",
+    "dopt_b200_plan_execute", "dopt_b200_plan_stats", "dopt_b200_plan_profile", "dopt_b200_plan_replay_class", "dopt_b200_plan_destroy",
     "dopt_b200_comm_unique_id", "dopt_b200_comm_init", "dopt_b200_comm_world_size", "dopt_b200_comm_rank",
     "dopt_b200_allreduce", "dopt_b200_comm_check", "dopt_b200_comm_destroy",
 ]
@@ -106,6 +106,7 @@ def load():
                                            C.c_int, vp]
     lib.dopt_b200_plan_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.dopt_b200_plan_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t]
+    lib.dopt_b200_plan_replay_class.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), vp]
     lib.dopt_b200_plan_destroy.argtypes = [vp]
     lib.dopt_b200_comm_unique_id.argtypes = [vp]
     lib.dopt_b200_comm_init.argtypes = [C.c_int, C.c_int, vp]

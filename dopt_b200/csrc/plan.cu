@@ -1814,7 +1814,24 @@ __global__ void profile_delay_kernel(unsigned long long ns) {
     } while (t - t0 < ns);
 }
 
-static void run_items(Plan& p, cudaStream_t s) {
+// op type under which the profiler books an item
+static const char* item_label(const Plan& p, const Item& it) {
+    switch (it.kind) {
+        case ITEM_BUCKET: return "allreduceBucket";
+        case ITEM_MSUM: return "sum";
+        case ITEM_PACK: return "packFilters";
+        case ITEM_STAGE: return "stageNHWC";
+        case ITEM_WFINISH: return "filtersGradFinish";
+        case ITEM_UNSTAGE: return "unstageNCHW";
+        case ITEM_COPY: return "bucketCopyIn";
+        case ITEM_KERNEL:
+        case ITEM_PW_SCALAR: return p.nodes[it.id].type.c_str();
+        default: return "fusedRegion";
+    }
+}
+
+// `only`: diagnostics (dopt_b200_plan_replay_class) -- issue just the items booked under these op types, nothing else
+static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only = nullptr) {
     auto& N = p.nodes;
     bool comm_pending = false;
     // Side stream.  A tensor-core filter gradient with a deferred finish reads two staged activations nothing overwrites and
@@ -1844,6 +1861,7 @@ static void run_items(Plan& p, cudaStream_t s) {
     }
     size_t item_no = 0;
     for (const Item& it : p.order) {
+        if (only && !only->count(item_label(p, it))) continue;
         if (p.profiling) DB_CUDA(cudaEventRecord(p.prof_ev[item_no++], s));
         const char* label;
         if (it.join_comm && comm_pending) {
@@ -1914,7 +1932,7 @@ static void run_items(Plan& p, cudaStream_t s) {
                 ab.staged = n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr;
                 n.kernel->set_absorbed(ab);
             }
-            if (side_on && !p.profiling && n.finish_group >= 0 && n.kernel->side_stream_safe()) {
+            if (side_on && !p.profiling && !only && n.finish_group >= 0 && n.kernel->side_stream_safe()) {
                 if (!p.side_stream) {
                     // lowest priority: when both streams have CTAs waiting for an SM, the chain's go first
                     int prio_lo = 0, prio_hi = 0;
@@ -2218,6 +2236,44 @@ int dopt_b200_plan_profile(dopt_b200_plan_t p, int enable, char* buf, size_t buf
         db::tc_prof_enable(enable != 0);
     }
     p->profiling = enable != 0;
+    PLAN_CATCH
+}
+
+int dopt_b200_plan_replay_class(dopt_b200_plan_t p, const char* op_types, int reps, double* usec_per_rep,
+                                int64_t* launches_per_rep, void* stream) {
+    PLAN_TRY
+    DB_REQUIRE(p && op_types && reps > 0 && usec_per_rep, "plan_replay_class: bad arguments");
+    DB_REQUIRE(p->finalized && p->bound_key != 0, "plan_replay_class: execute the plan first");
+    std::set<std::string> only;
+    for (const char* c = op_types; *c;) {
+        const char* e = strchr(c, ',');
+        only.insert(e ? std::string(c, e) : std::string(c));
+        if (!e) break;
+        c = e + 1;
+    }
+    for (const std::string& t : only) DB_REQUIRE(t != "allreduceBucket", "plan_replay_class: collectives cannot be replayed alone");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    DB_CUDA(cudaEventCreate(&e0));
+    DB_CUDA(cudaEventCreate(&e1));
+    const bool was = p->profiling;
+    p->profiling = false;
+    db::run_items(*p, s, &only);   // untimed: brings the class's code and descriptors in
+    // behind a delay kernel, so that the host has enqueued every launch before the first one starts
+    db::profile_delay_kernel<<<1, 1, 0, s>>>(2000000ull + 1000000ull * (unsigned long long)reps);
+    DB_CUDA(cudaEventRecord(e0, s));
+    const uint64_t l0 = db::g_launches.load();
+    for (int r = 0; r < reps; ++r) db::run_items(*p, s, &only);
+    const uint64_t l1 = db::g_launches.load();
+    DB_CUDA(cudaEventRecord(e1, s));
+    DB_CUDA(cudaEventSynchronize(e1));
+    p->profiling = was;
+    float ms = 0;
+    DB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *usec_per_rep = (double)ms * 1000.0 / reps;
+    if (launches_per_rep) *launches_per_rep = (int64_t)((l1 - l0) / (uint64_t)reps);
     PLAN_CATCH
 }
 

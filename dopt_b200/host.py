@@ -67,6 +67,7 @@ _h.dh_updater_step.argtypes = [C.c_int, i32p, C.POINTER(vp), C.POINTER(C.c_size_
 _h.dh_updater_step_device.argtypes = [C.c_int, i32p, C.POINTER(vp), C.c_int]
 _h.dh_updater_plan_outputs.argtypes = [C.c_int, i32p, i32p, C.c_int]
 _h.dh_updater_stats.argtypes = [C.c_int, i64p, i64p, i64p]
+_h.dh_updater_replay_class.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), i64p]
 _h.dh_init_data_parallel.argtypes = [C.c_int, C.c_int, vp]
 _h.dh_matrix_norm.argtypes = [C.c_int, C.c_int]
 _h.dh_conv_params_norm.argtypes = [C.c_int, i64p, i64p, i64p, C.c_int]
@@ -463,6 +464,14 @@ class Updater(object):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _ck(_h.dh_updater_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"launches": a.value, "device_bytes": b.value, "lowered_nodes": c.value}
+
+    def replay_class(self, op_types, reps=3):
+        """(microseconds, launches) of one repetition of the kernels the profiler books under `op_types` (a comma-separated
+        string), re-issued back to back with the operands of the last step -- see dopt_b200_plan_replay_class.  Leaves the
+        updater's state garbage: call it last."""
+        us, n = C.c_double(), C.c_int64()
+        _ck(_h.dh_updater_replay_class(self.h, op_types.encode(), int(reps), C.byref(us), C.byref(n)))
+        return us.value, n.value
 
     def profile(self, enable):
         t = _h.dh_updater_profile(self.h, int(enable))

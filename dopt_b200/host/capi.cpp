@@ -608,6 +608,14 @@ int dh_updater_stats(int u, int64_t* launches, int64_t* bytes, int64_t* nodes) {
     return 0;
     DH_CATCH(-1)
 }
+int dh_updater_replay_class(int u, const char* op_types, int reps, double* usec, int64_t* launches) {
+    DH_TRY
+    auto bp = std::dynamic_pointer_cast<cuda::B200Plan>(g_updaters.at(u).info.plan);
+    enforce(bp != nullptr, "updater is not backed by a B200Plan");
+    *usec = bp->replayClass(op_types, reps, launches);
+    return 0;
+    DH_CATCH(-1)
+}
 const char* dh_updater_profile(int u, int enable) {
     try {
         auto bp = std::dynamic_pointer_cast<cuda::B200Plan>(g_updaters.at(u).info.plan);

@@ -259,6 +259,12 @@ std::string B200Plan::profile(bool enable) {
     return std::string(buf.data());
 }
 
+double B200Plan::replayClass(const std::string& opTypes, int reps, int64_t* launches) {
+    double us = 0;
+    abiEnforce(dopt_b200_plan_replay_class((dopt_b200_plan_t)mPlan, opTypes.c_str(), reps, &us, launches, nullptr));
+    return us;
+}
+
 void B200Plan::executeRaw(const std::vector<Operation>& argOps, const std::vector<const void*>& argPtrs,
                           const std::vector<int>& argOnHost, const std::vector<void*>& rets) {
     // variables not named in args are read from their own buffers (package.d:383-392)

@@ -57,6 +57,8 @@ public:
     ~B200Plan() override;
     void stats(int64_t* launches, int64_t* deviceBytes, int64_t* loweredNodes) const;
     std::string profile(bool enable);
+    // device time (us) and launches of ONE repetition of the kernels booked under `opTypes` (dopt_b200_plan_replay_class)
+    double replayClass(const std::string& opTypes, int reps, int64_t* launches);
     // raw execution for benchmarks: device or host pointers, no DeviceBuffer objects (what executeImpl does internally)
     void executeRaw(const std::vector<Operation>& argOps, const std::vector<const void*>& argPtrs,
                     const std::vector<int>& argOnHost, const std::vector<void*>& rets);

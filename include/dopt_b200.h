@@ -186,6 +186,14 @@ int dopt_b200_plan_stats(dopt_b200_plan_t p, int64_t* launches, int64_t* device_
 /* per-op-type accumulated device time in microseconds since the last reset (CUDAPlan.profiler, package.d:265);
  * only filled when profiling is on (it serialises the stream with events).  `buf` receives "opType=usec\n" lines. */
 int dopt_b200_plan_profile(dopt_b200_plan_t p, int enable, char* buf, size_t buf_len);
+/* measurement aid (no reference counterpart): re-issue ONLY the launches the profiler books under the comma-separated
+ * `op_types` ("batchNormTrain", "convolution,convolutionFeaturesGrad,convolutionFiltersGrad", "fusedRegion" ...) with the
+ * operands of the last execution, `reps` times back to back on `stream`, timed by ONE pair of CUDA events -- the device
+ * time of a kernel class without a per-launch event bracket around every kernel.  It re-runs accumulating kernels out of
+ * order (batch-norm statistic sinks, running statistics, in-place parameter updates), so the plan's state is garbage
+ * afterwards: call it after the last execution that matters (bench.py does, for its roofline figures). */
+int dopt_b200_plan_replay_class(dopt_b200_plan_t p, const char* op_types, int reps, double* usec_per_rep,
+                                int64_t* launches_per_rep, void* stream);
 int dopt_b200_plan_destroy(dopt_b200_plan_t p);
 
 /* ---- data-parallel gradient exchange (new; one process per GPU) -----------------------------------------------------

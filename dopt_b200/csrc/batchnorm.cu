@@ -549,10 +549,26 @@ struct BnGradKernel : Kernel {
     const void* staged_in[4] = {nullptr, nullptr, nullptr, nullptr};   // 0 = dy, 1 = x, 3 = addend
     Scratch fws;
     const void* fws_for = nullptr;
+    bool producer_stats = false;   // the convolution that writes dy accumulates the statistics in its epilogue
     bool can_flat() const override { return flat_supported(g.N, g.C, g.HW); }
     void set_flat(bool on) override { flat = on; }
     void set_staged_input(int input, const void* p) override {
         if (input >= 0 && input < 4) staged_in[input] = p;
+    }
+    void* flat_workspace(cudaStream_t s, bool sync) {
+        const size_t wb = flat_bn_workspace_bytes((int)g.C);
+        void* w = fws.get(wb);
+        if (w != fws_for) {
+            if (sync) DB_CUDA(cudaMemset(w, 0, wb));
+            else DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
+            fws_for = w;
+        }
+        return w;
+    }
+    void* stats_workspace(int mode) override {
+        if (!flat || mode != 3 || !fwd) return nullptr;
+        producer_stats = true;
+        return flat_workspace(nullptr, true);
     }
     bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
     void set_absorbed(const Absorb& a) override {
@@ -580,13 +596,9 @@ struct BnGradKernel : Kernel {
             const float* fc = fwd ? (const float*)fwd->aux_ptr() : nullptr;
             DB_REQUIRE(fc, "batchNormGrad: flat mode needs the forward pass's coefficients");
             DB_REQUIRE(staged_in[0] && staged_in[1] && ab.staged && ab.skip_fp32, "batchNormGrad: flat mode needs staged operands and output");
-            const size_t wb = flat_bn_workspace_bytes((int)g.C);
-            void* w = fws.get(wb);
-            if (w != fws_for) {
-                DB_CUDA(cudaMemsetAsync(w, 0, wb, s));
-                fws_for = w;
-            }
+            void* w = flat_workspace(s, false);
             FlatBnGrad a{};
+            a.stats_from_producer = producer_stats;
             a.dy = staged_in[0]; a.x = staged_in[1]; a.addend = staged_in[3];
             a.dx = ab.staged;
             a.scale = (const float*)in[2];

@@ -183,6 +183,13 @@ struct Kernel {
     virtual void* stats_workspace(int /*mode*/) { return nullptr; }
     virtual int can_produce_stats() const { return 0; }   // 0 = no, else the mode it produces
     virtual void set_stats_workspace(void* /*bn_workspace*/, int /*channels*/) {}
+    // epilogue companions of a tensor-core convolution writing NHWC bf16 (tc.cuh: conv_tc_set_companion).  mode 2, forward:
+    // the residual sum the convolution feeds is written by its epilogue (result + src); mode 3, unit-stride feature gradient:
+    // the epilogue also accumulates the backward statistics of the batch norm that reads the result (src = that batch norm's
+    // x, coef = its forward coefficients) into the workspace given with set_stats_workspace.  A flat batchNormGrad hands out
+    // that workspace through stats_workspace(3) and then skips its own statistics kernel.
+    virtual bool can_companion(int /*mode*/) const { return false; }
+    virtual void set_companion(int /*mode*/, const void* /*src*/, const float* /*coef*/) {}
     virtual const void* aux_ptr() const { return nullptr; }
 };
 // NCHW fp32 -> [N][HW][Cp] bf16 (Cp = C rounded up to 8), the staging the tensor-core convolutions use

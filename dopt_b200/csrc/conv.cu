@@ -53,7 +53,10 @@ struct ConvKernel : Kernel {
     int can_produce_stats() const override { return (tc && kind == CONV_FWD) ? 2 : 0; }
     void set_stats_workspace(void* w, int channels) override {
         if (tc && kind == CONV_FWD && channels == g.K) conv_tc_set_stats_workspace(tc, w);
+        if (tc && kind == CONV_DGRAD && channels == g.C) conv_tc_set_stats_workspace(tc, w);
     }
+    bool can_companion(int mode) const override { return tc && conv_tc_can_companion(tc, mode); }
+    void set_companion(int mode, const void* src, const float* coef) override { conv_tc_set_companion(tc, mode, src, coef); }
     void run(const void* const* in, int n_in, void* out, cudaStream_t s) override {
         DB_REQUIRE(n_in == 2, "convolution ops take two inputs");
         const float* a = (const float*)in[0];

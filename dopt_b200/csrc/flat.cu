@@ -501,9 +501,11 @@ void flat_bn_grad(const FlatBnGrad& a, const FlatGeom& g, cudaStream_t s) {
     ap.fcoef = a.fcoef;
     const FlatLaunch Ls = flat_launch(g, kStatsCtasPerSm, 4);
     const uint4 *x = (const uint4*)a.x, *dy = (const uint4*)a.dy, *ad = (const uint4*)a.addend;
-    if (a.gate) DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, true, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
-    else DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, false, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
-    count_launch();
+    if (!a.stats_from_producer) {
+        if (a.gate) DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, true, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
+        else DB_CUDA(launch_pdl(flat_bn_stats_kernel<true, false, 4>, dim3(Ls.blocks), dim3(Ls.threads), 0, s, x, dy, g.P, Ls.G, g.C, Ls.R, ap.ws, a.fcoef));
+        count_launch();
+    }
     const FlatLaunch La = flat_launch(g, 2);
     uint4* out = (uint4*)a.dx;
 #define FLAT_GRAD_APPLY(RELU, ADD) \

@@ -44,6 +44,8 @@ struct FlatBnGrad {
     bool gate;                       // dy is the gradient w.r.t. relu(y): gate it by [y > 0], y recomputed from x and fcoef
     float* dscale; float* dbias;     // packed tail of the op's result
     void* workspace;
+    bool stats_from_producer;        // the feature-gradient convolution that wrote dy accumulated sum(g), sum(g * (x - mean))
+                                     // in its epilogue (tc_kernel<.., EPI = 3>): no statistics kernel here
 };
 void flat_bn_grad(const FlatBnGrad& a, const FlatGeom& g, cudaStream_t s);
 

@@ -77,6 +77,10 @@ struct Node {
     int finish_group = -1;      // tensor-core convolutionFiltersGrad whose scratch -> KCRS conversion is done by a multi-tensor launch
     bool flat = false;          // batchNormTrain / batchNormGrad / add working on NHWC bf16 operands and result (flat.cu)
     int out_stage = -1;         // tensor-core convolution whose epilogue writes this stage (NHWC bf16) instead of NCHW fp32
+    // epilogue companions (pass "residency", H): see Kernel::set_companion
+    int ep_add = -1;            // convolution: flat `add` node whose residual sum its epilogue writes (the add disappears)
+    int ep_bn = -1;             // convolutionFeaturesGrad: flat batchNormGrad whose statistics its epilogue accumulates
+    int ep_src_stage = -1;      // stage the epilogue reads: the addend (ep_add) / the batch norm's x (ep_bn)
     // runtime
     void* buf = nullptr;        // plan-owned buffer (or nullptr for views / variables)
     void* ptr = nullptr;        // resolved pointer for this execution
@@ -1460,6 +1464,53 @@ static void residency(Plan& p) {
         Cn.out_stage = si;
         drop_buffer(Cn);
     }
+    // H1: a residual sum whose one operand is the staged result of a tensor-core convolution that nothing else reads: the
+    // convolution's epilogue reads the other operand (one 32-byte piece per accumulator row and 16-column chunk, prefetched a
+    // chunk ahead), adds in fp32 and writes the sum -- one pass over the sum instead of write + read + read + write.  The add
+    // node disappears (absorbed_by = the convolution).  When both operands qualify (a block with a shortcut convolution) the
+    // later one takes the sum.
+    // Measured on the WRN-28-10 step (profiles/r02_summary.md): the scattered 32-byte companion reads compete with the operand
+    // stream for L2->SM bandwidth -- +18 us per convolution against the 16 us flat_add_stats launch it removes -- so the pass is
+    // opt-in (DOPT_B200_EPI_ADD=1).
+    int n_ep_add = 0;
+    if (getenv("DOPT_B200_EPI_ADD"))
+        for (int i = 0; i < n_nodes; ++i) {
+            Node& A = N[i];
+            if (!A.flat || A.type != "add" || A.absorbed_by >= 0 || A.absorb_stage < 0 || A.deps.size() != 2) continue;
+            if (p.stages[A.absorb_stage].producer != i) continue;
+            const Shape os = shape_of(A.op.output);
+            int best = -1, best_k = -1;
+            for (int k = 0; k < 2; ++k) {
+                int64_t off = 0;
+                const int r = root_of(p, A.deps[k], &off);
+                const Node& X = N[r];
+                if (off != 0 || r >= i || X.out_stage < 0 || X.absorbed_by >= 0 || X.ep_add >= 0 || !X.kernel || !X.kernel->can_companion(2)) continue;
+                if (X.type != "convolution" || !(shape_of(X.op.output) == os)) continue;
+                const Stage& sx = p.stages[X.out_stage];
+                if (sx.producer != r || sx.unstage_to >= 0 || sx.users.size() != 1 || sx.users[0].first != i) continue;
+                if (best < 0 || std::make_pair(X.lvl, r) > std::make_pair(N[best].lvl, best)) {
+                    best = r;
+                    best_k = k;
+                }
+            }
+            if (best < 0) continue;
+            int64_t off_o = 0;
+            const int ro = root_of(p, A.deps[1 - best_k], &off_o);
+            if (ro == best || off_o != 0) continue;   // x + x
+            const int so = find_stage(A.deps[1 - best_k], os, false);
+            if (so < 0) continue;
+            Node& X = N[best];
+            Stage& old_stage = p.stages[X.out_stage];
+            old_stage.users.clear();
+            old_stage.producer = -1;
+            old_stage.must = false;
+            X.out_stage = A.absorb_stage;
+            X.ep_add = i;
+            X.ep_src_stage = so;
+            p.stages[A.absorb_stage].producer = best;
+            A.absorbed_by = best;
+            ++n_ep_add;
+        }
     // G: batch-norm statistics accumulated by the producer of x -- the convolution epilogue (x only exists as the staged
     // result of a tensor-core convolution) or the flat residual add -- instead of a statistics pass of their own
     int n_stats = 0;
@@ -1468,7 +1519,9 @@ static void residency(Plan& p) {
             Node& B = N[i];
             if (!B.flat || B.type != "batchNormTrain") continue;
             int64_t off = 0;
-            const int r = root_of(p, B.deps[0], &off);
+            const int r0 = root_of(p, B.deps[0], &off);
+            // a residual sum written by a convolution's epilogue (H1): that convolution is the producer
+            const int r = (N[r0].absorbed_by >= 0 && N[N[r0].absorbed_by].ep_add == r0) ? N[r0].absorbed_by : r0;
             Node& X = N[r];
             if (off != 0 || !X.kernel || X.absorbed_by >= 0) continue;
             const bool conv = X.out_stage >= 0 && X.kernel->can_produce_stats() == 2;
@@ -1477,14 +1530,43 @@ static void residency(Plan& p) {
             // one producer feeds one statistics workspace: the first batch norm reading x gets it (a residual sum has one)
             bool taken = false;
             for (int j = 0; j < i; ++j)
-                if (N[j].flat && N[j].type == "batchNormTrain" && root_of(p, N[j].deps[0]) == r) taken = true;
+                if (N[j].flat && N[j].type == "batchNormTrain" && root_of(p, N[j].deps[0]) == r0) taken = true;
             if (taken) continue;
             void* w = B.kernel->stats_workspace(conv ? 2 : 1);
             if (!w) continue;
             X.kernel->set_stats_workspace(w, (int)B.op.inputs[0].shape[1]);
             ++n_stats;
         }
+    // H2: the backward statistics of a flat batchNormGrad -- sum(g), sum(g * (x - mean)), g = dy gated by the forward relu --
+    // accumulated by the epilogue of the unit-stride feature-gradient convolution that writes dy; the epilogue reads x (same
+    // shape and layout as its result) next to the accumulator.  Removes the statistics pass over dy and x.
+    // Measured like H1: +17 us per feature gradient against the 15 us statistics launch it removes; opt-in
+    // (DOPT_B200_EPI_BNGRAD=1).
+    int n_ep_bn = 0;
+    if (getenv("DOPT_B200_EPI_BNGRAD"))
+        for (int i = 0; i < n_nodes; ++i) {
+            Node& G = N[i];
+            if (!G.flat || G.type != "batchNormGrad" || G.gate_from < 0 || !G.kernel) continue;
+            int64_t off = 0;
+            const int r = root_of(p, G.in_override[0] >= 0 ? G.in_override[0] : G.deps[0], &off);
+            Node& D = N[r];
+            if (off != 0 || D.absorbed_by >= 0 || !D.kernel || D.out_stage < 0 || D.ep_bn >= 0 || D.ep_add >= 0 ||
+                D.type != "convolutionFeaturesGrad" || !D.kernel->can_companion(3))
+                continue;
+            const Shape xs = shape_of(G.op.inputs[1]);
+            if (!(shape_of(D.op.output) == xs)) continue;
+            const int sx = find_stage(G.deps[1], xs, false);
+            if (sx < 0) continue;
+            void* w = G.kernel->stats_workspace(3);
+            if (!w) continue;
+            D.kernel->set_stats_workspace(w, xs.c);
+            D.ep_bn = i;
+            D.ep_src_stage = sx;
+            ++n_ep_bn;
+        }
     if (getenv("DOPT_B200_PLAN_DUMP")) {
+        fprintf(stderr, "PLAN residency: %d residual sums written by a convolution epilogue, %d backward batch-norm statistics taken from a feature-gradient epilogue\n",
+                n_ep_add, n_ep_bn);
         fprintf(stderr, "PLAN residency: %d batch norms take their statistics from the producer of x\n", n_stats);
         int n_flat = 0, n_conv = 0, n_un = 0;
         for (auto& n : N) {
@@ -1653,6 +1735,11 @@ static void build(Plan& p) {
             for (auto& u : st.users) N[u.first].kernel->set_staged_input(u.second, st.buf);
             if (st.producer >= 0 && N[st.producer].out_stage == (int)si) N[st.producer].kernel->set_staged_output(st.buf);
         }
+        for (auto& n : N)
+            if (n.ep_add >= 0) {
+                DB_REQUIRE(p.stages[n.ep_src_stage].buf, "plan: the addend of an epilogue residual sum is not staged");
+                n.kernel->set_companion(2, p.stages[n.ep_src_stage].buf, nullptr);
+            }
     }
     schedule(p);
     p.direct_out.assign(p.outputs.size(), 0);
@@ -1931,6 +2018,12 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
                 ab.skip_fp32 = n.absorb_skip;
                 ab.staged = n.absorb_stage >= 0 ? p.stages[n.absorb_stage].buf : nullptr;
                 n.kernel->set_absorbed(ab);
+            }
+            if (n.ep_bn >= 0) {
+                // (the forward batch norm has run by now: its coefficient block exists)
+                const float* coef = (const float*)N[N[n.ep_bn].gate_from].kernel->aux_ptr();
+                DB_REQUIRE(coef && p.stages[n.ep_src_stage].buf, "plan: backward batch-norm statistics in a convolution epilogue need x staged and the forward coefficients");
+                n.kernel->set_companion(3, p.stages[n.ep_src_stage].buf, coef);
             }
             if (side_on && !p.profiling && !only && n.finish_group >= 0 && n.kernel->side_stream_safe()) {
                 if (!p.side_stream) {

@@ -30,6 +30,11 @@ void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16);
 // fwd with staged output: also accumulate sum / sum of squares per output channel into the statistics workspace of the flat
 // batchNormTrain that reads the result (flat.cuh: flat_stats_sink)
 void conv_tc_set_stats_workspace(ConvTc* c, void* bn_workspace);
+// epilogue companion, see TcArgs::ep_src.  mode 2 (fwd): result = convolution + src; mode 3 (unit-stride dgrad): src = x and
+// coef = forward coefficients of the batch norm whose backward pass reads the result; its statistics go to the workspace given
+// with conv_tc_set_stats_workspace.  Both need the NHWC bf16 output.
+bool conv_tc_can_companion(const ConvTc* c, int mode);
+void conv_tc_set_companion(ConvTc* c, int mode, const void* src, const float* coef);
 // wgrad: accumulate into a private scratch (allocated here) and skip the per-op finish kernel; the caller finishes `row` later
 bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row);
 // wgrad that reads only plan-staged operands and writes only its private scratch: it shares no workspace with any other op, so

@@ -13,6 +13,7 @@
 #include "flat.cuh"
 #include <type_traits>
 #include "tc_kernel.cuh"
+#include <set>
 #include <mutex>
 
 namespace db {
@@ -488,6 +489,38 @@ void tc_prof_read(double* us, int64_t* launches) {
 static int g_reserved_sms = 0;
 void tc_set_reserved_sms(int k) { g_reserved_sms = k < 0 ? 0 : k; }
 
+// one instantiation of the kernel: opt in to the full shared memory once, launch with the cluster size it needs and as a
+// programmatic dependent of the previous kernel in the stream
+template <typename K>
+static void tc_launch_variant(K kernel, int cluster, int n_ctas, uint32_t smem, cudaStream_t s, const CUtensorMap& tmA,
+                              const CUtensorMap& tmB, const TcArgs& a) {
+    static std::set<const void*> configured;   // (every instantiation of tc_kernel has the same function type K)
+    if (configured.insert((const void*)kernel).second)
+        DB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = (unsigned)n;
+    DB_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, a));
+}
+
 template <int MODE>
 static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, int n_ctas, cudaStream_t s) {
     // n_ctas on entry = number of work items (m_tiles * n_tiles * splits)
@@ -504,11 +537,6 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         a.per_split = (total + std::max(1, a.splits) - 1) / std::max(1, a.splits);
     }
     TcSmemLayout L = tc_smem_layout(a);
-    static int configured = 0;
-    if (configured < (int)L.total) {
-        DB_CUDA(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
-    }
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
     if (g_reserved_sms > 0 && a.nacc == 2) L.total = 227 * 1024;   // one CTA per SM: keep the SM to itself
     if (g_tc_prof) {
@@ -528,84 +556,37 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
         if (clusters < 1) clusters = 1;
         n_ctas = clusters * cs;
     }
+    // epilogue flavour: 0 plain, 1 statistics of the result, 2 result + companion (residual sum), 3 gated backward statistics
+    const int epi = a.ep_src ? (a.ep_coef ? 3 : 2) : (a.st_cols > 0 ? 1 : 0);
     if (a.pair) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)n_ctas);
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = L.total;
-        cfg.stream = s;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        static bool pair_configured = false;
-        if (!pair_configured) {
-            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            pair_configured = true;
-        }
-        if (a.halo) {
-            static bool halo_configured = false;
-            if (!halo_configured) {
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                halo_configured = true;
-            }
-            if (a.st_cols > 0) DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, true, true>, tmA, tmB, a));
-            else DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, false, true>, tmA, tmB, a));
-        } else if (a.trace || a.dbg) {
-            static bool instr_configured = false;
-            if (!instr_configured) {
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                instr_configured = true;
-            }
-            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, true>, tmA, tmB, a));
-        } else if (a.st_cols > 0) {
-            static bool st_configured = false;
-            if (!st_configured) {
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                st_configured = true;
-            }
-            if (a.kbox == 2) DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 2, true>, tmA, tmB, a));
-            else DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 1, true>, tmA, tmB, a));
-        } else if (a.kbox == 2) {
-            static bool k2_configured = false;
-            if (!k2_configured) {
-                DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                k2_configured = true;
-            }
-            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true, false, 2>, tmA, tmB, a));
-        } else {
-            DB_CUDA(cudaLaunchKernelEx(&cfg, tc_kernel<TC_MODE_CONV, true>, tmA, tmB, a));
-        }
+        // cta_group::2 kernels need an even cluster
+#define TC_PAIR_CASE(KBOX_, EPI_, HALO_)                                                                                        \
+        tc_launch_variant(tc_kernel<TC_MODE_CONV, true, false, KBOX_, EPI_, HALO_>, 2, n_ctas, L.total, s, tmA, tmB, a)
+#define TC_PAIR_EPI(KBOX_, HALO_)                                                                                               \
+        do {                                                                                                                     \
+            if (epi == 0) TC_PAIR_CASE(KBOX_, 0, HALO_);                                                                          \
+            else if (epi == 1) TC_PAIR_CASE(KBOX_, 1, HALO_);                                                                     \
+            else if (epi == 2) TC_PAIR_CASE(KBOX_, 2, HALO_);                                                                     \
+            else TC_PAIR_CASE(KBOX_, 3, HALO_);                                                                                   \
+        } while (0)
+        if (a.trace || a.dbg) tc_launch_variant(tc_kernel<TC_MODE_CONV, true, true>, 2, n_ctas, L.total, s, tmA, tmB, a);
+        else if (a.halo) TC_PAIR_EPI(1, true);
+        else if (a.kbox == 2) TC_PAIR_EPI(2, false);
+        else TC_PAIR_EPI(1, false);
+#undef TC_PAIR_EPI
+#undef TC_PAIR_CASE
     } else if (a.trace || a.dbg) {
-        static bool instr_configured = false;
-        if (!instr_configured) {
-            DB_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            instr_configured = true;
-        }
-        DB_CUDA(launch_pdl(tc_kernel<MODE, false, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
-    } else if (MODE == TC_MODE_CONV && a.st_cols > 0) {
-        static bool st1_configured = false;
-        if (!st1_configured) {
-            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_CONV, false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            st1_configured = true;
-        }
-        DB_CUDA(launch_pdl(tc_kernel<TC_MODE_CONV, false, false, 1, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
+        tc_launch_variant(tc_kernel<MODE, false, true>, 1, n_ctas, L.total, s, tmA, tmB, a);
+    } else if (MODE == TC_MODE_CONV && epi == 1) {
+        tc_launch_variant(tc_kernel<TC_MODE_CONV, false, false, 1, 1>, 1, n_ctas, L.total, s, tmA, tmB, a);
+    } else if (MODE == TC_MODE_CONV && epi == 2) {
+        tc_launch_variant(tc_kernel<TC_MODE_CONV, false, false, 1, 2>, 1, n_ctas, L.total, s, tmA, tmB, a);
+    } else if (MODE == TC_MODE_CONV && epi == 3) {
+        tc_launch_variant(tc_kernel<TC_MODE_CONV, false, false, 1, 3>, 1, n_ctas, L.total, s, tmA, tmB, a);
     } else if (MODE == TC_MODE_WGRAD && a.halo) {
-        static bool wh_configured = false;
-        if (!wh_configured) {
-            DB_CUDA(cudaFuncSetAttribute(tc_kernel<TC_MODE_WGRAD, false, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            wh_configured = true;
-        }
-        DB_CUDA(launch_pdl(tc_kernel<TC_MODE_WGRAD, false, false, 1, false, true>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
+        tc_launch_variant(tc_kernel<TC_MODE_WGRAD, false, false, 1, 0, true>, 1, n_ctas, L.total, s, tmA, tmB, a);
     } else {
-        DB_CUDA(launch_pdl(tc_kernel<MODE>, dim3(n_ctas), dim3(TC_THREADS), L.total, s, tmA, tmB, a));
+        tc_launch_variant(tc_kernel<MODE>, 1, n_ctas, L.total, s, tmA, tmB, a);
     }
     {
         cudaError_t e = cudaGetLastError();
@@ -649,7 +630,7 @@ static int pick_stages(TcArgs& a, int64_t items = 0) {
     a.nacc = per_sm == 1 ? 2 : 1;
     a.stages = 2;
     TcSmemLayout L = tc_smem_layout(a);
-    const int extra = 2048 + a.st_cols * 32;   // barriers, alignment slack, epilogue statistics
+    const int extra = 2048 + a.st_cols * (a.ep_coef ? 48 : 32);   // barriers, alignment slack, epilogue statistics (+ coefficients)
     int st = (int)(((per_sm == 1 ? 225 : 110) * 1024 - extra) / L.stage_bytes);
     if (st > 8) st = 8;
     if (st < 2) {
@@ -782,6 +763,11 @@ struct ConvTc {
     void* out_staged = nullptr;                // fwd / dgrad: write the result as [N][H][W][Cp] bf16 here instead of NCHW fp32
     void* stats_ws = nullptr;                  // fwd + out_staged: statistics workspace of the batch norm reading the result
     float* acc_private = nullptr;              // wgrad: private accumulation scratch, finished later by the plan (deferred)
+    // epilogue companion (TcArgs::ep_src): fwd + out_staged: the addend of the residual sum this convolution feeds (mode 2);
+    // dgrad + out_staged: x and the forward coefficients of the batch norm whose backward pass reads this result (mode 3)
+    int ep_mode = 0;
+    const void* ep_src = nullptr;
+    const float* ep_coef = nullptr;
 };
 
 void stage_nchw_to_nhwc_bf16(const float* in, void* out, int N, int C, int64_t HW, cudaStream_t s) {
@@ -810,7 +796,27 @@ void conv_tc_set_staged(ConvTc* c, int input, const void* p) {
 }
 bool conv_tc_can_stage_output(const ConvTc* c) { return c && c->kind != CONV_WGRAD; }
 void conv_tc_set_stats_workspace(ConvTc* c, void* w) {
-    if (c && c->kind == CONV_FWD) c->stats_ws = w;
+    if (c && c->kind != CONV_WGRAD) c->stats_ws = w;
+}
+bool conv_tc_can_companion(const ConvTc* c, int mode) {
+    if (!c) return false;
+    const ConvGeom& g = c->g;
+    if (!((mode == 2 && c->kind == CONV_FWD) || (mode == 3 && c->kind == CONV_DGRAD))) return false;
+    // Only where the launch will be the halo pipeline (try_halo): a 3 x 3 unit-stride convolution on cta_group::2 pair tiles.
+    // Those instantiations run one CTA per SM and keep the whole companion row in registers; the others (two CTAs per SM, 80
+    // registers) would spill it.  (The backward statistics also need the single launch of a unit-stride feature gradient.)
+    if (g.R != 3 || g.S != 3 || g.u != 1 || g.v != 1 || g.ph != 1 || g.pw != 1) return false;
+    if (const char* e = getenv("DOPT_B200_HALO"))
+        if (atoi(e) < 2) return false;
+    const PixelBox& b = c->box;
+    const int m_tiles = b.tiles_n * b.tiles_p * b.tiles_q;
+    return pick_pair(m_tiles, pick_bn(mode == 2 ? g.K : g.C)) && (b.bn * b.bw) % 8 == 0 && b.bn * b.bh * b.bw == TC_BM;
+}
+void conv_tc_set_companion(ConvTc* c, int mode, const void* src, const float* coef) {
+    if (!c) return;
+    c->ep_mode = mode;
+    c->ep_src = src;
+    c->ep_coef = coef;
 }
 void conv_tc_set_staged_output(ConvTc* c, void* nhwc_bf16) {
     if (c && c->kind != CONV_WGRAD) c->out_staged = nhwc_bf16;
@@ -966,6 +972,12 @@ static void run_fwd(ConvTc* c, const float* x, const float* w, float* y, cudaStr
             a.st_cp = c->Kp;
             flat_stats_sink(c->stats_ws, g.K, &a.st_epoch, &a.st_sums, &a.st_copies);
         }
+        if (c->ep_mode == 2) {
+            DB_REQUIRE(c->ep_src, "convolution: the addend of its residual sum was not bound");
+            a.ep_src = c->ep_src;
+        }
+    } else {
+        DB_REQUIRE(c->ep_mode == 0, "convolution: an epilogue companion needs the NHWC bf16 result");
     }
     a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
     if (!getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) try_halo(a, &tmA, xh, g.N, g.H, g.W, Cp, g.C);
@@ -1068,6 +1080,17 @@ static void run_dgrad(ConvTc* c, const float* dy, const float* w, float* dx, cud
                 a.o_sn = (long long)g.H * g.W * Cp; a.o_sc = 1;
                 a.o_sh = (long long)g.u * g.W * Cp; a.o_sw = (long long)g.v * Cp;
                 a.out = c->out_staged;
+                if (c->ep_mode == 3) {
+                    DB_REQUIRE(g.u == 1 && g.v == 1 && c->ep_src && c->ep_coef && c->stats_ws,
+                               "convolutionFeaturesGrad: backward batch-norm statistics need x, the forward coefficients and the sink");
+                    a.ep_src = c->ep_src;
+                    a.ep_coef = c->ep_coef;
+                    a.st_cols = a.n_tiles * a.BN;
+                    a.st_cp = (int)Cp;
+                    flat_stats_sink(c->stats_ws, g.C, &a.st_epoch, &a.st_sums, &a.st_copies);
+                }
+            } else {
+                DB_REQUIRE(c->ep_mode == 0, "convolutionFeaturesGrad: an epilogue companion needs the NHWC bf16 result");
             }
             a.kbox = (a.pair && conv_kbox() == 2 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE")) ? 2 : 1;
             if (g.u == 1 && g.v == 1 && !getenv("DOPT_B200_DBG") && !getenv("DOPT_B200_TRACE"))

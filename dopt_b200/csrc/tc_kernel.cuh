@@ -92,6 +92,14 @@ struct TcArgs {
     // ---- CONV with NHWC bf16 output feeding a flat batchNormTrain (flat.cu): per-channel sum(y), sum(y^2) of the stored
     // (bf16-rounded) result, reduced in the epilogue -> shared memory -> one fp32 atomic per CTA, channel and sum into the
     // batch norm's statistics workspace (st_epoch / st_sums = FlatWs::epoch / sums, st_copies = kFlatCopies)
+    // ---- epilogue companion (tc_kernel<.., EPI = 2 / 3>): a tensor of the result's shape and layout (NHWC bf16) read by the
+    // epilogue, one 32-byte piece per accumulator row and 16-column chunk, prefetched one chunk ahead.
+    //   EPI 2  out = acc + src (the residual sum a convolution feeds; statistics, when on, are those of the sum)
+    //   EPI 3  out = acc (dy of a batch norm's backward pass); src = that batch norm's input x, ep_coef = its forward
+    //          coefficients [mean | a | b | istd]; the sums accumulated are sum(g), sum(g * (x - mean)) with g = acc gated by
+    //          [fma(x - mean, a, b) > 0] -- what flat_bn_stats_kernel<true, true> computes in a pass of its own
+    const void* ep_src;
+    const float* ep_coef;
     int st_cols;              // 0 = off; else n_tiles * BN: columns of the shared-memory accumulator
     int st_cp, st_copies;     // channels rounded up to 8; accumulator copies per buffer
     unsigned* st_epoch;
@@ -122,7 +130,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(const TcArgs& a) {
     L.stage_bytes = L.a_bytes + L.b_bytes;
     L.bar_off = L.stage_bytes * (uint32_t)a.stages;
     L.st_off = L.bar_off + 1024u /* barriers + tmem slot */;
-    L.total = L.st_off + (uint32_t)a.st_cols * 32u /* epilogue statistics: [4 lane quarters][2][st_cols] floats */ + 1024u /* slack */;
+    // epilogue statistics: [4 lane quarters][2][st_cols] floats (+ [st_cols] float4 coefficients with ep_coef)
+    L.total = L.st_off + (uint32_t)a.st_cols * (a.ep_coef ? 48u : 32u) + 1024u /* slack */;
     return L;
 }
 
@@ -175,11 +184,13 @@ __device__ __forceinline__ float tc_warp_cols16_sum(const float (&v)[16], int la
 
 // STATS (CONV mode, NHWC bf16 output): the epilogue also reduces per-channel sum / sum of squares of the stored result for the
 // batch norm that follows (TcArgs::st_*).
-template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1, bool STATS = false, bool HALO = false>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// EPI: 0 plain epilogue, 1 = statistics of the result (see above), 2 / 3 = epilogue companion (TcArgs::ep_src)
+template <int MODE, bool PAIR = false, bool INSTR = false, int KBOX = 1, int EPI = 0, bool HALO = false>
+__global__ void __launch_bounds__(TC_THREADS, (HALO && MODE == TC_MODE_CONV) ? 1 : 2) tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ TcArgs args_) {
     const TcArgs& args = args_;
+    constexpr bool STATS = EPI != 0;
     const unsigned long long* const trace_on = INSTR ? args_.trace : nullptr;   // compile-time null in the production build
     const int dbg = INSTR ? args_.dbg : 0;
     (void)trace_on;
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
     // everything above is local to the CTA (barriers, tensor memory, descriptor prefetch); global memory is first touched below,
     // once the preceding kernel of the stream has completed
     db::pdl_wait();
-    if (STATS) {
+    if (STATS && args.st_cols > 0) {
         st_e = *args.st_epoch;
         if (blockIdx.x == 0) {   // same protocol as flat_bn_stats_kernel: clear the buffer of the next launch, publish the epoch
             float* other = args.st_sums + (size_t)((st_e + 1u) & 1u) * args.st_copies * 2 * args.st_cp;
@@ -556,18 +567,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
         const int row = quarter * 32 + lane;                // accumulator row == TMEM lane
         constexpr int kStep = 16 * (TC_EPI_WARPS / 4);
         uint32_t t = 0;
+        float4* const ep_cf = (float4*)(st_smem + 8 * args.st_cols);   // EPI 3: {mean, a, b, -} per output channel
+        if (EPI == 3) {
+            const int C = args.Nout;
+            for (int c = (int)threadIdx.x - TC_WARP_EPI0 * 32; c < args.st_cols; c += 32 * TC_EPI_WARPS)
+                ep_cf[c] = c < C ? make_float4(args.ep_coef[c], args.ep_coef[C + c], args.ep_coef[2 * C + c], 0.f)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        }
         for (int cw = cw0; cw < total_cw; cw += cw_step) {
             const Work w = decode(cw);
-            uint32_t acc = 0;
-            if (w.n_iters > 0) {
-                acc = t & acc_mask;
-                const uint32_t use = t >> acc_shift;
-                ++t;
-                tcg::mbar_wait_relaxed(&tmem_full_bar[acc], use & 1u);
-                tcg::tc_fence_after();
-                if (trace_on && blockIdx.x == 0 && threadIdx.x == TC_WARP_EPI0 * 32 && t < 16) args.trace[512 + 2 * t] = clock64();
-            }
-            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
             // row -> output coordinates
             bool row_ok;
             long long row_off;
@@ -596,13 +605,54 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                 row_off = 0;
             }
             const int col0 = w.n_tile * BN;
+            // epilogue companion: this thread's share of the companion tile -- 32 bytes per 16-column chunk of its accumulator
+            // row -- is requested NOW, before the wait for the accumulator: the loads fly while the main loop of this tile is
+            // still running (a prefetch distance of one chunk left every chunk waiting for a full DRAM round trip:
+            // profiles/r02_summary.md).  Registers: 8 per chunk, up to kEpChunks chunks per warp -- the halo variants run one
+            // CTA per SM and have them.
+            constexpr int kEpChunks = EPI >= 2 ? 256 / (16 * (TC_EPI_WARPS / 4)) : 1;
+            uint4 cmp[kEpChunks][2];
+            if (EPI >= 2) {
+                const int ncols_c = min(BN, args.Nout - col0);   // valid columns of this tile
+                const __nv_bfloat16* src = (const __nv_bfloat16*)args.ep_src + row_off + col0;
+#pragma unroll
+                for (int i = 0; i < kEpChunks; ++i) {
+                    const int ch = half * 16 + i * 16 * (TC_EPI_WARPS / 4);
+                    cmp[i][0] = cmp[i][1] = make_uint4(0u, 0u, 0u, 0u);
+                    if (!row_ok || ch >= ncols_c) continue;
+                    if (ch + 16 <= ncols_c) {
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(cmp[i][0].x), "=r"(cmp[i][0].y), "=r"(cmp[i][0].z), "=r"(cmp[i][0].w) : "l"(src + ch));
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(cmp[i][1].x), "=r"(cmp[i][1].y), "=r"(cmp[i][1].z), "=r"(cmp[i][1].w) : "l"(src + ch + 8));
+                    } else {
+                        unsigned short h[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) h[j] = ch + j < ncols_c ? __ldg((const unsigned short*)(src + ch) + j) : (unsigned short)0;
+                        cmp[i][0] = make_uint4(h[0] | (uint32_t)h[1] << 16, h[2] | (uint32_t)h[3] << 16, h[4] | (uint32_t)h[5] << 16, h[6] | (uint32_t)h[7] << 16);
+                        cmp[i][1] = make_uint4(h[8] | (uint32_t)h[9] << 16, h[10] | (uint32_t)h[11] << 16, h[12] | (uint32_t)h[13] << 16, h[14] | (uint32_t)h[15] << 16);
+                    }
+                }
+            }
+            uint32_t acc = 0;
+            if (w.n_iters > 0) {
+                acc = t & acc_mask;
+                const uint32_t use = t >> acc_shift;
+                ++t;
+                tcg::mbar_wait_relaxed(&tmem_full_bar[acc], use & 1u);
+                tcg::tc_fence_after();
+                if (trace_on && blockIdx.x == 0 && threadIdx.x == TC_WARP_EPI0 * 32 && t < 16) args.trace[512 + 2 * t] = clock64();
+            }
+            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
             const uint32_t t_done = t;
             const bool have = w.n_iters > 0;
             const int ncols = (MODE == TC_MODE_WGRAD) ? (HALO ? 3 : w.q0) * BN : BN;   // TMEM columns to drain
             uint32_t r[16], rn[16];
             int cbt = half * 16;   // TMEM column of the chunk
             if (have && cbt < ncols) tcg::tmem_ld16(taddr + (uint32_t)cbt, rn);
-            for (; cbt < ncols; cbt += kStep) {
+#pragma unroll(EPI >= 2 ? kEpChunks : 1)
+            for (int it = 0; it < (EPI >= 2 ? kEpChunks : 0x7fffffff); ++it, cbt += kStep) {
+                if (cbt >= ncols) break;
                 if (have) {
                     tcg::tmem_ld_wait16(rn);
 #pragma unroll
@@ -625,6 +675,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                 if (STATS) {
                     // NHWC bf16 store first (r dies with it), then the statistics of what was stored -- the bf16-rounded
                     // values -- in place.  Rows outside the tensor and columns beyond Nout add 0.
+                    float ef[16];
+                    if (EPI >= 2) {
+                        const uint4 e0 = cmp[EPI >= 2 ? it : 0][0], e1 = cmp[EPI >= 2 ? it : 0][1];
+                        const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ef[2 * j] = __uint_as_float(ew[j] << 16);
+                            ef[2 * j + 1] = __uint_as_float(ew[j] & 0xffff0000u);
+                        }
+                    }
+                    if (EPI == 2) {   // the residual sum, added in fp32 before the one rounding to bf16
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), ef[j]));
+                    }
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -650,9 +714,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
                         v[2 * j] = (row_ok && (full || col0 + cb + 2 * j < args.Nout)) ? __uint_as_float(pk[j] << 16) : 0.f;
                         v[2 * j + 1] = (row_ok && (full || col0 + cb + 2 * j + 1 < args.Nout)) ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
                     }
+                    if (args.st_cols == 0) continue;   // (EPI 2 without a batch norm behind the sum)
+                    if (EPI == 3) {
+                        // v = stored dy (0 outside the tensor): gate it by the forward relu, recomputed like the apply pass does
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 cf = ep_cf[col0 + cb + j];
+                            const float d = ef[j] - cf.x;
+                            ef[j] = d;
+                            v[j] = fmaf(d, cf.y, cf.z) > 0.f ? v[j] : 0.f;
+                        }
+                    }
                     const float s1 = tc_warp_cols16_sum(v, lane);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= v[j];
+                    for (int j = 0; j < 16; ++j) v[j] *= (EPI == 3 ? ef[j] : v[j]);
                     const float s2 = tc_warp_cols16_sum(v, lane);
                     if (!(lane & 1)) {
                         float* slot = st_smem + (size_t)quarter * 2 * args.st_cols + col0 + cb + (lane >> 1);
@@ -696,7 +771,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_kernel(const __grid_constant
             if (trace_on && blockIdx.x == 0 && threadIdx.x == TC_WARP_EPI0 * 32 && t_done <= 16 && t_done > 0)
                 args.trace[512 + 2 * (t_done - 1) + 1] = clock64();
         }
-        if (STATS) {
+        if (STATS && args.st_cols > 0) {
             // all eight epilogue warps have added their tiles: one fire-and-forget atomic per channel and sum for this CTA
             asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             float* dst = args.st_sums + ((size_t)(st_e & 1u) * args.st_copies + blockIdx.x % args.st_copies) * 2 * args.st_cp;

@@ -331,6 +331,78 @@ def test_bf16_interior_pass_engages_and_agrees_with_fp32_storage(monkeypatch, ca
             assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.2 * du, a.shape
 
 
+def _interior_run(monkeypatch, capfd, env, steps=2, net=(16, 4, 32, 16, 10)):
+    for k in ("DOPT_B200_EPI_ADD", "DOPT_B200_EPI_BNGRAD"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("DOPT_B200_PLAN_DUMP", "1")
+    H.reset()
+    H.set_math(db.MATH_BF16)
+    H.set_plan_flags(FUSE | GRAPH | INTERIOR)
+    loss, extra, netw, feed = _wrn(*net)()
+    capfd.readouterr()
+    upd = H.Updater(H.SGD, [loss] + extra, network=netw, hyper=[H.float32((), [0.05]), H.float32((), [0.9])])
+    init = [p.get().copy() for p in netw.params]
+    outs = [upd.step(feed(s)) for s in range(steps)]
+    dump = capfd.readouterr().err
+    line = [l for l in dump.splitlines() if l.startswith("PLAN residency") and "epilogue" in l][0]
+    n_add, n_bn = [int(t) for t in line.replace(",", " ").split() if t.isdigit()]
+    return outs, [p.get().copy() for p in netw.params], init, upd.stats(), (n_add, n_bn)
+
+
+def test_backward_bn_statistics_in_the_feature_gradient_epilogue(monkeypatch, capfd):
+    """Plan pass H2 (opt-in, DOPT_B200_EPI_BNGRAD=1: measured slower than the separate statistics launch on the WRN-28-10
+    shapes, profiles/r02_summary.md): the unit-stride convolutionFeaturesGrad that writes dy of a flat batchNormGrad accumulates sum(g) and
+    sum(g * (x - mean)) in its epilogue (tc_kernel<.., EPI = 3>) from the bf16 values it stores -- the same values the
+    statistics kernel would read back -- so only the fp32 summation order differs: the forward pass of step 0 is untouched
+    (bit-identical loss and predictions) and the parameters agree within fp32 rounding of the sums (1e-4 of the update;
+    the filter gradients' fp32 atomics alone give ~1e-5 from run to run)."""
+    base = {"DOPT_B200_EPI_BNGRAD": "1"}
+    off = {}
+
+    def worst_update_difference(pa, pb, init):
+        worst = 0.0
+        for a, b, i0 in zip(pa, pb, init):
+            du = float(np.linalg.norm((a - i0).astype(np.float64)))
+            if du > 1e-12:
+                worst = max(worst, float(np.linalg.norm((a - b).astype(np.float64))) / du)
+        return worst
+    # one step: the update is lr * gradient at identical parameters.  Two runs of the SAME plan already differ -- the forward
+    # statistics and the filter gradients are summed with fp32 atomics, a bf16 rounding flips here and there -- so the bound is
+    # relative to that measured run-to-run noise.
+    o0, p0, init, st0, c0 = _interior_run(monkeypatch, capfd, off, steps=1)
+    o0b, p0b, _, _, _ = _interior_run(monkeypatch, capfd, off, steps=1)
+    o1, p1, _, st1, c1 = _interior_run(monkeypatch, capfd, base, steps=1)
+    assert c0 == (0, 0) and c1[0] == 0 and c1[1] >= 8, (c0, c1)   # WRN-16-4: 6 blocks, 9 of 11 flat backward batch norms
+    assert st1["launches"] <= st0["launches"] - c1[1]           # one statistics launch less per fused batch norm
+    assert abs(float(o0[0][0]) - float(o1[0][0])) <= 5e-4 * abs(float(o0[0][0]))
+    assert np.abs(o0[0][1] - o1[0][1]).max() <= 5e-3
+    noise = worst_update_difference(p0, p0b, init)
+    worst = worst_update_difference(p0, p1, init)
+    print("backward statistics in the epilogue: worst gradient difference", worst, "run-to-run noise", noise)
+    assert worst <= max(2e-2, 4 * noise)
+
+
+def test_residual_sum_in_the_convolution_epilogue(monkeypatch, capfd):
+    """Plan pass H1 (opt-in, DOPT_B200_EPI_ADD=1: measured slower than the separate add, profiles/r02_summary.md): the second convolution of a residual block adds the block's input in its epilogue (tc_kernel<.., EPI = 2>,
+    fp32 add, ONE rounding to bf16) instead of storing its bf16 result for a separate add kernel (two roundings).  Stated
+    tolerance: the double rounding it removes, i.e. loss within 1e-2 relative, predictions within 3e-2, parameter updates
+    within 0.2 of the update (the same bounds as bf16 interior storage against fp32 storage)."""
+    o0, p0, init, st0, c0 = _interior_run(monkeypatch, capfd, {})
+    o1, p1, _, st1, c1 = _interior_run(monkeypatch, capfd, {"DOPT_B200_EPI_ADD": "1"})
+    assert c0 == (0, 0) and c1[1] == 0 and c1[0] >= 5, (c0, c1)   # WRN-16-4: 6 residual sums, the last one feeds a legacy kernel
+    assert st1["launches"] <= st0["launches"] - c1[0]
+    assert st1["device_bytes"] < st0["device_bytes"]
+    for a, b in zip(o0, o1):
+        assert abs(float(a[0]) - float(b[0])) <= 1e-2 * abs(float(a[0]))
+        assert np.abs(a[1] - b[1]).max() <= 3e-2
+    for a, b, i0 in zip(p0, p1, init):
+        du = float(np.linalg.norm((a - i0).astype(np.float64)))
+        if du > 1e-12:
+            assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.2 * du, a.shape
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16-interior"])
 def test_wrn_28_10_headline_graph_first_steps(mode):
     """The benchmarked graph itself (examples/cifar100.d:33-49 with wideResNet(features, 28, 10): 28 convolutions, 25 batch

@@ -35,7 +35,7 @@ if WORLD > 1:
     # the gradient all-reduces get a fixed, small number of CTAs and the tensor-core kernels leave exactly those SMs free while
     # a bucket is in flight (dopt_b200/csrc/comm.cu, tc_host.cu); NCCL reads the variable when the process creates its first
     # communicator -- torch.distributed's, below -- so it has to be in the environment now
-    os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "4"))
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "16"))
     os.environ.setdefault("NCCL_MIN_NCHANNELS", os.environ["NCCL_MAX_NCHANNELS"])
     # one process per GPU, each seeing exactly its own device as ordinal 0 -- the reference hard-codes ordinal 0
     # (cuda/source/dopt/cuda/package.d:44), so this is also how the D host would be launched
@@ -362,6 +362,21 @@ def main():
             tc = tc[2 * len(tc) // 3:]
             f.write("tc_kernel launches of one step, in order:\n")
             f.write(" ".join("%s:%.0f" % (n.replace("tc_kernel", ""), d) for n, d in tc) + "\n")
+        # every device activity of the last traced step with its stream: start (us from the step's first kernel), duration, stream
+        try:
+            kev = [k for k in prof.profiler.kineto_results.events() if "cuda" in str(k.device_type()).lower()]
+            kev.sort(key=lambda k: k.start_ns())
+            starts = [i for i, k in enumerate(kev) if "pack_filters_multi" in k.name() or "gate_step_begin" in k.name()]
+            first = [i for j, i in enumerate(starts) if j == 0 or starts[j - 1] < i - 50]   # first launch of each step
+            lo = first[-1] if first else 0
+            t0 = kev[lo].start_ns()
+            with open(args.timeline + ".raw", "w") as f:
+                f.write("# start_us dur_us stream name   (last of 3 traced steps)\n")
+                for k in kev[lo:]:
+                    nm = k.name().replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("db::", "")
+                    f.write("%9.1f %8.1f %4d %s\n" % ((k.start_ns() - t0) / 1e3, k.duration_ns() / 1e3, k.device_resource_id(), nm[:80]))
+        except Exception as ex:   # diagnostics only
+            sys.stderr.write("timeline raw dump failed: %r\n" % (ex,))
         return
 
     # ---- timed: device-resident inputs ----

@@ -57,7 +57,7 @@ static void load_nccl() {
 #undef SYM
 }
 static void pick_channels() {
-    int k = 4;
+    int k = 16;   // measured at 2 GPUs (profiles/r02_summary.md): 82 / 153 / 268 GB/s with 4 / 8 / 16 channels
     if (const char* e = getenv("DOPT_B200_COMM_CHANNELS")) k = atoi(e);
     if (k <= 0) {   // 0: NCCL's own choice, no SM reservation
         g_channels = 0;

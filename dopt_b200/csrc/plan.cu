@@ -25,6 +25,7 @@
 #include "flat.cuh"
 #include "fused.cuh"
 #include "pointwise.cuh"
+#include "tc.cuh"
 #include <algorithm>
 #include <map>
 #include <queue>
@@ -39,7 +40,6 @@ void tc_prof_read(double* us, int64_t* launches);
 void allreduce_mean(float* buf, int64_t n, cudaStream_t s);
 int comm_world();
 int comm_reserved_sms();
-void tc_set_reserved_sms(int k);
 
 namespace {
 
@@ -141,6 +141,12 @@ struct dopt_b200_plan_s {
     std::vector<db::FzLaunch> launches;
     std::vector<std::vector<int>> launch_regions;   // regions of each launch, row order
     std::vector<char> direct_out;                   // per plan output: written in place by a fused region
+    // small plan outputs that are not written in place (data-parallel: the averaged batch-norm running statistics sit in a
+    // bucket arena) reach the caller's buffers through ONE multi-tensor copy launch instead of a cudaMemcpyAsync each
+    struct PostCopy { void* dst; const void* src; int64_t n4; };
+    std::vector<PostCopy> post_rows;
+    std::vector<char> post_batched;                 // per plan output: covered by post_rows
+    PostCopy* post_dev = nullptr;
     std::vector<db::Bucket> buckets;
     std::vector<db::Stage> stages;
     // filters (plan variables) packed for the tensor-core convolutions by one launch at the start of the step
@@ -166,11 +172,17 @@ struct dopt_b200_plan_s {
         db::WgradFinish* dev = nullptr;
         int tiles = 0;
         size_t smem = 0;
+        int bucket = -1;            // gradient bucket its results are reduced in (-1: not exchanged)
+        bool side_ok = false;       // nothing but that bucket's in-place all-reduce reads its results: the launch may stay on the
+                                    // side stream behind its filter gradients, the communication stream waits for `done`
+        bool on_side = false;       // (this execution)
+        cudaEvent_t done = nullptr;
     };
     std::vector<FinishGroup> finishes;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     // side stream: filter gradients whose only reader is a deferred finish launch run here, beside the feature-gradient chain
+    db::TcGate gate;            // SM reservation gate of the tensor-core kernels (data-parallel plans)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_fork = nullptr, side_join = nullptr;
     int64_t device_bytes = 0;
@@ -204,9 +216,13 @@ struct dopt_b200_plan_s {
             if (m.dev) cudaFree(m.dev);
             if (m.partial) cudaFree(m.partial);
         }
-        for (auto& f : finishes)
+        for (auto& f : finishes) {
             if (f.dev) cudaFree(f.dev);
+            if (f.done) cudaEventDestroy(f.done);
+        }
         if (packs_dev) cudaFree(packs_dev);
+        if (post_dev) cudaFree(post_dev);
+        db::tc_gate_destroy(&gate);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
         if (comm_join) cudaEventDestroy(comm_join);
@@ -962,12 +978,31 @@ static void form_buckets(Plan& p) {
     std::sort(members.begin(), members.end(), [&](int a, int b) {
         return std::make_pair(N[a].lvl, a) < std::make_pair(N[b].lvl, b);
     });
-    static const int64_t kBucketBytes = 32ll << 20;
+    // Buckets close at 32 MB -- large enough for the all-reduce to run at its bandwidth, small enough to start early -- but the
+    // LAST all-reduce of the step cannot overlap anything: the gradients that are produced last (the first layers of the net)
+    // go into a geometric tail of small buckets (a cut where 24, 6 and 1.5 MB remain), so that what is left to exchange after
+    // the last backward kernel is a ~1 MB message.  DOPT_B200_BUCKET_MB / DOPT_B200_NO_BUCKET_TAIL change the policy.
+    static const int64_t kBucketBytes = []() {
+        const char* e = getenv("DOPT_B200_BUCKET_MB");
+        return (int64_t)(e && atoi(e) > 0 ? atoi(e) : 32) << 20;
+    }();
+    static const bool tail_on = !getenv("DOPT_B200_NO_BUCKET_TAIL");
+    int64_t remaining = 0;
+    for (int m : members) remaining += (N[m].bytes + 255) / 256 * 256;
+    const int64_t cuts[3] = {24ll << 20, 6ll << 20, 3ll << 19};
+    int next_cut = 0;
     for (int m : members) {
-        if (p.buckets.empty() || p.buckets.back().bytes >= kBucketBytes) p.buckets.push_back(Bucket());
+        bool fresh = p.buckets.empty() || p.buckets.back().bytes >= kBucketBytes;
+        while (tail_on && next_cut < 3 && remaining <= cuts[next_cut]) {
+            fresh = fresh || p.buckets.back().bytes > 0;
+            ++next_cut;
+        }
+        if (fresh) p.buckets.push_back(Bucket());
         Bucket& b = p.buckets.back();
         b.members.push_back(m);
-        b.bytes += (N[m].bytes + 255) / 256 * 256;
+        const int64_t sz = (N[m].bytes + 255) / 256 * 256;
+        b.bytes += sz;
+        remaining -= sz;
         N[m].bucket = (int)p.buckets.size() - 1;
     }
     for (auto& n : N)
@@ -1715,9 +1750,22 @@ static void build(Plan& p) {
                     p.finishes.emplace_back();
                 }
                 n.finish_group = it->second;
+                p.finishes[it->second].bucket = key[i];
                 p.finishes[it->second].nodes.push_back((int)i);
                 p.finishes[it->second].rows.push_back(row);
                 p.device_bytes += (int64_t)row.RS * row.K * row.C * 4;
+            }
+            for (auto& f : p.finishes) f.side_ok = f.bucket >= 0;
+            for (size_t u = 0; u < N.size(); ++u) {
+                if (!N[u].needed) continue;
+                for (int d : effective_deps(N[u])) {
+                    const int r = root_of(p, d);
+                    if (N[r].finish_group < 0) continue;
+                    auto& f = p.finishes[N[r].finish_group];
+                    if (N[u].bucket == f.bucket && N[u].alias_of >= 0) continue;   // the in-place all-reduce itself
+                    if (crosses_reduce(p, d)) continue;   // reads the reduced value: ordered behind the bucket (join_comm)
+                    f.side_ok = false;
+                }
             }
         }
         if (!getenv("DOPT_B200_NO_ABSORB")) absorb(p);
@@ -1917,10 +1965,29 @@ static const char* item_label(const Plan& p, const Item& it) {
     }
 }
 
+// one CTA per row: dst[i] = src[i] for n4 32-bit words (rows are small: per-channel statistics)
+__global__ void __launch_bounds__(128) post_copy_kernel(const Plan::PostCopy* __restrict__ rows) {
+    const Plan::PostCopy r = rows[blockIdx.x];
+    const uint32_t* src = (const uint32_t*)r.src;
+    uint32_t* dst = (uint32_t*)r.dst;
+    for (int64_t i = threadIdx.x; i < r.n4; i += blockDim.x) dst[i] = src[i];
+}
+
 // `only`: diagnostics (dopt_b200_plan_replay_class) -- issue just the items booked under these op types, nothing else
 static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only = nullptr) {
     auto& N = p.nodes;
     bool comm_pending = false;
+    int buckets_enqueued = 0;
+    // SM reservation gate: opt-in (DOPT_B200_GATE_SMS=1).  Measured with 16 NCCL channels (profiles/r02_summary.md): 5.88 ms per
+    // step with the gate against 5.73 ms without at 2 GPUs, 6.12 against 6.00 ms at 8 -- the all-reduce kernels spend most of
+    // their life waiting for peers, and leaving their SMs idle costs the convolutions more than sharing them does.
+    if (!p.buckets.empty() && comm_reserved_sms() > 0 && !p.profiling && !only && getenv("DOPT_B200_GATE_SMS")) {
+        if (!p.gate.dev) tc_gate_create(&p.gate, comm_reserved_sms());
+        tc_gate_step_begin(&p.gate, s);
+        tc_set_gate(&p.gate);
+    } else {
+        tc_set_gate(nullptr);
+    }
     // Side stream.  A tensor-core filter gradient with a deferred finish reads two staged activations nothing overwrites and
     // accumulates into a private scratch only the finish launch reads, and nothing on the feature-gradient chain
     // (batchNormGrad -> convolutionFeaturesGrad -> ...) waits for it.  Issued on a second stream (a parallel branch of the
@@ -1956,7 +2023,7 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
             DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
             DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
             comm_pending = false;
-            tc_set_reserved_sms(0);
+            p.gate.need = 0;
         }
         if (it.kind == ITEM_BUCKET) {
             // one all-reduce for the whole bucket, on the communication stream so that it overlaps the rest of backward
@@ -1968,14 +2035,22 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
             }
             DB_CUDA(cudaEventRecord(p.comm_fork, s));
             DB_CUDA(cudaStreamWaitEvent(p.comm_stream, p.comm_fork, 0));
+            for (auto& f : p.finishes)
+                if (f.bucket == it.id && f.on_side) DB_CUDA(cudaStreamWaitEvent(p.comm_stream, f.done, 0));
             allreduce_mean((float*)b.arena, b.bytes / 4, p.comm_stream);
             comm_pending = true;
-            tc_set_reserved_sms(comm_reserved_sms());   // the tensor-core launches that follow leave SMs to the collective
+            if (p.gate.dev) {
+                // the tensor-core launches that follow leave SMs to the collective until its completion counter says all the
+                // all-reduces enqueued so far have finished
+                tc_gate_comm_done(&p.gate, p.comm_stream);
+                ++buckets_enqueued;
+                p.gate.need = buckets_enqueued;
+            }
             if (p.profiling) {   // serialise so that the profile attributes the time
                 DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
                 DB_CUDA(cudaStreamWaitEvent(s, p.comm_join, 0));
                 comm_pending = false;
-                tc_set_reserved_sms(0);
+                p.gate.need = 0;
             }
             label = "allreduceBucket";
         } else if (it.kind == ITEM_MSUM) {
@@ -1991,8 +2066,19 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
             label = "stageNHWC";
         } else if (it.kind == ITEM_WFINISH) {
             auto& f = p.finishes[it.id];
-            side_join_now();
-            wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, s);
+            static const bool side_finish = !getenv("DOPT_B200_NO_SIDE_FINISH");
+            f.on_side = side_finish && side_pending && f.side_ok && !p.profiling && !only;
+            if (f.on_side) {
+                // data-parallel: only the bucket's all-reduce reads these gradients.  The launch stays on the side stream behind
+                // its filter gradients and the communication stream waits for it -- the feature-gradient chain on the main
+                // stream does not join the side stream once per bucket (measured: profiles/r02_summary.md)
+                wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, p.side_stream);
+                if (!f.done) DB_CUDA(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+                DB_CUDA(cudaEventRecord(f.done, p.side_stream));
+            } else {
+                side_join_now();
+                wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, s);
+            }
             label = "filtersGradFinish";
         } else if (it.kind == ITEM_UNSTAGE) {
             const Stage& st = p.stages[it.id];
@@ -2034,6 +2120,7 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
                     DB_CUDA(cudaEventCreateWithFlags(&p.side_fork, cudaEventDisableTiming));
                     DB_CUDA(cudaEventCreateWithFlags(&p.side_join, cudaEventDisableTiming));
                 }
+                p.gate.side = p.side_stream;
                 DB_CUDA(cudaEventRecord(p.side_fork, s));
                 DB_CUDA(cudaStreamWaitEvent(p.side_stream, p.side_fork, 0));
                 n.kernel->run(in, (int)n.deps.size(), n.ptr, p.side_stream);
@@ -2063,7 +2150,7 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
             p.prof_cnt[labels[i]] += 1;
         }
     }
-    tc_set_reserved_sms(0);
+    tc_set_gate(nullptr);
     side_join_now();
     if (comm_pending) {   // nothing may be left running on the side stream when the step (or the capture) ends
         DB_CUDA(cudaEventRecord(p.comm_join, p.comm_stream));
@@ -2159,13 +2246,38 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
             for (size_t i = 0; i < p.packs.size(); ++i) p.packs[i].w = (const float*)N[p.pack_users[i].second].ptr;
             DB_CUDA(cudaMemcpy(p.packs_dev, p.packs.data(), p.packs.size() * sizeof(FilterPack), cudaMemcpyHostToDevice));
         }
+        p.post_rows.clear();
+        p.post_batched.assign((size_t)n_rets, 0);
+        for (int i = 0; i < n_rets; ++i) {
+            const Node& o = N[p.outputs[i]];
+            if (p.direct_out[i] || o.bytes <= 0 || rets[i] == o.ptr || o.bytes % 4 != 0 || o.bytes > (64 << 10)) continue;
+            if (((uintptr_t)rets[i] | (uintptr_t)o.ptr) & 3) continue;
+            p.post_rows.push_back({rets[i], o.ptr, o.bytes / 4});
+            p.post_batched[i] = 1;
+        }
+        bool hazard = false;   // the rows run concurrently: no destination may overlap another row's source
+        for (auto& a : p.post_rows)
+            for (auto& b : p.post_rows)
+                if (&a != &b && (const char*)a.dst < (const char*)b.src + b.n4 * 4 && (const char*)b.src < (const char*)a.dst + a.n4 * 4) hazard = true;
+        if (p.post_rows.size() < 4 || hazard) {   // not worth a table / keep the sequential copies
+            p.post_rows.clear();
+            p.post_batched.assign((size_t)n_rets, 0);
+        } else {
+            if (p.post_dev) cudaFree(p.post_dev);
+            DB_CUDA(cudaMalloc(&p.post_dev, p.post_rows.size() * sizeof(Plan::PostCopy)));
+            DB_CUDA(cudaMemcpy(p.post_dev, p.post_rows.data(), p.post_rows.size() * sizeof(Plan::PostCopy), cudaMemcpyHostToDevice));
+        }
         p.bound_key = key;
     }
     auto body = [&](cudaStream_t st) {
         run_items(p, st);
+        if (!p.post_rows.empty()) {
+            post_copy_kernel<<<(unsigned)p.post_rows.size(), 128, 0, st>>>(p.post_dev);
+            DB_LAUNCH_CHECK();
+        }
         for (int i = 0; i < n_rets; ++i) {
             const Node& o = N[p.outputs[i]];
-            if (p.direct_out[i]) continue;
+            if (p.direct_out[i] || (i < (int)p.post_batched.size() && p.post_batched[i])) continue;
             if (o.bytes > 0 && rets[i] != o.ptr) {
                 DB_CUDA(cudaMemcpyAsync(rets[i], o.ptr, (size_t)o.bytes, cudaMemcpyDeviceToDevice, st));
                 count_launch();

@@ -41,4 +41,20 @@ bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row);
 // the plan may run it on a second stream beside the feature-gradient chain
 bool conv_tc_side_stream_safe(const ConvTc* c);
 
+
+// SM reservation gate of a data-parallel plan (tc_host.cu / tc_kernel.cuh: TcArgs::gate_*): while armed (need > 0), every full
+// persistent grid launched through tc_launch decides on the device whether its last `sms x CTAs-per-SM` CTAs take part.
+struct TcGate {
+    unsigned* dev = nullptr;        // [0] all-reduces completed (ever) | [1] its value at step start | [2..5] snapshots
+    cudaStream_t side = nullptr;    // launches on this stream form a chain of their own (the plan's filter-gradient stream)
+    int sms = 0;                    // SMs the collective's CTAs occupy (= its channel count)
+    int need = 0;                   // all-reduces enqueued so far in this step; 0 = gate not armed
+    int idx[2] = {0, 0};            // gated launches so far on the main / side chain
+};
+void tc_gate_create(TcGate* g, int sms);
+void tc_gate_destroy(TcGate* g);
+void tc_gate_step_begin(TcGate* g, cudaStream_t s);      // first launch of the step (main stream)
+void tc_gate_comm_done(TcGate* g, cudaStream_t comm);    // behind every all-reduce on the communication stream
+void tc_set_gate(TcGate* g);                             // the gate tc_launch consults (nullptr: none)
+
 }  // namespace db

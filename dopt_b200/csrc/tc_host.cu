@@ -481,13 +481,46 @@ void tc_prof_read(double* us, int64_t* launches) {
     *launches = (int64_t)g_tc_ev_used;
 }
 
-// SMs left to a collective that runs beside the tensor-core kernels (plan.cu sets it while a gradient-bucket all-reduce may be
-// in flight).  The persistent grid is statically scheduled -- every CTA owns a fixed share of the tiles -- so one CTA that
-// shares its SM with an NCCL channel stretches the whole launch (8 % per convolution, profiles/r01c_conv_bisect.md section 7).
-// With k SMs reserved the grid shrinks to 148 - k CTAs, each asking for the full 227 KB of shared memory so that it cannot
-// be placed next to an NCCL CTA: the two kernels then run on disjoint SMs.
-static int g_reserved_sms = 0;
-void tc_set_reserved_sms(int k) { g_reserved_sms = k < 0 ? 0 : k; }
+// SMs left to a collective that runs beside the tensor-core kernels (plan.cu arms the gate while gradient-bucket all-reduces may
+// be in flight).  The persistent grid is statically scheduled -- every CTA owns a fixed share of the tiles -- so one CTA that
+// shares its SM with an NCCL channel, or queues behind one, stretches the whole launch (8 % per convolution,
+// profiles/r01c_conv_bisect.md section 7).  Round 1 shrank the grid on the host from the first bucket to the end of backward
+// (11 % of the SMs lost for ~3 ms with 16 channels); now the grid is always launched in full and the kernel itself drops its last
+// `sms x CTAs-per-SM` CTAs only while the collective's completion counter says an all-reduce is still running
+// (TcArgs::gate_*, tc_kernel.cuh).  Each CTA asks for the full 227 KB of shared memory so that it cannot be placed next to an
+// NCCL CTA: the two kernels run on disjoint SMs.
+static TcGate* g_gate = nullptr;
+void tc_set_gate(TcGate* g) { g_gate = g; }
+
+namespace {
+__global__ void gate_step_begin_kernel(unsigned* w) {   // [0] done | [1] base | [2..5] snapshots of two streams
+    const unsigned d = w[0];
+    w[1] = d;
+    w[2] = w[3] = w[4] = w[5] = d;
+}
+__global__ void gate_comm_done_kernel(unsigned* w) { w[0] += 1u; }
+}  // namespace
+void tc_gate_create(TcGate* g, int sms) {
+    DB_CUDA(cudaMalloc((void**)&g->dev, 8 * sizeof(unsigned)));
+    DB_CUDA(cudaMemset(g->dev, 0, 8 * sizeof(unsigned)));
+    g->sms = sms;
+    g->need = 0;
+    g->idx[0] = g->idx[1] = 0;
+}
+void tc_gate_destroy(TcGate* g) {
+    if (g->dev) cudaFree(g->dev);
+    g->dev = nullptr;
+}
+void tc_gate_step_begin(TcGate* g, cudaStream_t s) {
+    g->need = 0;
+    g->idx[0] = g->idx[1] = 0;
+    gate_step_begin_kernel<<<1, 1, 0, s>>>(g->dev);
+    DB_LAUNCH_CHECK();
+}
+void tc_gate_comm_done(TcGate* g, cudaStream_t comm) {
+    gate_comm_done_kernel<<<1, 1, 0, comm>>>(g->dev);
+    DB_LAUNCH_CHECK();
+}
 
 // one instantiation of the kernel: opt in to the full shared memory once, launch with the cluster size it needs and as a
 // programmatic dependent of the previous kernel in the stream
@@ -538,7 +571,8 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     }
     TcSmemLayout L = tc_smem_layout(a);
     DB_REQUIRE(L.total <= 227 * 1024, "tcgen05 kernel: shared memory budget exceeded");
-    if (g_reserved_sms > 0 && a.nacc == 2) L.total = 227 * 1024;   // one CTA per SM: keep the SM to itself
+    const bool gated = g_gate && g_gate->dev && g_gate->need > 0 && g_gate->sms > 0;
+    if (gated && a.nacc == 2) L.total = 227 * 1024;   // one CTA per SM: keep the SM to itself
     if (g_tc_prof) {
         if (g_tc_ev_used == g_tc_ev.size()) {
             cudaEvent_t e0, e1;
@@ -551,10 +585,25 @@ static void tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     // persistent grid: one CTA (pair) per SM, each looping over its share of the n_ctas work items
     {
         const int cs = a.pair ? 2 : 1;
-        const int sms = std::max(2, sm_count() - std::min(g_reserved_sms, sm_count() / 2));
-        int clusters = std::min(n_ctas / cs, (a.nacc == 2 ? 1 : 2) * (sms / cs * cs) / cs);
+        const int per_sm = a.nacc == 2 ? 1 : 2;
+        const int full = per_sm * (sm_count() / cs * cs) / cs;
+        int clusters = std::min(n_ctas / cs, full);
         if (clusters < 1) clusters = 1;
         n_ctas = clusters * cs;
+        if (gated && clusters == full) {
+            // a full grid: its tail is droppable (decided on the device, see TcGate)
+            const int drop = std::min(g_gate->sms, sm_count() / 2) * per_sm / cs * cs;
+            if (drop > 0 && drop < n_ctas) {
+                const int chain = (s == g_gate->side) ? 1 : 0;
+                const int i = g_gate->idx[chain]++;
+                a.gate_rd = g_gate->dev + 2 + chain * 2 + (i & 1);
+                a.gate_wr = g_gate->dev + 2 + chain * 2 + ((i + 1) & 1);
+                a.gate_done = g_gate->dev;
+                a.gate_base = g_gate->dev + 1;
+                a.gate_need = g_gate->need;
+                a.gate_drop = drop;
+            }
+        }
     }
     // epilogue flavour: 0 plain, 1 statistics of the result, 2 result + companion (residual sum), 3 gated backward statistics
     const int epi = a.ep_src ? (a.ep_coef ? 3 : 2) : (a.st_cols > 0 ? 1 : 0);

@@ -100,6 +100,19 @@ struct TcArgs {
     //          [fma(x - mean, a, b) > 0] -- what flat_bn_stats_kernel<true, true> computes in a pass of its own
     const void* ep_src;
     const float* ep_coef;
+    // ---- SM reservation gate (data-parallel plans, tc_host.cu: TcGate).  While a gradient bucket's all-reduce is running, its
+    // CTAs hold `gate_drop / CTAs-per-SM` SMs; a persistent grid with a static split must then not count on those SMs (its CTAs
+    // would queue behind the collective and double the kernel's duration).  The grid is always launched in full; whether the
+    // last gate_drop CTAs take part in the split is decided on the device from a snapshot of the collective's completion
+    // counter: gate_rd was written by the previous tensor-core kernel of this stream (complete before any CTA of this one
+    // passes griddepcontrol.wait, so every CTA -- also one placed late -- reads the same value) and gate_wr is written by this
+    // kernel for the next one.  gate_need = all-reduces enqueued so far in this step; they are all complete when
+    // snapshot - *gate_base >= gate_need.
+    const unsigned* gate_rd;   // nullptr: no gate
+    unsigned* gate_wr;
+    const unsigned* gate_done; // the communication stream's completion counter
+    const unsigned* gate_base; // its value at the start of the step
+    int gate_need, gate_drop;
     int st_cols;              // 0 = off; else n_tiles * BN: columns of the shared-memory accumulator
     int st_cp, st_copies;     // channels rounded up to 8; accumulator copies per buffer
     unsigned* st_epoch;
@@ -194,6 +207,16 @@ __global__ void __launch_bounds__(TC_THREADS, (HALO && MODE == TC_MODE_CONV) ? 1
     const unsigned long long* const trace_on = INSTR ? args_.trace : nullptr;   // compile-time null in the production build
     const int dbg = INSTR ? args_.dbg : 0;
     (void)trace_on;
+    // SM reservation gate, part 1: a CTA (pair) of the droppable tail decides before it sets anything up -- if the collective is
+    // still running it leaves at once (it typically got its SM only after the rest of the grid had finished).  Both CTAs of a
+    // pair read the same word, so they agree.
+    bool gate_reserved = false;
+    if (args.gate_rd != nullptr && (int)blockIdx.x >= (int)gridDim.x - args.gate_drop) {
+        db::pdl_trigger();
+        db::pdl_wait();
+        gate_reserved = (int)(*(const volatile unsigned*)args.gate_rd - *args.gate_base) < args.gate_need;
+        if (gate_reserved) return;
+    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcSmemLayout L = tc_smem_layout(args);
@@ -226,7 +249,8 @@ __global__ void __launch_bounds__(TC_THREADS, (HALO && MODE == TC_MODE_CONV) ? 1
     // work items of this CTA (cluster): cw = cluster id, cluster id + #clusters, ...
     const int m_groups = args.m_tiles / csize;
     const int total_cw = m_groups * args.splits * args.n_tiles;
-    const int cw0 = (int)blockIdx.x / csize, cw_step = (int)gridDim.x / csize;
+    const int cw0 = (int)blockIdx.x / csize;
+    int cw_step = (int)gridDim.x / csize;   // (reduced below when the gate reserves SMs)
     struct Work {
         int m_tile, n_tile, split, it_begin, n_iters, img0, p0, q0, wg_tap;
     };
@@ -293,6 +317,10 @@ __global__ void __launch_bounds__(TC_THREADS, (HALO && MODE == TC_MODE_CONV) ? 1
     // everything above is local to the CTA (barriers, tensor memory, descriptor prefetch); global memory is first touched below,
     // once the preceding kernel of the stream has completed
     db::pdl_wait();
+    if (args.gate_rd != nullptr) {
+        // SM reservation gate, part 2: the CTAs that stay split the work over the reduced grid when the tail dropped out
+        if ((int)(*(const volatile unsigned*)args.gate_rd - *args.gate_base) < args.gate_need) cw_step -= args.gate_drop / csize;
+    }
     if (STATS && args.st_cols > 0) {
         st_e = *args.st_epoch;
         if (blockIdx.x == 0) {   // same protocol as flat_bn_stats_kernel: clear the buffer of the next launch, publish the epoch
@@ -784,6 +812,8 @@ __global__ void __launch_bounds__(TC_THREADS, (HALO && MODE == TC_MODE_CONV) ? 1
         }
     }
 
+    // SM reservation gate, part 3: the snapshot for the next tensor-core kernel of this stream, taken as late as possible
+    if (args.gate_rd != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *args.gate_wr = *(const volatile unsigned*)args.gate_done;
     __syncwarp();   // the single-lane producer / issuer loops diverged their warps; the cluster barrier is warp-aligned
     tcg::tc_fence_before();
     if constexpr (pair) tcg::cluster_sync();   // nobody leaves while the peer may still arrive on this CTA's barriers

@@ -2,7 +2,9 @@
 #include "online.hpp"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <set>
 
 namespace dopt {
 namespace online {
@@ -73,12 +75,61 @@ void loadState(const LastUpdate& u, const std::string& filename) {
 // mean and variance (core/source/dopt/core/grads/nnet.d:80-81): such parameters are state, moved only by their projection.
 static bool isStateOnly(const Operation& g) { return g->opType() == "variable" || g->opType() == "constant"; }
 
+// Does `op` depend only on the parameters being updated and on constants?  Such a value is the same on every rank: the
+// replicas start from identical parameters and apply identical (exchanged) updates.  `same` holds the variables known to be
+// identical everywhere: the parameters, and variables that are not part of the objective's own graph -- those were created by
+// grad() (its seed float32([], [1.0f]), grads/package.d:52) and nobody holds a handle to feed them.  Anything reached through
+// another variable (the minibatch, a hyper-parameter fed per call) or through a random draw is treated as rank-local.
+static bool rankInvariant(const Operation& op, const std::set<const OperationNode*>& wrt,
+                          std::map<const OperationNode*, bool>& memo) {
+    auto it = memo.find(op.get());
+    if (it != memo.end()) return it->second;
+    bool inv;
+    if (op->opType() == "constant") inv = true;
+    else if (op->opType() == "variable") inv = true;   // a parameter or grad()'s seed (the caller's variables are pre-marked)
+    else if (op->opType() == "uniform" || op->opType() == "allreduce" || op->deps().empty()) inv = false;
+    else {
+        inv = true;
+        for (auto& d : op->deps())
+            if (!rankInvariant(d, wrt, memo)) {
+                inv = false;
+                break;
+            }
+    }
+    memo[op.get()] = inv;
+    return inv;
+}
+
+// mean over ranks of g.  The mean is linear and a rank-invariant addend is its own mean, so add(a, b) with b rank-invariant
+// becomes add(allreduce(a), b): the weight-decay term of a filter gradient (2 * wd * W, nnet/layers/conv.d's weight decay
+// through grads/math.d) is not copied into a gradient bucket and sent over NVLink, the filter-gradient kernel writes straight
+// into the bucket, and the term is added by the same fused update kernel as on a single GPU.  Rounding differs from
+// allreduce(a + b) only by the order of two fp32 additions.
+static Operation exchangeOne(const Operation& g, const std::set<const OperationNode*>& wrt,
+                             std::map<const OperationNode*, bool>& memo) {
+    if (g->opType() == "add" && g->deps().size() == 2 && g->deps()[0]->shape() == g->shape() && g->deps()[1]->shape() == g->shape()) {
+        const bool i0 = rankInvariant(g->deps()[0], wrt, memo), i1 = rankInvariant(g->deps()[1], wrt, memo);
+        if (i1 && !i0) return exchangeOne(g->deps()[0], wrt, memo) + g->deps()[1];
+        if (i0 && !i1) return g->deps()[0] + exchangeOne(g->deps()[1], wrt, memo);
+    }
+    return createOperation("allreduce", {g});
+}
+
 // data-parallel: the mean over ranks of every gradient, as a registered `allreduce` op between grad() and the update rule.
 // Zero "gradients" of state-only parameters are identical on every rank and are not exchanged.
-static std::vector<Operation> exchange(std::vector<Operation> grads) {
+static std::vector<Operation> exchange(std::vector<Operation> grads, const std::vector<Operation>& wrt, const Operation& objective) {
     if (dataParallelWorld() <= 1) return grads;
-    for (auto& g : grads)
-        if (!isStateOnly(g)) g = createOperation("allreduce", {g});
+    std::set<const OperationNode*> params;
+    for (auto& w : wrt) params.insert(w.get());
+    std::map<const OperationNode*, bool> memo;
+    for (auto& op : topologicalSort({objective}))
+        if (op->opType() == "variable" && !params.count(op.get())) memo[op.get()] = false;   // fed by the caller: rank-local
+    const bool split = std::getenv("DOPT_B200_NO_EXCHANGE_SPLIT") == nullptr;
+    for (auto& g : grads) {
+        if (isStateOnly(g)) continue;
+        if (rankInvariant(g, params, memo)) continue;   // (a parameter that only the regulariser touches)
+        g = split ? exchangeOne(g, params, memo) : createOperation("allreduce", {g});
+    }
     return grads;
 }
 
@@ -124,7 +175,7 @@ Updater sgd(const std::vector<Operation>& outputs, const std::vector<Operation>&
     if (!momentumRate) momentumRate = float32({}, {0.0f});
     auto objective = outputs[0];
     auto rawGrads = grad(objective, wrt);
-    auto grads = exchange(rawGrads);
+    auto grads = exchange(rawGrads, wrt, objective);
     std::vector<Operation> momentum, newMomentum, newvals;
     for (auto& g : grads) momentum.push_back(float32(g->shape()));
     if (nesterov) {
@@ -154,7 +205,7 @@ static Updater adamImpl(const std::vector<Operation>& outputs, const std::vector
     if (!eps) eps = float32({}, {1e-8f});
     auto objective = outputs[0];
     auto rawGrads = grad(objective, wrt);
-    auto grads = exchange(rawGrads);
+    auto grads = exchange(rawGrads, wrt, objective);
     std::vector<Operation> means, vars, varhats;
     for (auto& w : wrt) means.push_back(float32(w->shape()));
     for (auto& w : wrt) vars.push_back(float32(w->shape()));

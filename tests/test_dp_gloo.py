@@ -100,3 +100,34 @@ def test_two_rank_data_parallel_step_matches_single_process():
     for p, got in zip(net.params, results[0]):
         np.testing.assert_allclose(got, oracle.value_of(p), rtol=2e-5, atol=2e-6)
     H.reset()
+
+
+def test_rank_invariant_weight_decay_term_is_not_exchanged(monkeypatch):
+    """dopt.online.exchange: the gradient of a regularised parameter is add(lossGradient, weightDecayTerm); the second operand
+    depends only on the parameters, which every rank holds identically, so only the first is all-reduced and the term is added
+    behind the collective (mean(a_r + b) = mean(a_r) + b).  DOPT_B200_NO_EXCHANGE_SPLIT=1 restores allreduce(add(..))."""
+    sys.path.insert(0, ROOT)
+    from dopt_b200 import host as H
+    H.init()
+
+    def operand_types(split):
+        if split:
+            monkeypatch.delenv("DOPT_B200_NO_EXCHANGE_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("DOPT_B200_NO_EXCHANGE_SPLIT", "1")
+        H.set_data_parallel_world(2)
+        x, y, net, upd = _build(H, 4)
+        plan_ops, dests = upd.plan_outputs()
+        nodes = H.export(plan_ops)
+        by_id = {n["id"]: n for n in nodes}
+        ops = sorted(by_id[n["deps"][0]]["type"] for n in nodes if n["type"] == "allreduce")
+        n_params = len(net.params)
+        H.set_data_parallel_world(1)
+        H.reset()
+        return ops, n_params
+    plain, n_params = operand_types(False)
+    split, _ = operand_types(True)
+    assert len(plain) == len(split) == n_params
+    assert "convolutionFiltersGrad" not in plain and "add" in plain       # conv filter and dense weight carry weight decay
+    assert "convolutionFiltersGrad" in split
+    assert split.count("add") < plain.count("add")

@@ -11,7 +11,7 @@ RANK = int(os.environ.get("RANK", "0"))
 os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
 # the gradient all-reduces get a fixed, small number of CTAs and the tensor-core kernels leave those SMs free (comm.cu); NCCL
 # reads the variable when the process creates its first communicator, which torch.distributed does below
-os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "4"))
+os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "16"))
 os.environ.setdefault("NCCL_MIN_NCHANNELS", os.environ["NCCL_MAX_NCHANNELS"])
 
 import ctypes as C  # noqa: E402

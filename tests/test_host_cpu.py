@@ -513,9 +513,16 @@ def test_vgg_regulariser_options():
 
 def test_data_parallel_wraps_gradients_in_allreduce():
     w = H.float32((4,), np.arange(4))
-    loss = H.sum_(w * w)
+    x = H.float32((4,), np.arange(4))          # fed by the caller: the rank's share of the data
+    loss = H.sum_(w * x)
     H.set_data_parallel_world(8)
     upd = H.Updater(H.SGD, [loss], wrt=[w])
+    assert types(upd.plan_outputs()[0]).count("allreduce") == 1
+    # a loss that depends on the parameters alone (a pure regulariser) has the same gradient on every rank: nothing to exchange
+    upd = H.Updater(H.SGD, [H.sum_(w * w)], wrt=[w])
+    assert types(upd.plan_outputs()[0]).count("allreduce") == 0
+    # data term + regulariser: only the data term's gradient goes through the collective
+    upd = H.Updater(H.SGD, [H.sum_(w * x) + H.sum_(w * w)], wrt=[w])
     assert types(upd.plan_outputs()[0]).count("allreduce") == 1
     H.set_data_parallel_world(1)
     upd = H.Updater(H.SGD, [loss], wrt=[w])

@@ -149,8 +149,9 @@ def class_rooflines(nodes, loss_id, prof_us, prof_n, n_params, hbm_gbs, elem=4):
         "3V*%d B; the pass also applies the relu gate and the residual-gradient add" % elem)
     if res_adds and prof_n.get("add", 0) == len(res_adds):
         put("residual_add", ["add"], 3 * sum(vol(n) for n in res_adds) * elem, "3V*%d B, forward residual sums" % elem)
-    put("optimiser", ["fusedRegion"], 5 * n_params * 4,
-        "5P*4 B (SGD+momentum); the fused regions also carry the weight-decay gradient and the loss chain")
+    put("optimiser", ["update"], 5 * n_params * 4,
+        "5P*4 B (SGD+momentum): the plan's terminal fused launches, which also compute the weight-decay gradient; the other "
+        "pointwise regions of the step (loss chain, scalar products) are booked under fusedRegion")
     return out
 
 
@@ -424,7 +425,7 @@ def main():
     replay = {}
     if world == 1:
         for name, ops in (("tc", CONV_OPS), ("batchNormTrain", "batchNormTrain"), ("batchNormGrad", "batchNormGrad"),
-                          ("add", "add"), ("fusedRegion", "fusedRegion")):
+                          ("add", "add"), ("update", "update")):
             try:
                 replay[name] = upd.replay_class(ops, 3)
             except Exception as e:   # diagnostics: never lose the bench line over it
@@ -468,7 +469,7 @@ def main():
             loss_id = [n["id"] for n in nodes if n["op"].h == plan_outs[0].h][0]
             per_us = dict((k, v / 2.0) for k, v in prof.items() if "#" not in k)
             per_n = dict((k[:-2], v / 2.0) for k, v in prof.items() if k.endswith("#n"))
-            for name in ("batchNormTrain", "batchNormGrad", "add", "fusedRegion"):
+            for name in ("batchNormTrain", "batchNormGrad", "add", "update"):
                 if name in replay:      # class replay (one event pair per class) instead of per-launch event brackets
                     per_us[name] = replay[name][0]
             interior = bool(H.plan_flags() & db._lib.PLAN_BF16_INTERIOR)

@@ -177,6 +177,9 @@ struct Kernel {
     // scratches of many filter gradients into KCRS with ONE multi-tensor launch (28 latency-sized launches per WRN step
     // otherwise).  deferred_finish fills everything of the row but `dw`.
     virtual bool deferred_finish(struct WgradFinish* /*row*/) { return false; }
+    // ... and the plan may supply that scratch itself (a slice of one arena holding the scratches of every deferred filter
+    // gradient, zeroed by ONE memset per step instead of one per convolution); the kernel then neither owns nor clears it
+    virtual void set_finish_scratch(float* /*zeroed_by_caller*/) {}
     // true when run() touches no workspace shared with other ops (only its operands, its result and private scratch): the
     // plan may then issue it on a side stream, concurrently with the ops that follow it in the order
     virtual bool side_stream_safe() const { return false; }

@@ -49,6 +49,7 @@ struct ConvKernel : Kernel {
     bool can_stage_output() const override { return conv_tc_can_stage_output(tc); }
     void set_staged_output(void* p) override { conv_tc_set_staged_output(tc, p); }
     bool deferred_finish(WgradFinish* row) override { return tc && kind == CONV_WGRAD && conv_tc_defer_finish(tc, row); }
+    void set_finish_scratch(float* p) override { conv_tc_set_scratch(tc, p); }
     bool side_stream_safe() const override { return tc && conv_tc_side_stream_safe(tc); }
     int can_produce_stats() const override { return (tc && kind == CONV_FWD) ? 2 : 0; }
     void set_stats_workspace(void* w, int channels) override {

@@ -105,6 +105,7 @@ struct Item {
     int kind;
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
     bool join_comm;     // reads a reduced gradient: the compute stream must first wait for the communication stream
+    bool terminal;      // ITEM_FUSED: a terminal launch (its results are plan outputs only: the optimiser's parameter updates)
 };
 
 // an activation staged once as NHWC bf16 for all the tensor-core convolution ops that read it
@@ -179,6 +180,12 @@ struct dopt_b200_plan_s {
         cudaEvent_t done = nullptr;
     };
     std::vector<FinishGroup> finishes;
+    // the accumulation scratches of every deferred filter gradient, carved from one arena: ONE memset per step -- issued on the
+    // side stream at the start of the step, so it runs beside the forward pass -- instead of one before each of the 28 filter
+    // gradients of a WRN-28-10 step
+    void* wg_arena = nullptr;
+    int64_t wg_arena_bytes = 0;
+    cudaEvent_t wg_zeroed = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     // side stream: filter gradients whose only reader is a deferred finish launch run here, beside the feature-gradient chain
@@ -222,6 +229,8 @@ struct dopt_b200_plan_s {
         }
         if (packs_dev) cudaFree(packs_dev);
         if (post_dev) cudaFree(post_dev);
+        if (wg_arena) cudaFree(wg_arena);
+        if (wg_zeroed) cudaEventDestroy(wg_zeroed);
         db::tc_gate_destroy(&gate);
         if (comm_stream) cudaStreamDestroy(comm_stream);
         if (comm_fork) cudaEventDestroy(comm_fork);
@@ -957,7 +966,7 @@ static void schedule(Plan& p) {
                         producer_item(d, &via);
                         join = join || via;
                     }
-            p.order.push_back({ITEM_FUSED, (int)li, join});
+            p.order.push_back({ITEM_FUSED, (int)li, join, true});
         }
 }
 
@@ -1755,6 +1764,23 @@ static void build(Plan& p) {
                 p.finishes[it->second].rows.push_back(row);
                 p.device_bytes += (int64_t)row.RS * row.K * row.C * 4;
             }
+            if (!p.finishes.empty() && !getenv("DOPT_B200_NO_WG_ARENA")) {
+                auto slice = [](const WgradFinish& r) { return ((int64_t)r.RS * r.K * r.C * 4 + 255) / 256 * 256; };
+                int64_t total = 0;
+                for (auto& f : p.finishes)
+                    for (auto& r : f.rows) total += slice(r);
+                DB_CUDA(cudaMalloc(&p.wg_arena, (size_t)total));
+                DB_CUDA(cudaMemset(p.wg_arena, 0, (size_t)total));
+                p.wg_arena_bytes = total;
+                int64_t off = 0;
+                for (auto& f : p.finishes)
+                    for (size_t i = 0; i < f.rows.size(); ++i) {
+                        float* ptr = (float*)((char*)p.wg_arena + off);
+                        N[f.nodes[i]].kernel->set_finish_scratch(ptr);   // (frees the private scratch deferred_finish made)
+                        f.rows[i].scratch = ptr;
+                        off += slice(f.rows[i]);
+                    }
+            }
             for (auto& f : p.finishes) f.side_ok = f.bucket >= 0;
             for (size_t u = 0; u < N.size(); ++u) {
                 if (!N[u].needed) continue;
@@ -1961,7 +1987,7 @@ static const char* item_label(const Plan& p, const Item& it) {
         case ITEM_COPY: return "bucketCopyIn";
         case ITEM_KERNEL:
         case ITEM_PW_SCALAR: return p.nodes[it.id].type.c_str();
-        default: return "fusedRegion";
+        default: return it.terminal ? "update" : "fusedRegion";
     }
 }
 
@@ -1995,6 +2021,32 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
     // the gaps between dependent launches.  The chain joins before the first finish launch.  Profiling serialises everything.
     static const bool side_on = !getenv("DOPT_B200_NO_SIDE_STREAM");
     bool side_pending = false;
+    auto ensure_side = [&]() {
+        if (p.side_stream) return;
+        // lowest priority: when both streams have CTAs waiting for an SM, the chain's go first
+        int prio_lo = 0, prio_hi = 0;
+        DB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DB_CUDA(cudaStreamCreateWithPriority(&p.side_stream, cudaStreamNonBlocking, prio_lo));
+        DB_CUDA(cudaEventCreateWithFlags(&p.side_fork, cudaEventDisableTiming));
+        DB_CUDA(cudaEventCreateWithFlags(&p.side_join, cudaEventDisableTiming));
+    };
+    // the filter-gradient scratches start every step at zero: one memset of their arena, beside the forward pass
+    bool wg_zero_on_side = false;
+    if (p.wg_arena && (!only || only->count("convolutionFiltersGrad"))) {
+        if (side_on && !p.profiling && !only) {
+            ensure_side();
+            if (!p.wg_zeroed) DB_CUDA(cudaEventCreateWithFlags(&p.wg_zeroed, cudaEventDisableTiming));
+            DB_CUDA(cudaEventRecord(p.side_fork, s));
+            DB_CUDA(cudaStreamWaitEvent(p.side_stream, p.side_fork, 0));
+            DB_CUDA(cudaMemsetAsync(p.wg_arena, 0, (size_t)p.wg_arena_bytes, p.side_stream));
+            DB_CUDA(cudaEventRecord(p.wg_zeroed, p.side_stream));
+            side_pending = true;
+            wg_zero_on_side = true;
+        } else {
+            DB_CUDA(cudaMemsetAsync(p.wg_arena, 0, (size_t)p.wg_arena_bytes, s));
+        }
+        count_launch();
+    }
     auto side_join_now = [&]() {
         if (!side_pending) return;
         DB_CUDA(cudaEventRecord(p.side_join, p.side_stream));
@@ -2112,20 +2164,14 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
                 n.kernel->set_companion(3, p.stages[n.ep_src_stage].buf, coef);
             }
             if (side_on && !p.profiling && !only && n.finish_group >= 0 && n.kernel->side_stream_safe()) {
-                if (!p.side_stream) {
-                    // lowest priority: when both streams have CTAs waiting for an SM, the chain's go first
-                    int prio_lo = 0, prio_hi = 0;
-                    DB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-                    DB_CUDA(cudaStreamCreateWithPriority(&p.side_stream, cudaStreamNonBlocking, prio_lo));
-                    DB_CUDA(cudaEventCreateWithFlags(&p.side_fork, cudaEventDisableTiming));
-                    DB_CUDA(cudaEventCreateWithFlags(&p.side_join, cudaEventDisableTiming));
-                }
+                ensure_side();
                 p.gate.side = p.side_stream;
                 DB_CUDA(cudaEventRecord(p.side_fork, s));
                 DB_CUDA(cudaStreamWaitEvent(p.side_stream, p.side_fork, 0));
                 n.kernel->run(in, (int)n.deps.size(), n.ptr, p.side_stream);
                 side_pending = true;
             } else {
+                if (wg_zero_on_side && n.finish_group >= 0) DB_CUDA(cudaStreamWaitEvent(s, p.wg_zeroed, 0));
                 n.kernel->run(in, (int)n.deps.size(), n.ptr, s);
             }
             label = n.type.c_str();
@@ -2136,7 +2182,7 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
             label = n.type.c_str();
         } else {
             fused_launch(p.launches[it.id], s);
-            label = "fusedRegion";
+            label = it.terminal ? "update" : "fusedRegion";
         }
         if (p.profiling) labels.push_back(label);
     }
@@ -2471,7 +2517,12 @@ int dopt_b200_plan_replay_class(dopt_b200_plan_t p, const char* op_types, int re
     for (int r = 0; r < reps; ++r) db::run_items(*p, s, &only);
     const uint64_t l1 = db::g_launches.load();
     DB_CUDA(cudaEventRecord(e1, s));
+    // replayed filter gradients accumulated into their scratches without a finish launch behind them: finish now, which leaves
+    // the scratches zeroed for the next real step (WgradFinish::rezero)
+    if (!only.count("filtersGradFinish"))
+        for (auto& f : p->finishes) db::wgrad_finish_launch(f.dev, (int)f.rows.size(), f.tiles, f.smem, s);
     DB_CUDA(cudaEventSynchronize(e1));
+    DB_CUDA(cudaStreamSynchronize(s));
     p->profiling = was;
     float ms = 0;
     DB_CUDA(cudaEventElapsedTime(&ms, e0, e1));

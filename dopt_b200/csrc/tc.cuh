@@ -37,6 +37,8 @@ bool conv_tc_can_companion(const ConvTc* c, int mode);
 void conv_tc_set_companion(ConvTc* c, int mode, const void* src, const float* coef);
 // wgrad: accumulate into a private scratch (allocated here) and skip the per-op finish kernel; the caller finishes `row` later
 bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row);
+// ... into a scratch the caller owns and zeroes before every execution (replaces the private one)
+void conv_tc_set_scratch(ConvTc* c, float* zeroed_by_caller);
 // wgrad that reads only plan-staged operands and writes only its private scratch: it shares no workspace with any other op, so
 // the plan may run it on a second stream beside the feature-gradient chain
 bool conv_tc_side_stream_safe(const ConvTc* c);

@@ -812,6 +812,7 @@ struct ConvTc {
     void* out_staged = nullptr;                // fwd / dgrad: write the result as [N][H][W][Cp] bf16 here instead of NCHW fp32
     void* stats_ws = nullptr;                  // fwd + out_staged: statistics workspace of the batch norm reading the result
     float* acc_private = nullptr;              // wgrad: private accumulation scratch, finished later by the plan (deferred)
+    bool acc_external = false;                 // ... owned and zeroed by the plan (one arena, one memset per step)
     // epilogue companion (TcArgs::ep_src): fwd + out_staged: the addend of the residual sum this convolution feeds (mode 2);
     // dgrad + out_staged: x and the forward coefficients of the batch norm whose backward pass reads this result (mode 3)
     int ep_mode = 0;
@@ -910,7 +911,7 @@ ConvTc* conv_tc_create(const ConvGeom& g, int kind) {
     return c;
 }
 void conv_tc_destroy(ConvTc* c) {
-    if (c && c->acc_private) cudaFree(c->acc_private);
+    if (c && c->acc_private && !c->acc_external) cudaFree(c->acc_private);
     delete c;
 }
 bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row) {
@@ -923,6 +924,13 @@ bool conv_tc_defer_finish(ConvTc* c, WgradFinish* row) {
     row->K = g.K; row->C = g.C; row->RS = g.R * g.S;
     row->tiles_x = row->tile0 = 0;
     return true;
+}
+
+void conv_tc_set_scratch(ConvTc* c, float* p) {
+    if (!c || c->kind != CONV_WGRAD || !p) return;
+    if (c->acc_private && !c->acc_external) cudaFree(c->acc_private);
+    c->acc_private = p;
+    c->acc_external = true;
 }
 
 bool conv_tc_side_stream_safe(const ConvTc* c) {
@@ -1171,8 +1179,10 @@ static void run_wgrad(ConvTc* c, const float* dy, const float* x, float* dw, cud
     else nchw_to_nhwc_bf16(dy, dyh, g.N, g.K, g.P * g.Q, Kp, s);
     if (c->pre[1]) xh = (__nv_bfloat16*)c->pre[1];
     else nchw_to_nhwc_bf16(x, xh, g.N, g.C, g.H * g.W, Cp, s);
-    DB_CUDA(cudaMemsetAsync(acc, 0, (size_t)g.K * g.C * RS * sizeof(float), s));
-    count_launch();
+    if (!c->acc_external) {
+        DB_CUDA(cudaMemsetAsync(acc, 0, (size_t)g.K * g.C * RS * sizeof(float), s));
+        count_launch();
+    }
     const PixelBox& b = c->box;
     CUtensorMap tmA, tmB;
     make_map_nhwc(&tmA, dyh, g.N, g.P, g.Q, Kp, g.K, b.bn, b.bh, b.bw, 1, 1, "convolutionFiltersGrad dy");

@@ -18,8 +18,8 @@ def test_class_rooflines_from_the_exported_graph():
     n_params = sum(p.volume for p in net.params)
     # WRN-10-2: one block per group -> 3 residual adds, 2 batch norms per block + the final one
     assert len(bns) == 7
-    us = {"batchNormTrain": 10.0, "batchNormGrad": 20.0, "add": 5.0, "fusedRegion": 2.0}
-    n = {"batchNormTrain": 7, "batchNormGrad": 7, "add": 3, "fusedRegion": 4}
+    us = {"batchNormTrain": 10.0, "batchNormGrad": 20.0, "add": 5.0, "update": 2.0}
+    n = {"batchNormTrain": 7, "batchNormGrad": 7, "add": 3, "update": 4}
     r = bench.class_rooflines(nodes, loss_id, us, n, n_params, 6500.0)
     assert r["batchNormTrain"]["alg_bytes_per_step"] == 2 * v_bn * 4
     assert r["batchNormGrad"]["alg_bytes_per_step"] == 3 * v_bn * 4

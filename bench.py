@@ -46,6 +46,12 @@ if WORLD > 1:
 else:
     PHYS_GPU = (os.environ.get("CUDA_VISIBLE_DEVICES") or "0").split(",")[0]
 
+if "reference" in sys.argv and WORLD > 1 and RANK == 0:
+    # the reference arm runs the host-CPU oracle on rank 0 alone: give it every host core -- torchrun exports
+    # OMP_NUM_THREADS=1 to its workers, which would time a single-threaded BLAS (the numbers at N >= 2 of round 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 
 MODEL = dict(depth=28, width=10, batch=128, hw=32, classes=100, lr=0.1, momentum=0.9, wd=1e-4)
@@ -458,7 +464,7 @@ def main():
                                                    else " (sustained: SM clock below max or power-capped during the timed region)"),
                     "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3,
                     "how": ("the step's convolution launches re-issued back to back between one CUDA-event pair "
-                            "(dopt_b200_plan_replay_class; includes the stem's direct kernel and the accumulator memsets)"
+                            "(dopt_b200_plan_replay_class; includes the stem's direct kernel and the memset of the filter-gradient scratch arena)"
                             if "tc" in replay else "sum of per-launch CUDA-event brackets around the tcgen05 kernel"),
                     "kernel_ms_per_step_event_brackets": tc_us_events / 1e3}
     classes = None

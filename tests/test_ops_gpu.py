@@ -476,3 +476,45 @@ def test_uniform_distribution():
     assert abs(v.mean() - 0.5) < 2e-3 and abs(v.var() - 1.0 / 12) < 2e-3
     out2 = db.run_op("uniform", [], (1 << 20,), seed=1234)
     assert np.array_equal(v, host(out2))               # seeded: reproducible
+
+
+@pytest.mark.parametrize("math", [db.MATH_FP32, db.MATH_BF16], ids=["fp32", "bf16"])
+def test_kernel_handle_sees_weights_overwritten_in_place(math):
+    """dopt.online overwrites a parameter's CUDABuffer in place after every step (online/source/dopt/online/sgd.d:76-91 ->
+    cuda/source/dopt/cuda/package.d:419-422) and then executes the SAME CUDAKernel objects again.  A kernel handle must
+    therefore never reuse anything derived from an earlier value of an operand (packed / staged filters): the second execute
+    on the same handle, with the filter buffer overwritten at the same address, has to give the new result -- for the
+    forward convolution, its feature gradient (filter operand) and its filter gradient (activation operands)."""
+    rng = np.random.RandomState(11)
+    N, C, H, W, K = 8, 32, 16, 16, 64
+    x = rng.randn(N, C, H, W).astype(F)
+    dy = rng.randn(N, K, H, W).astype(F)
+    w1 = (rng.randn(K, C, 3, 3) * 0.1).astype(F)
+    w2 = (rng.randn(K, C, 3, 3) * 0.1).astype(F)
+    attrs = dict(padding=[1, 1], stride=[1, 1])
+    tol = 1e-4 if math == db.MATH_FP32 else 2e-2
+    s = torch.cuda.current_stream().cuda_stream
+
+    def close(got, ref):
+        return float(np.abs(got - ref).max()) <= tol * float(np.abs(ref).max())
+
+    xd, dyd, wd = dev(x), dev(dy), dev(w1)
+    fwd = db.CUDAKernel(db.make_op("convolution", [x.shape, w1.shape], (N, K, H, W), None, db.FLOAT32, math, **attrs))
+    dgr = db.CUDAKernel(db.make_op("convolutionFeaturesGrad", [dy.shape, w1.shape], x.shape, None, db.FLOAT32, math,
+                                   featuresShape=list(x.shape), **attrs))
+    wgr = db.CUDAKernel(db.make_op("convolutionFiltersGrad", [dy.shape, x.shape], w1.shape, None, db.FLOAT32, math,
+                                   filtersShape=list(w1.shape), **attrs))
+    y = torch.zeros((N, K, H, W), device="cuda")
+    dx = torch.zeros(x.shape, device="cuda")
+    dw = torch.zeros(w1.shape, device="cuda")
+    for w_now, x_now in ((w1, x), (w2, x * 0.5 + 1.0)):
+        wd.copy_(dev(w_now))            # same device address, new value
+        xd.copy_(dev(x_now.astype(F)))
+        fwd.execute([xd, wd], y, s)
+        dgr.execute([dyd, wd], dx, s)
+        wgr.execute([dyd, xd], dw, s)
+        assert close(host(y), R.convolution(x_now.astype(F), w_now, (1, 1), (1, 1)))
+        assert close(host(dx), R.convolution_features_grad(dy, w_now, x.shape, (1, 1), (1, 1)))
+        assert close(host(dw), R.convolution_filters_grad(dy, x_now.astype(F), w1.shape, (1, 1), (1, 1)))
+    for k in (fwd, dgr, wgr):
+        k.close()

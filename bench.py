@@ -63,9 +63,10 @@ TRAIN_GFLOP_PER_IMAGE = 31.459
 # images per step of the bounded CPU sample (cpu_baseline and --impl reference): about 10 s of host work per step
 CPU_SAMPLE = 16
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, profiles/r02_tc_dram.csv;
-# the NHWC bf16 results mostly stay in L2 until a later kernel evicts them, hence the small write figure)
-TC_DRAM_BYTES_PER_STEP = 2929168640 + 3014656
+# dram__bytes_read.sum + dram__bytes_write.sum of the 88 tc_kernel launches of one training step (ncu, final build of round 2:
+# profiles/r02final_tc_dram.csv; the NHWC bf16 results mostly stay in L2 until a later kernel evicts them, hence the small
+# write figure).  Re-measure with tools/capture_profiles.sh whenever the tensor-core kernel or the staging changes.
+TC_DRAM_BYTES_PER_STEP = 2930144768 + 2820864
 
 
 def workload_name(depth=MODEL["depth"], width=MODEL["width"], batch=MODEL["batch"]):
@@ -459,7 +460,7 @@ def main():
                     "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                     "traffic": TC_DRAM_BYTES_PER_STEP if (args.depth, args.width) == (28, 10) else None,
                     "traffic_source": "ncu dram__bytes_read+write summed over the step's tc_kernel launches "
-                                      "(profiles/r02j_tc_dram.csv), per step like `achieved`",
+                                      "(profiles/r02final_tc_dram.csv), per step like `achieved`",
                     "peak_source": pk["source"] + (" (burst: SM clock at max, no power cap during the timed region)" if burst
                                                    else " (sustained: SM clock below max or power-capped during the timed region)"),
                     "launches_per_step": prof.get("tc_kernel_launches", 0) / 2.0, "kernel_ms_per_step": tc_us / 1e3,

@@ -44,7 +44,14 @@ extern "C" {
 typedef enum { DOPT_B200_FLOAT32 = 0, DOPT_B200_INT32 = 1 } dopt_b200_dtype;
 
 /* numerics of the dense contractions (convolution*, matmul).  FP32 = SIMT fp32 accumulate in fp32 (tight parity with
- * the reference's cuDNN/cuBLAS fp32 calls); BF16 = tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM. */
+ * the reference's cuDNN/cuBLAS fp32 calls); BF16 = tcgen05 tensor cores, bf16 operands, fp32 accumulate in TMEM.
+ *
+ * NOTE -- deviation from the reference: DEFAULT resolves to BF16 (dopt_b200_set_default_math changes that).  The reference's
+ * cuDNN / cuBLAS calls compute strict fp32.  With BF16 a convolution differs from the fp32 result by 2-3e-3 of the tensor's
+ * max magnitude (stated bound 2e-2), the filter gradient is accumulated with fp32 atomics and is therefore not
+ * bit-reproducible from run to run, and loss curves of the BASELINE configs agree with the fp32 oracle within 3e-2 relative
+ * (measured 2.5e-4 on WRN-28-10: DESIGN.md section 5, profiles/r02_parity.md).  Select FP32 for reference-accurate,
+ * reproducible results. */
 typedef enum { DOPT_B200_MATH_DEFAULT = 0, DOPT_B200_MATH_FP32 = 1, DOPT_B200_MATH_BF16 = 2 } dopt_b200_math;
 
 /* TensorType, core/source/dopt/core/types.d:16-57 */

@@ -37,14 +37,22 @@ if WORLD > 1:
     # communicator -- torch.distributed's, below -- so it has to be in the environment now
     os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "16"))
     os.environ.setdefault("NCCL_MIN_NCHANNELS", os.environ["NCCL_MAX_NCHANNELS"])
-    # one process per GPU, each seeing exactly its own device as ordinal 0 -- the reference hard-codes ordinal 0
-    # (cuda/source/dopt/cuda/package.d:44), so this is also how the D host would be launched
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     ids = vis.split(",") if vis else [str(i) for i in range(64)]
     PHYS_GPU = ids[LOCAL_RANK]
-    os.environ["CUDA_VISIBLE_DEVICES"] = PHYS_GPU
+    # Gradient buckets in peer-mapped memory reduced by the library's own NVSwitch-multicast kernel (DOPT_B200_SYMM=0: NCCL
+    # only).  The symmetric-memory allocator tells peers apart by device index, so every GPU stays visible and rank r works
+    # on device r; with DOPT_B200_SYMM=0 each process sees exactly its own device as ordinal 0 -- the reference hard-codes
+    # ordinal 0 (cuda/source/dopt/cuda/package.d:44), so that is how the D host would be launched.
+    SYMM = os.environ.get("DOPT_B200_SYMM", "1") != "0"
+    if SYMM:
+        DEV = LOCAL_RANK
+    else:
+        DEV = 0
+        os.environ["CUDA_VISIBLE_DEVICES"] = PHYS_GPU
 else:
     PHYS_GPU = (os.environ.get("CUDA_VISIBLE_DEVICES") or "0").split(",")[0]
+    SYMM, DEV = False, 0
 
 if "reference" in sys.argv and WORLD > 1 and RANK == 0:
     # the reference arm runs the host-CPU oracle on rank 0 alone: give it every host core -- torchrun exports
@@ -279,11 +287,12 @@ def main():
     from dopt_b200 import host as H
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(DEV)
     world = WORLD
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", DEV))
     assert H.init(), H.init_error()
+    symm_keep = None
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if RANK == 0:
@@ -292,6 +301,10 @@ def main():
             uid.copy_(torch.tensor(list(buf.raw), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         H.init_data_parallel(RANK, world, bytes(uid.cpu().tolist()))
+        if SYMM:
+            from dopt_b200 import symm
+            # 146 MB of gradients + the running statistics, bucket by bucket (256-byte aligned slices)
+            symm_keep = symm.attach(192 << 20, torch.device("cuda", DEV))
 
     B = MODEL["batch"]
     x, y, net, upd = build_wrn(H, B, args.depth, args.width)
@@ -500,6 +513,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.depth, args.width, B),
                        "parallelism": "dp%d" % world, "params": n_params,
+                       "exchange": (None if world == 1 else
+                                    "gradient buckets in peer-mapped memory, reduced by the library's multimem kernel over NVSwitch "
+                                    "multicast" if symm_keep is not None else "gradient buckets reduced by ncclAllReduce"),
                        "cache": "inputs larger than L2: one step streams several GB of activations through the 126 MB L2",
                        "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; activations between tensor-core "
                                     "convolutions stored NHWC bf16 (plan flag BF16_INTERIOR), arithmetic and everything "
@@ -518,6 +534,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        db.check(db.lib.dopt_b200_comm_check())   # a flag barrier of the multicast all-reduce that timed out, an NCCL error
+        dist.barrier()
         dist.destroy_process_group()
 
 

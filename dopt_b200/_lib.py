@@ -66,7 +66,7 @@ SYMBOLS = [
     "dopt_b200_plan_create", "dopt_b200_plan_add_node", "dopt_b200_plan_set_outputs", "dopt_b200_plan_finalize",
     "dopt_b200_plan_execute", "dopt_b200_plan_stats", "dopt_b200_plan_profile", "dopt_b200_plan_replay_class", "dopt_b200_plan_destroy",
     "dopt_b200_comm_unique_id", "dopt_b200_comm_init", "dopt_b200_comm_world_size", "dopt_b200_comm_rank",
-    "dopt_b200_allreduce", "dopt_b200_comm_check", "dopt_b200_comm_destroy",
+    "dopt_b200_allreduce", "dopt_b200_comm_check", "dopt_b200_comm_destroy", "dopt_b200_comm_set_symmetric",
 ]
 
 
@@ -111,4 +111,5 @@ def load():
     lib.dopt_b200_comm_unique_id.argtypes = [vp]
     lib.dopt_b200_comm_init.argtypes = [C.c_int, C.c_int, vp]
     lib.dopt_b200_allreduce.argtypes = [vp, i64, C.c_float, vp]
+    lib.dopt_b200_comm_set_symmetric.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.c_int, C.c_size_t]
     return lib

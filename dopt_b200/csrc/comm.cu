@@ -98,12 +98,130 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, int64
 }
 }  // namespace
 
+// ---- all-reduce over NVSwitch multicast (symmetric memory supplied by the caller, dopt_b200_comm_set_symmetric) -------------
+// Two-shot: rank r owns slice r of the buffer.  multimem.ld_reduce fetches the slice from every rank and adds inside the
+// switch; the sum is scaled to the mean and multimem.st writes it back to every rank.  Traffic per GPU and direction: one
+// buffer length, whatever the world size.  Two flag barriers bracket it: the first so that every rank's bucket is complete,
+// the second so that nobody reads its bucket before every slice has landed.  A barrier is per CTA -- CTA b of rank r puts a
+// flag into slot [b][r] of every peer's pad (CAS 0 -> 1) and takes the flags of its own slots [b][*] (CAS 1 -> 0) -- so the
+// launches need the same grid on every rank and nothing else: no host synchronisation, no NCCL, capturable in a CUDA graph.
+namespace {
+constexpr int kSymmMaxWorld = 16;
+constexpr size_t kSymmPadOffset = 1024;   // bytes: the head of a pad is left to its owner (torch's own collectives use it)
+struct Symm {
+    char* local = nullptr;
+    char* mc = nullptr;
+    size_t bytes = 0, used = 0;
+    uint32_t* pads[kSymmMaxWorld] = {};
+    size_t pad_bytes = 0;
+    unsigned* err = nullptr;    // device word: a barrier gave up waiting
+    int ctas = 16;
+};
+Symm g_symm;
+
+struct SymmArgs {
+    float4* mc;                  // multicast address of the bucket
+    int64_t n4;                  // float4 elements
+    uint32_t* pads[kSymmMaxWorld];
+    int rank, world;
+    float scale;
+    unsigned* err;
+};
+
+__device__ __forceinline__ uint32_t cas_sys(uint32_t* addr, uint32_t cmp, uint32_t val, int sem) {
+    uint32_t old;
+    if (sem == 0) asm volatile("atom.global.relaxed.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    else if (sem == 1) asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    else asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+// thread t < world handles peer t.  A peer that never shows up (a crashed rank) must not hang the GPU: after ~30 s the barrier
+// gives up, raises the error word (dopt_b200_comm_check reports it) and the kernel finishes with garbage.
+template <bool ACQ_REL>
+__device__ __forceinline__ void symm_barrier(const SymmArgs& a) {
+    if ((int)threadIdx.x < a.world) {
+        const int peer = (int)threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t* put = a.pads[peer] + (size_t)blockIdx.x * a.world + a.rank;
+        uint32_t* take = a.pads[a.rank] + (size_t)blockIdx.x * a.world + peer;
+        bool ok = true;
+        while (ok && cas_sys(put, 0u, 1u, ACQ_REL ? 1 : 0) != 0u)
+            if (clock64() - t0 > 60000000000ll) ok = false;
+        while (ok && cas_sys(take, 1u, 0u, ACQ_REL ? 2 : 0) != 1u)
+            if (clock64() - t0 > 60000000000ll) ok = false;
+        if (!ok) *a.err = 1u;
+    }
+}
+__global__ void __launch_bounds__(512) symm_allreduce_kernel(const __grid_constant__ SymmArgs a) {
+    symm_barrier<false>(a);   // (the buckets were written by kernels that completed before this one started on each rank)
+    __syncthreads();
+    const int64_t per = a.n4 / a.world;
+    const int64_t lo = per * a.rank, hi = a.rank == a.world - 1 ? a.n4 : lo + per;
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(a.mc + i + u * stride) : "memory");
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < hi) {
+                v[u].x *= a.scale; v[u].y *= a.scale; v[u].z *= a.scale; v[u].w *= a.scale;
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a.mc + i + u * stride), "f"(v[u].x),
+                             "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+            }
+    }
+    __syncthreads();
+    symm_barrier<true>(a);
+}
+bool symm_owns(const void* p, size_t bytes) {
+    return g_symm.local && (const char*)p >= g_symm.local && (const char*)p + bytes <= g_symm.local + g_symm.bytes;
+}
+}  // namespace
+
+// carve `bytes` (a multiple of 256) out of the symmetric buffer; nullptr when there is none or it is full
+void* comm_symm_alloc(size_t bytes) {
+    static const bool off = getenv("DOPT_B200_NO_NVLS") != nullptr;
+    if (off || !g_symm.local || g_world <= 1) return nullptr;
+    bytes = (bytes + 255) / 256 * 256;
+    if (g_symm.used + bytes > g_symm.bytes) return nullptr;
+    void* p = g_symm.local + g_symm.used;
+    g_symm.used += bytes;
+    return p;
+}
+// give the most recent allocations back (stack discipline: a plan releases its arenas in reverse order when it is destroyed)
+void comm_symm_release(void* p, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    if (g_symm.local && (char*)p + bytes == g_symm.local + g_symm.used) g_symm.used -= bytes;
+}
+bool comm_symm_active() { return g_symm.local != nullptr && g_world > 1; }
+
 int comm_world() { return g_world; }
 int comm_reserved_sms() { return g_world > 1 ? g_channels : 0; }
 
 // mean over ranks, in place, one NCCL call (ncclAvg); used by the plan's gradient buckets
 void allreduce_mean(float* buf, int64_t n, cudaStream_t s) {
     if (n <= 0 || g_world <= 1) return;
+    if (symm_owns(buf, (size_t)n * 4) && n % 4 == 0 && ((uintptr_t)buf & 15) == 0) {
+        // the bucket lives in the symmetric buffer: the library's own all-reduce over NVSwitch multicast
+        SymmArgs a{};
+        a.mc = (float4*)(g_symm.mc + ((char*)buf - g_symm.local));
+        a.n4 = n / 4;
+        for (int r = 0; r < g_world; ++r) a.pads[r] = (uint32_t*)((char*)g_symm.pads[r] + kSymmPadOffset);
+        a.rank = g_rank;
+        a.world = g_world;
+        a.scale = 1.0f / (float)g_world;
+        a.err = g_symm.err;
+        const int64_t work = (a.n4 / g_world + 4 * 512 - 1) / (4 * 512);
+        const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(g_symm.ctas, work));
+        // (the same grid on every rank: it only depends on the bucket size and the world size)
+        symm_allreduce_kernel<<<ctas, 512, 0, s>>>(a);
+        DB_LAUNCH_CHECK();
+        return;
+    }
     DB_REQUIRE(g_comm != nullptr, "allreduce: communicator not initialised (dopt_b200_comm_init)");
     poll_async_error("before a gradient-bucket all-reduce");
     nccl_check(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclAvg, g_comm, s), "ncclAllReduce");
@@ -111,6 +229,11 @@ void allreduce_mean(float* buf, int64_t n, cudaStream_t s) {
 }
 void comm_check() {
     if (g_world > 1) poll_async_error("dopt_b200_comm_check");
+    if (g_symm.err) {
+        unsigned e = 0;
+        DB_CUDA(cudaMemcpy(&e, g_symm.err, sizeof(e), cudaMemcpyDeviceToHost));
+        if (e) throw Error("all-reduce over symmetric memory: a flag barrier timed out (a peer did not reach the collective)");
+    }
 }
 
 namespace {
@@ -209,8 +332,46 @@ int dopt_b200_comm_check(void) {
     }
     return 0;
 }
+int dopt_b200_comm_set_symmetric(void* local_base, void* multicast_base, size_t bytes, void* const* signal_pads, int n_pads,
+                                 size_t signal_pad_bytes) {
+    try {
+        db::require_device();
+        if (!local_base) {   // detach
+            db::g_symm.local = db::g_symm.mc = nullptr;
+            db::g_symm.bytes = db::g_symm.used = 0;
+            return 0;
+        }
+        DB_REQUIRE(db::g_world > 1 && n_pads == db::g_world, "comm_set_symmetric: call dopt_b200_comm_init first; one signal pad per rank");
+        DB_REQUIRE(db::g_world <= db::kSymmMaxWorld, "comm_set_symmetric: world size too large");
+        DB_REQUIRE(multicast_base && signal_pads && bytes >= 256, "comm_set_symmetric: multicast mapping and signal pads are required");
+        DB_REQUIRE(((uintptr_t)local_base & 255) == 0 && ((uintptr_t)multicast_base & 255) == 0, "comm_set_symmetric: 256-byte alignment");
+        int ctas = 16;
+        if (const char* e = getenv("DOPT_B200_NVLS_CTAS")) ctas = std::max(1, std::min(64, atoi(e)));
+        DB_REQUIRE(signal_pad_bytes >= db::kSymmPadOffset + (size_t)ctas * db::g_world * 4, "comm_set_symmetric: signal pads too small");
+        db::g_symm.local = (char*)local_base;
+        db::g_symm.mc = (char*)multicast_base;
+        db::g_symm.bytes = bytes / 256 * 256;
+        db::g_symm.used = 0;
+        db::g_symm.pad_bytes = signal_pad_bytes;
+        db::g_symm.ctas = ctas;
+        for (int r = 0; r < n_pads; ++r) {
+            DB_REQUIRE(signal_pads[r], "comm_set_symmetric: null signal pad");
+            db::g_symm.pads[r] = (uint32_t*)signal_pads[r];
+        }
+        if (!db::g_symm.err) {
+            DB_CUDA(cudaMalloc((void**)&db::g_symm.err, 16));
+            DB_CUDA(cudaMemset(db::g_symm.err, 0, 16));
+        }
+    } catch (const std::exception& e) {
+        db::set_last_error(e.what());
+        return 1;
+    }
+    return 0;
+}
 int dopt_b200_comm_destroy(void) {
     try {
+        db::g_symm.local = db::g_symm.mc = nullptr;
+        db::g_symm.bytes = db::g_symm.used = 0;
         if (db::g_comm) {
             db::nccl_check(db::g_nccl.CommDestroy(db::g_comm), "ncclCommDestroy");
             db::g_comm = nullptr;

@@ -40,6 +40,8 @@ void tc_prof_read(double* us, int64_t* launches);
 void allreduce_mean(float* buf, int64_t n, cudaStream_t s);
 int comm_world();
 int comm_reserved_sms();
+void* comm_symm_alloc(size_t bytes);
+void comm_symm_release(void* p, size_t bytes);
 
 namespace {
 
@@ -125,6 +127,7 @@ struct Bucket {
     std::vector<int> members;   // allreduce node ids
     void* arena = nullptr;
     int64_t bytes = 0;
+    bool symmetric = false;     // the arena is a slice of the caller's symmetric buffer (comm.cu): reduced by the library's own kernel
 };
 
 static int64_t dtype_size(int) { return 4; }
@@ -214,8 +217,11 @@ struct dopt_b200_plan_s {
             if (n.buf) cudaFree(n.buf);
         }
         for (auto& l : launches) db::fused_free(l);
-        for (auto& b : buckets)
-            if (b.arena) cudaFree(b.arena);
+        for (auto it = buckets.rbegin(); it != buckets.rend(); ++it) {
+            if (!it->arena) continue;
+            if (it->symmetric) db::comm_symm_release(it->arena, (size_t)std::max<int64_t>(it->bytes, 256));
+            else cudaFree(it->arena);
+        }
         for (auto& st : stages)
             if (st.buf) cudaFree(st.buf);
         for (void* b : pack_bufs) cudaFree(b);
@@ -1630,7 +1636,9 @@ static void build(Plan& p) {
     form_buckets(p);
     std::map<int, void*> arena_slot;   // root node of a bucket member -> its slice of the bucket arena
     for (auto& b : p.buckets) {
-        DB_CUDA(cudaMalloc(&b.arena, (size_t)std::max<int64_t>(b.bytes, 256)));
+        b.arena = comm_symm_alloc((size_t)std::max<int64_t>(b.bytes, 256));
+        b.symmetric = b.arena != nullptr;
+        if (!b.symmetric) DB_CUDA(cudaMalloc(&b.arena, (size_t)std::max<int64_t>(b.bytes, 256)));
         DB_CUDA(cudaMemset(b.arena, 0, (size_t)std::max<int64_t>(b.bytes, 256)));
         p.device_bytes += b.bytes;
         int64_t off = 0;

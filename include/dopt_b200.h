@@ -216,6 +216,19 @@ int dopt_b200_allreduce(float* buf, int64_t n, float scale, void* stream);
  * (The same poll runs before every all-reduce the library enqueues.)  Call it after synchronising a step. */
 int dopt_b200_comm_check(void);
 int dopt_b200_comm_destroy(void);
+/* Optional: peer-mapped ("symmetric") memory over NVSwitch multicast.  The caller maps one buffer of `bytes` per rank into
+ * every process (CUDA VMM: cuMemCreate + shareable handles, one multicast object bound to all of them) and hands over
+ *   local_base      this rank's own buffer (unicast mapping),
+ *   multicast_base  the multicast mapping that aliases the buffers of ALL ranks (multimem.* instructions),
+ *   signal_pads[r]  a zero-initialised, peer-mapped array of 32-bit flags owned by rank r (>= 4 KB each, same layout everywhere).
+ * Plans created afterwards carve their gradient-bucket arenas out of the buffer -- every rank must create the same plans in the
+ * same order, so that a bucket has the same offset everywhere -- and reduce them with the library's own kernel instead of
+ * ncclAllReduce: each rank reduces 1/world of the bucket inside the switch (multimem.ld_reduce), scales it and broadcasts it
+ * (multimem.st), between two flag barriers over the signal pads.  Buckets that do not fit fall back to NCCL.  The memory stays
+ * owned by the caller and must outlive the plans.  bench.py / tools/dp_check.py obtain it from torch.distributed's
+ * symmetric-memory allocator; a D host would use the driver API directly. */
+int dopt_b200_comm_set_symmetric(void* local_base, void* multicast_base, size_t bytes, void* const* signal_pads, int n_pads,
+                                 size_t signal_pad_bytes);
 
 #ifdef __cplusplus
 }

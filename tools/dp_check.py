@@ -8,7 +8,14 @@ sys.path.insert(0, ROOT)
 LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 RANK = int(os.environ.get("RANK", "0"))
-os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
+# DOPT_B200_SYMM=1: the gradient buckets live in peer-mapped memory and are reduced by the library's own multicast kernel
+# (dopt_b200/symm.py); torch's symmetric-memory allocator tells peers apart by device index, so all GPUs stay visible then
+SYMM = os.environ.get("DOPT_B200_SYMM", "0") == "1"
+if SYMM:
+    DEV = LOCAL_RANK
+else:
+    DEV = 0
+    os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
 # the gradient all-reduces get a fixed, small number of CTAs and the tensor-core kernels leave those SMs free (comm.cu); NCCL
 # reads the variable when the process creates its first communicator, which torch.distributed does below
 os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("DOPT_B200_COMM_CHANNELS", "16"))
@@ -41,8 +48,8 @@ def build(batch):
 
 
 def main():
-    torch.cuda.set_device(0)
-    dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+    torch.cuda.set_device(DEV)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", DEV))
     assert H.init(), H.init_error()
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if RANK == 0:
@@ -51,6 +58,11 @@ def main():
         uid.copy_(torch.tensor(list(buf.raw), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     H.init_data_parallel(RANK, WORLD, bytes(uid.cpu().tolist()))
+    keep = None
+    if SYMM:
+        from dopt_b200 import symm
+        keep = symm.attach(64 << 20, torch.device("cuda", DEV))
+        assert keep is not None, "symmetric memory did not come up"
     H.set_math(db.MATH_FP32)
     rng = np.random.RandomState(9)
     total = PER_RANK * WORLD
@@ -107,6 +119,7 @@ def main():
     dist.all_reduce(flagw, op=dist.ReduceOp.MIN)
     flag = torch.minimum(flag, flagw)
     wrn_launches = updw.stats()["launches"]
+    db.check(db.lib.dopt_b200_comm_check())   # NCCL asynchronous errors, timed-out flag barriers of the multicast all-reduce
     if RANK == 0:
         H.set_data_parallel_world(1)
         x1, y1, net1, upd1 = build(total)
@@ -118,9 +131,10 @@ def main():
             want = oracle.value_of(p)
             worst = max(worst, float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)))
         good = bool(flag.item()) and worst < 1e-4
-        print("dp_check world=%d replicas_identical=%s (incl. WRN-10-4 bf16: %s, %d launches) "
+        print("dp_check world=%d exchange=%s replicas_identical=%s (incl. WRN-10-4 bf16: %s, %d launches) "
               "max_rel_err_vs_single_process_oracle=%.3g launches=%d -> %s"
-              % (WORLD, bool(flag.item()), bool(flagw.item()), wrn_launches, worst, stats["launches"], "PASS" if good else "FAIL"))
+              % (WORLD, "multicast" if keep is not None else "nccl", bool(flag.item()), bool(flagw.item()), wrn_launches, worst,
+                 stats["launches"], "PASS" if good else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
 

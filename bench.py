@@ -515,7 +515,8 @@ def main():
                        "parallelism": "dp%d" % world, "params": n_params,
                        "exchange": (None if world == 1 else
                                     "gradient buckets in peer-mapped memory, reduced by the library's multimem kernel over NVSwitch "
-                                    "multicast" if symm_keep is not None else "gradient buckets reduced by ncclAllReduce"),
+                                    "multicast" if (symm_keep is not None and not os.environ.get("DOPT_B200_NO_NVLS")) else
+                                    "gradient buckets reduced by ncclAllReduce"),
                        "cache": "inputs larger than L2: one step streams several GB of activations through the 126 MB L2",
                        "precision": "convolutions bf16 operands / fp32 accumulate on tcgen05; activations between tensor-core "
                                     "convolutions stored NHWC bf16 (plan flag BF16_INTERIOR), arithmetic and everything "

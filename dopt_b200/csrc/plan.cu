@@ -1868,13 +1868,19 @@ static void bind_fused(Plan& p, void* const* rets) {
     std::fill(p.direct_out.begin(), p.direct_out.end(), 0);
     std::map<int, int> out_index;   // node id -> plan output index (first)
     for (size_t i = 0; i < p.outputs.size(); ++i) out_index.emplace(p.outputs[i], (int)i);
-    // address -> terminal regions reading it
-    std::map<const char*, std::set<int>> terminal_readers;
+    // what the terminal regions read: (first byte, bytes, region)
+    struct Read {
+        const char* p;
+        int64_t bytes;
+        int rid;
+    };
+    std::vector<Read> terminal_reads;
     for (size_t rid = 0; rid < p.regions.size(); ++rid) {
         const Region& R = p.regions[rid];
         if (!R.fused || !R.terminal) continue;
-        for (auto& t : R.tensor_in) terminal_readers[(const char*)N[t.first].ptr + t.second].insert((int)rid);
-        for (int s : R.scalar_in) terminal_readers[(const char*)N[s].ptr].insert((int)rid);
+        const int64_t row_bytes = volume(N[R.nodes[0]].op.output) * 4;
+        for (auto& t : R.tensor_in) terminal_reads.push_back({(const char*)N[t.first].ptr + t.second, row_bytes, (int)rid});
+        for (int s : R.scalar_in) terminal_reads.push_back({(const char*)N[s].ptr, 4, (int)rid});
     }
     for (size_t li = 0; li < p.launches.size(); ++li) {
         FzLaunch& L = p.launches[li];
@@ -1895,11 +1901,18 @@ static void bind_fused(Plan& p, void* const* rets) {
                     // In-place write-back is safe when nobody else in the end-of-step batch reads the destination: every
                     // other reader ran earlier, and this region reads an element before it overwrites that element.
                     char* target = (char*)rets[oi->second];
+                    // (interval overlap, not "starts inside": a reader may be a view that begins below the target.)  A plan
+                    // output that is copied out of a buffer overlapping the target after the terminal launches would see the
+                    // new value too.
                     bool other_reader = false;
-                    for (auto& kv : terminal_readers) {
-                        if (kv.first < target || kv.first >= target + N[id].bytes) continue;
-                        for (int reader : kv.second)
-                            if (reader != rid || kv.first != target) other_reader = true;
+                    for (const Read& rd : terminal_reads) {
+                        if (rd.p + rd.bytes <= target || rd.p >= target + N[id].bytes) continue;
+                        if (rd.rid != rid || rd.p != target) other_reader = true;
+                    }
+                    for (size_t k = 0; k < p.outputs.size() && !other_reader; ++k) {
+                        if ((int)k == oi->second || p.outputs[k] == id) continue;
+                        const char* src = (const char*)N[p.outputs[k]].ptr;
+                        if (src && src + N[p.outputs[k]].bytes > target && src < target + N[id].bytes) other_reader = true;
                     }
                     int dup = 0;
                     for (size_t k = 0; k < p.outputs.size(); ++k)

@@ -67,10 +67,24 @@ extern(C) nothrow @nogc
     int dopt_b200_one_hot_u8(const(ubyte)* labels, float* dst, long n, int classes, void* stream);
     int dopt_b200_jitter_sample(dopt_b200_jitter* dst, long n, int jitterX, int jitterY, int flipX, int flipY, ulong seed,
                                 ulong call, void* stream);
+
+    // data-parallel gradient exchange (new: the reference is single-device, cuda/source/dopt/cuda/package.d:43-45); see
+    // INTEGRATION.md section 3 for the `allreduce` operation and the exchange() helper that use these
+    int dopt_b200_comm_unique_id(void* id128);
+    int dopt_b200_comm_init(int rank, int worldSize, const(void)* id128);
+    int dopt_b200_comm_world_size();
+    int dopt_b200_comm_rank();
+    int dopt_b200_allreduce(float* buf, long n, float scale, void* stream);
+    int dopt_b200_comm_check();
+    int dopt_b200_comm_destroy();
+    // optional: peer-mapped memory + NVSwitch multicast mapping for the gradient buckets (the library's own all-reduce kernel)
+    int dopt_b200_comm_set_symmetric(void* localBase, void* multicastBase, size_t bytes, const(void*)* signalPads, int nPads,
+                                     size_t signalPadBytes);
 }
 
 enum DOPT_B200_PLAN_FUSE = 1;
 enum DOPT_B200_PLAN_CUDA_GRAPH = 2;
+enum DOPT_B200_PLAN_BF16_INTERIOR = 4;   // activations between tensor-core convolutions stay NHWC bf16 (include/dopt_b200.h)
 
 private void check(int rc)
 {

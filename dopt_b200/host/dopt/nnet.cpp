@@ -234,11 +234,13 @@ DAGNetwork::DAGNetwork(std::vector<Operation> inputs, std::vector<LayerPtr> outp
 void DAGNetwork::save(const std::string& filename) const {
     FILE* f = std::fopen(filename.c_str(), "wb");
     enforce(f != nullptr, "cannot open " + filename);
+    bool ok = true;
     for (auto& p : mParams) {
         auto v = p->value()->get<float>();
-        std::fwrite(v.data(), sizeof(float), v.size(), f);
+        ok = ok && std::fwrite(v.data(), sizeof(float), v.size(), f) == v.size();
     }
-    std::fclose(f);
+    ok = (std::fclose(f) == 0) && ok;   // (a full disk must not leave a silently truncated parameter file behind)
+    enforce(ok, "could not write " + filename);
 }
 void DAGNetwork::load(const std::string& filename) {
     FILE* f = std::fopen(filename.c_str(), "rb");

@@ -355,22 +355,25 @@ def test_backward_bn_statistics_in_the_feature_gradient_epilogue(monkeypatch, ca
     """Plan pass H2 (opt-in, DOPT_B200_EPI_BNGRAD=1: measured slower than the separate statistics launch on the WRN-28-10
     shapes, profiles/r02_summary.md): the unit-stride convolutionFeaturesGrad that writes dy of a flat batchNormGrad accumulates sum(g) and
     sum(g * (x - mean)) in its epilogue (tc_kernel<.., EPI = 3>) from the bf16 values it stores -- the same values the
-    statistics kernel would read back -- so only the fp32 summation order differs: the forward pass of step 0 is untouched
-    (bit-identical loss and predictions) and the parameters agree within fp32 rounding of the sums (1e-4 of the update;
-    the filter gradients' fp32 atomics alone give ~1e-5 from run to run)."""
+    statistics kernel would read back -- so only the fp32 summation order differs.  Stated tolerance: step-0 loss within 5e-4
+    relative (the forward pass does not change; two runs of one plan differ by up to 6e-5 through the atomics of the forward
+    statistics), the median parameter tensor's update within 0.12 and every tensor within 0.25 -- the measured run-to-run
+    differences of the unchanged plan are 0.06 / 0.11."""
     base = {"DOPT_B200_EPI_BNGRAD": "1"}
     off = {}
 
-    def worst_update_difference(pa, pb, init):
-        worst = 0.0
+    def update_differences(pa, pb, init):
+        out = []
         for a, b, i0 in zip(pa, pb, init):
             du = float(np.linalg.norm((a - i0).astype(np.float64)))
             if du > 1e-12:
-                worst = max(worst, float(np.linalg.norm((a - b).astype(np.float64))) / du)
-        return worst
-    # one step: the update is lr * gradient at identical parameters.  Two runs of the SAME plan already differ -- the forward
-    # statistics and the filter gradients are summed with fp32 atomics, a bf16 rounding flips here and there -- so the bound is
-    # relative to that measured run-to-run noise.
+                out.append(float(np.linalg.norm((a - b).astype(np.float64))) / du)
+        return np.array(out)
+    # one step: the update is lr * gradient at identical parameters.  Two runs of the SAME bf16-interior plan already differ:
+    # the forward statistics are summed with fp32 atomics, a few bf16 roundings flip, the step-0 loss lands on one of three or
+    # four values 1.5e-5 apart, and the gradients of two runs that landed on different values differ by 0.06 of the update in
+    # the median tensor and 0.11 in the worst (runs that landed on the same value: 1e-3; fp32 storage: 3e-6) -- measured with
+    # tools/noise_probe.py, profiles/r02_parity.md.  The bounds are therefore those of that noise, not tighter.
     o0, p0, init, st0, c0 = _interior_run(monkeypatch, capfd, off, steps=1)
     o0b, p0b, _, _, _ = _interior_run(monkeypatch, capfd, off, steps=1)
     o1, p1, _, st1, c1 = _interior_run(monkeypatch, capfd, base, steps=1)
@@ -378,10 +381,12 @@ def test_backward_bn_statistics_in_the_feature_gradient_epilogue(monkeypatch, ca
     assert st1["launches"] <= st0["launches"] - c1[1]           # one statistics launch less per fused batch norm
     assert abs(float(o0[0][0]) - float(o1[0][0])) <= 5e-4 * abs(float(o0[0][0]))
     assert np.abs(o0[0][1] - o1[0][1]).max() <= 5e-3
-    noise = worst_update_difference(p0, p0b, init)
-    worst = worst_update_difference(p0, p1, init)
-    print("backward statistics in the epilogue: worst gradient difference", worst, "run-to-run noise", noise)
-    assert worst <= max(2e-2, 4 * noise)
+    noise = update_differences(p0, p0b, init)
+    diff = update_differences(p0, p1, init)
+    print("backward statistics in the epilogue: gradient difference median %.3g worst %.3g; run-to-run noise median %.3g worst %.3g"
+          % (np.median(diff), diff.max(), np.median(noise), noise.max()))
+    assert np.median(diff) <= 0.12
+    assert diff.max() <= 0.25
 
 
 def test_residual_sum_in_the_convolution_epilogue(monkeypatch, capfd):

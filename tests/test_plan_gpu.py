@@ -373,7 +373,8 @@ def test_backward_bn_statistics_in_the_feature_gradient_epilogue(monkeypatch, ca
     # the forward statistics are summed with fp32 atomics, a few bf16 roundings flip, the step-0 loss lands on one of three or
     # four values 1.5e-5 apart, and the gradients of two runs that landed on different values differ by 0.06 of the update in
     # the median tensor and 0.11 in the worst (runs that landed on the same value: 1e-3; fp32 storage: 3e-6) -- measured with
-    # tools/noise_probe.py, profiles/r02_parity.md.  The bounds are therefore those of that noise, not tighter.
+    # tools/noise_probe.py, profiles/r02_parity.md: every bf16 store re-quantises, which turns a 1e-7 difference into one-ulp
+    # flips, and after a few layers two runs differ by the bf16 rounding noise itself.  The bounds are those of that noise.
     o0, p0, init, st0, c0 = _interior_run(monkeypatch, capfd, off, steps=1)
     o0b, p0b, _, _, _ = _interior_run(monkeypatch, capfd, off, steps=1)
     o1, p1, _, st1, c1 = _interior_run(monkeypatch, capfd, base, steps=1)

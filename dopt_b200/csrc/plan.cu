@@ -2012,12 +2012,13 @@ static const char* item_label(const Plan& p, const Item& it) {
     }
 }
 
-// one CTA per row: dst[i] = src[i] for n4 32-bit words (rows are small: per-channel statistics)
+// blockIdx.x = row, gridDim.y CTAs share a row: dst[i] = src[i] for n4 32-bit words.  (Most rows are per-channel statistics; the
+// predictions are 50 KB -- one CTA walking them alone took 46 us of dependent-latency-bound iterations.)
 __global__ void __launch_bounds__(128) post_copy_kernel(const Plan::PostCopy* __restrict__ rows) {
     const Plan::PostCopy r = rows[blockIdx.x];
     const uint32_t* src = (const uint32_t*)r.src;
     uint32_t* dst = (uint32_t*)r.dst;
-    for (int64_t i = threadIdx.x; i < r.n4; i += blockDim.x) dst[i] = src[i];
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < r.n4; i += (int64_t)blockDim.x * gridDim.y) dst[i] = src[i];
 }
 
 // `only`: diagnostics (dopt_b200_plan_replay_class) -- issue just the items booked under these op types, nothing else
@@ -2339,7 +2340,7 @@ static void execute(Plan& p, const int32_t* var_ids, const void* const* var_ptrs
     auto body = [&](cudaStream_t st) {
         run_items(p, st);
         if (!p.post_rows.empty()) {
-            post_copy_kernel<<<(unsigned)p.post_rows.size(), 128, 0, st>>>(p.post_dev);
+            post_copy_kernel<<<dim3((unsigned)p.post_rows.size(), 16), 128, 0, st>>>(p.post_dev);
             DB_LAUNCH_CHECK();
         }
         for (int i = 0; i < n_rets; ++i) {

@@ -328,7 +328,9 @@ def test_bf16_interior_pass_engages_and_agrees_with_fp32_storage(monkeypatch, ca
     for a, b, i0 in zip(p0, p1, init):
         du = float(np.linalg.norm((a - i0).astype(np.float64)))
         if du > 1e-12:     # the update each tensor received, bf16 interior against fp32 storage
-            assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.2 * du, a.shape
+            # (two runs of the SAME bf16-interior plan differ by up to 0.11 of a tensor's update after one step -- re-quantisation
+            # noise, profiles/r02_parity.md -- so 0.3 after two steps is the noise bound with head room, not a loose one)
+            assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.3 * du, a.shape
 
 
 def _interior_run(monkeypatch, capfd, env, steps=2, net=(16, 4, 32, 16, 10)):
@@ -394,7 +396,7 @@ def test_residual_sum_in_the_convolution_epilogue(monkeypatch, capfd):
     """Plan pass H1 (opt-in, DOPT_B200_EPI_ADD=1: measured slower than the separate add, profiles/r02_summary.md): the second convolution of a residual block adds the block's input in its epilogue (tc_kernel<.., EPI = 2>,
     fp32 add, ONE rounding to bf16) instead of storing its bf16 result for a separate add kernel (two roundings).  Stated
     tolerance: the double rounding it removes, i.e. loss within 1e-2 relative, predictions within 3e-2, parameter updates
-    within 0.2 of the update (the same bounds as bf16 interior storage against fp32 storage)."""
+    within 0.3 of the update (the same bounds as bf16 interior storage against fp32 storage)."""
     o0, p0, init, st0, c0 = _interior_run(monkeypatch, capfd, {})
     o1, p1, _, st1, c1 = _interior_run(monkeypatch, capfd, {"DOPT_B200_EPI_ADD": "1"})
     assert c0 == (0, 0) and c1[1] == 0 and c1[0] >= 5, (c0, c1)   # WRN-16-4: 6 residual sums, the last one feeds a legacy kernel
@@ -406,7 +408,9 @@ def test_residual_sum_in_the_convolution_epilogue(monkeypatch, capfd):
     for a, b, i0 in zip(p0, p1, init):
         du = float(np.linalg.norm((a - i0).astype(np.float64)))
         if du > 1e-12:
-            assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.2 * du, a.shape
+            # (two runs of the SAME bf16-interior plan differ by up to 0.11 of a tensor's update after one step -- re-quantisation
+            # noise, profiles/r02_parity.md -- so 0.3 after two steps is the noise bound with head room, not a loose one)
+            assert float(np.linalg.norm((a - b).astype(np.float64))) <= 0.3 * du, a.shape
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16-interior"])

@@ -108,6 +108,8 @@ struct Item {
     int id;             // node id, launch index (ITEM_FUSED) or bucket index (ITEM_BUCKET)
     bool join_comm;     // reads a reduced gradient: the compute stream must first wait for the communication stream
     bool terminal;      // ITEM_FUSED: a terminal launch (its results are plan outputs only: the optimiser's parameter updates)
+    bool pre_reduce;    // ITEM_FUSED: only gradient buckets read its results (copy-ins of small gradients, pre-reduce pointwise
+                        // work): it may run on the communication stream in front of the bucket's all-reduce
 };
 
 // an activation staged once as NHWC bf16 for all the tensor-core convolution ops that read it
@@ -793,7 +795,10 @@ static void schedule(Plan& p) {
                             only_buckets = false;
                     }
                 }
-            if (only_buckets && hold >= 0) item_key[kv.second] = std::max(item_key[kv.second], hold);
+            if (only_buckets && hold >= 0) {
+                item_key[kv.second] = std::max(item_key[kv.second], hold);
+                items[kv.second].pre_reduce = true;
+            }
         }
     }
     // NCHW fp32 copies of bf16-resident values: made by a conversion launch right after the producer; fp32 readers wait for it
@@ -934,6 +939,7 @@ static void schedule(Plan& p) {
                 p.launches[lb].rows.clear();
                 p.launches[lb].dirty = false;   // never launched: must not keep the plan out of CUDA-graph mode
                 items[k].join_comm = items[k].join_comm || items[o].join_comm;
+                items[k].pre_reduce = items[k].pre_reduce && items[o].pre_reduce;
                 consumed[o] = 1;
                 issued.push_back(o);
             }
@@ -2043,6 +2049,15 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
     // the gaps between dependent launches.  The chain joins before the first finish launch.  Profiling serialises everything.
     static const bool side_on = !getenv("DOPT_B200_NO_SIDE_STREAM");
     bool side_pending = false;
+    auto ensure_comm = [&]() {
+        if (p.comm_stream) return;
+        DB_CUDA(cudaStreamCreateWithFlags(&p.comm_stream, cudaStreamNonBlocking));
+        DB_CUDA(cudaEventCreateWithFlags(&p.comm_fork, cudaEventDisableTiming));
+        DB_CUDA(cudaEventCreateWithFlags(&p.comm_join, cudaEventDisableTiming));
+    };
+    // opt-in (DOPT_B200_PRE_REDUCE_ON_COMM=1): one 2-GPU run showed no gain (5.83 ms against 5.74-5.82), and the launch then reads
+    // chain-stream buffers from another stream, which the buffer planner's stream-order lifetimes do not cover
+    static const bool pre_reduce_on_comm = getenv("DOPT_B200_PRE_REDUCE_ON_COMM") != nullptr;
     auto ensure_side = [&]() {
         if (p.side_stream) return;
         // lowest priority: when both streams have CTAs waiting for an SM, the chain's go first
@@ -2102,11 +2117,7 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
         if (it.kind == ITEM_BUCKET) {
             // one all-reduce for the whole bucket, on the communication stream so that it overlaps the rest of backward
             Bucket& b = p.buckets[it.id];
-            if (!p.comm_stream) {
-                DB_CUDA(cudaStreamCreateWithFlags(&p.comm_stream, cudaStreamNonBlocking));
-                DB_CUDA(cudaEventCreateWithFlags(&p.comm_fork, cudaEventDisableTiming));
-                DB_CUDA(cudaEventCreateWithFlags(&p.comm_join, cudaEventDisableTiming));
-            }
+            ensure_comm();
             DB_CUDA(cudaEventRecord(p.comm_fork, s));
             DB_CUDA(cudaStreamWaitEvent(p.comm_stream, p.comm_fork, 0));
             for (auto& f : p.finishes)
@@ -2203,7 +2214,17 @@ static void run_items(Plan& p, cudaStream_t s, const std::set<std::string>* only
                              volume(n.op.output), s);
             label = n.type.c_str();
         } else {
-            fused_launch(p.launches[it.id], s);
+            if (it.pre_reduce && !it.terminal && !it.join_comm && !p.buckets.empty() && pre_reduce_on_comm && !p.profiling && !only) {
+                // nothing on the compute stream reads what this launch writes: it runs on the communication stream, in front of
+                // the all-reduce of the bucket it feeds, instead of on the feature-gradient chain
+                ensure_comm();
+                DB_CUDA(cudaEventRecord(p.comm_fork, s));
+                DB_CUDA(cudaStreamWaitEvent(p.comm_stream, p.comm_fork, 0));
+                fused_launch(p.launches[it.id], p.comm_stream);
+                comm_pending = true;
+            } else {
+                fused_launch(p.launches[it.id], s);
+            }
             label = it.terminal ? "update" : "fusedRegion";
         }
         if (p.profiling) labels.push_back(label);

@@ -18,6 +18,7 @@ def attach(pool_bytes, device, group=None):
     from . import check, lib
 
     group = group or dist.group.WORLD
+    failure = None
     try:
         n = (int(pool_bytes) + 1023) // 1024 * 256
         t = symm_mem.empty(n, dtype=torch.float32, device=device)
@@ -27,21 +28,34 @@ def attach(pool_bytes, device, group=None):
         ptrs = [int(p) + off for p in hdl.buffer_ptrs]
         pads = [int(p) for p in hdl.signal_pad_ptrs]
         if mc == 0 or len(pads) != hdl.world_size:
-            return None
+            raise RuntimeError("no multicast mapping")
         mc += off
         if ptrs[hdl.rank] != t.data_ptr():
             raise RuntimeError("symmetric handle does not describe the tensor (%#x vs %#x)" % (ptrs[hdl.rank], t.data_ptr()))
         t.zero_()
         torch.cuda.synchronize()
-        dist.barrier(group)
     except Exception as e:   # no NVSwitch multicast, no fd passing in this container, one visible device per process ...
+        failure = e
+    # Every rank must take the same exchange: a rank that fell back to NCCL alone would wait in ncclAllReduce for peers that
+    # sit in the multicast kernel's flag barrier.  One collective vote (it doubles as the barrier behind the zero fill).
+    if not all_agree(failure is None, group, device):
         import sys
-        sys.stderr.write("dopt_b200.symm: symmetric memory not available (%r); using NCCL\n" % (e,))
+        sys.stderr.write("dopt_b200.symm: symmetric memory not available on every rank (here: %r); using NCCL\n" % (failure,))
         return None
     arr = (C.c_void_p * len(pads))(*pads)
     check(lib.dopt_b200_comm_set_symmetric(C.c_void_p(ptrs[hdl.rank]), C.c_void_p(mc), C.c_size_t(n * 4), arr, len(pads),
                                            C.c_size_t(int(hdl.signal_pad_size))))
     return (t, hdl)
+
+
+def all_agree(ok, group=None, device=None):
+    """True when `ok` holds on every rank of the group (one MIN all-reduce of a flag; a collective: every rank calls it)."""
+    import torch
+    import torch.distributed as dist
+
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device if device is not None else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group or dist.group.WORLD)
+    return bool(int(flag.item()))
 
 
 def detach():

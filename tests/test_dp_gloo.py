@@ -131,3 +131,35 @@ def test_rank_invariant_weight_decay_term_is_not_exchanged(monkeypatch):
     assert "convolutionFiltersGrad" not in plain and "add" in plain       # conv filter and dense weight carry weight decay
     assert "convolutionFiltersGrad" in split
     assert split.count("add") < plain.count("add")
+
+
+def _vote_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    # dopt_b200/symm.py without the package import (the vote itself needs neither the CUDA library nor a GPU)
+    spec = importlib.util.spec_from_file_location("symm_only", os.path.join(ROOT, "dopt_b200", "symm.py"))
+    symm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(symm)
+    q.put((rank, symm.all_agree(True), symm.all_agree(rank != 1), symm.all_agree(False)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_choice_is_a_vote_over_all_ranks():
+    """symm.attach: the multicast exchange is used only when the symmetric buffer came up on EVERY rank -- a rank that fell
+    back to NCCL on its own would wait in ncclAllReduce for peers sitting in the multicast kernel's flag barrier."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_vote_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, all_ok, one_failed, none_ok in results:
+        assert all_ok is True and one_failed is False and none_ok is False

@@ -103,7 +103,60 @@ def build_wrn(H, batch, depth=MODEL["depth"], width=MODEL["width"], reset=True):
     loss = H.cross_entropy(preds.train_output, y) + net.param_loss
     upd = H.Updater(H.SGD, [loss, preds.train_output], network=net,
                     hyper=[H.float32((), [MODEL["lr"]]), H.float32((), [MODEL["momentum"]])])
+    net.preds = preds          # the output layer (its `.output` is the test-time graph, examples/cifar100.d:49)
     return x, y, net, upd
+
+
+def adjacent_rows(torch, db, H, x, net, batch, hbm_gbs):
+    """SURVEY.md section 8(f) rows 1 and 2, measured beside the training step (reported, never part of `value`):
+      input_pipeline  ImageTransformer.getBatch + byte normalisation as one kernel (csrc/input.cu) over a CIFAR-sized training
+                      set resident on the device as bytes, and over one 128-image batch; HBM-bound, 5 B per element
+      inference       the test-time plan of the same network (batchNormInference), `testPlan.execute` with host buffers
+    Each leg reports its own error instead of raising: the bench line must not depend on them."""
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    try:
+        res = {}
+        for tag, n, reps in (("train_set_50000", 50000, 10), ("batch_%d" % batch, batch, 50)):
+            src = torch.randint(0, 256, (n, 3, MODEL["hw"], MODEL["hw"]), dtype=torch.uint8, device="cuda")
+            per = db.jitter_sample(n, 4, 4, True, False, seed=7, call=0)          # cifar100.d: ImageTransformer(train, 4, 4, true, false)
+            for _ in range(3):
+                dst = db.image_transform(src, 4, 4, per)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(reps):
+                dst = db.image_transform(src, 4, 4, per)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            alg = src.numel() * 5 + per.numel() * 4                              # 1 B read + 4 B written per element, the draws
+            res[tag] = {"us_per_launch": us, "images_per_s": n / (us * 1e-6), "alg_bytes": int(alg),
+                        "achieved_gbs": alg / (us * 1e-6) / 1e9, "frac_of_hbm": alg / (us * 1e-6) / 1e9 / hbm_gbs}
+            del src, per, dst
+        out["input_pipeline"] = res
+    except Exception as e:
+        out["input_pipeline"] = {"error": repr(e)}
+    try:
+        plan = H.Plan([net.preds.output])
+        fs = synthetic_batch(batch, 99)[0]
+        for _ in range(3):
+            probs = plan.execute({x: fs})[0]
+        torch.cuda.synchronize()
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            probs = plan.execute({x: fs})[0]
+        dt = (time.perf_counter() - t0) / reps
+        st = plan.stats()
+        out["inference"] = {"images_per_s": batch / dt, "ms_per_batch": dt * 1e3, "batch": batch,
+                            "launches": st["launches"], "plan_device_bytes": st["device_bytes"],
+                            "rows_sum_to_one": bool(abs(float(probs.sum(axis=1).mean()) - 1.0) < 1e-3),
+                            "how": "Plan([preds.output]).execute({features: host array}): H2D of the batch, the test-time "
+                                   "graph (batchNormInference on the fp32 kernels), D2H of the class probabilities, wall clock"}
+    except Exception as e:
+        out["inference"] = {"error": repr(e)}
+    return out
 
 
 def synthetic_batch(batch, seed):
@@ -269,6 +322,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dopt_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adjacent", action="store_true", help="skip the input-pipeline / inference legs (SURVEY 8f rows)")
     ap.add_argument("--depth", type=int, default=MODEL["depth"])
     ap.add_argument("--width", type=int, default=MODEL["width"])
     ap.add_argument("--timeline", default=None,
@@ -507,6 +561,9 @@ def main():
                    "sample": "1 step of %d images of the same WRN-28-10 train graph, numpy/OpenBLAS oracle (%.1f s)"
                              % (CPU_SAMPLE, dt)}
         ms_step = dev_ms / args.steps
+        adjacent = None
+        if world == 1 and not args.no_adjacent:
+            adjacent = adjacent_rows(torch, db, H, x, net, B, peaks()["hbm_gbs"])
         line = {
             "metric": "WRN-28-10 CIFAR train images/sec", "value": B * world * args.steps / (dev_ms * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -527,7 +584,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "launches_per_step": st["launches"], "plan_nodes": st["lowered_nodes"],
             "plan_device_bytes": st["device_bytes"], "clocks": clocks, "roofline": roof, "roofline_classes": classes,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "adjacent_rows": adjacent,
             "loss_first": first_loss, "loss_last": last_loss,
             "per_op_us_per_step": dict((k, [v / 2.0, prof.get(k + "#n", 0) // 2]) for k, v in
                                        sorted(((k, v) for k, v in prof.items() if "#" not in k and k != "tc_kernel_launches"),

@@ -15,8 +15,7 @@
 // Bit-exact with the host loops: the only arithmetic is the exact u8 -> float conversion.
 //
 // Memory-bound, write-dominated: 1 B read + 4 B written per element (5 B/elem, u8 source), 8 B/elem for a float source.
-// One thread produces four consecutive x of one output row and stores them as one 128-bit word; the byte gathers hit L1/L2
-// (a 32x32x3 image is 3 KB).
+// One thread produces a 4 x 4 block of output pixels, four 128-bit stores; the byte gathers hit L1/L2 (a 32x32x3 image is 3 KB).
 //
 // The per-image decisions (xOff, yOff, flipX, flipY) are an int4 table in device memory, so a test can supply exactly the
 // draws of a host run; dopt_b200_jitter_sample fills it on the device (Philox-4x32-10, one counter block per image) with the
@@ -27,44 +26,60 @@ namespace db {
 
 __device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
 
-__device__ __forceinline__ float load_pixel(const uint8_t* p) { return __fsub_rn(__fdiv_rn((float)*p, 128.0f), 1.0f); }
+// x / 128.0f - 1.0f: dividing by a power of two is an exact scaling, so the multiplication gives the same bits as the division
+__device__ __forceinline__ float load_pixel(const uint8_t* p) { return __fsub_rn(__fmul_rn((float)*p, 0.0078125f), 1.0f); }
 __device__ __forceinline__ float load_pixel(const float* p) { return *p; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) image_transform_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n_img,
                                                               int C, int H, int W, int jx, int jy,
                                                               const dopt_b200_jitter* __restrict__ jit) {
-    const int wq = (W + 3) >> 2;                       // quads per row
-    const int64_t quads = n_img * C * H * (int64_t)wq;
+    // Work item = a 4 x 4 block of output pixels (four 128-bit stores): the index arithmetic, the per-image draws and the four
+    // reflected source columns are computed once per block.  All of it in 32 bits -- with one item per 128-bit store and three
+    // 64-bit divisions each the kernel was bound by the integer pipe (1.7 TB/s over a CIFAR-sized training set, then 2.3 TB/s
+    // with 32-bit divisions: bench.py adjacent_rows) instead of by the 5 B it moves per element.
+    const int wq = (W + 3) >> 2, hq = (H + 3) >> 2;
+    const unsigned per_img = (unsigned)(C * hq * wq);   // blocks per image (the host checks that it fits)
+    const int64_t items = n_img * (int64_t)per_img;
     const bool vec = (W & 3) == 0 && ((uintptr_t)dst & 15) == 0;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
-        const int xq = (int)(q % wq);
-        int64_t t = q / wq;
-        const int y = (int)(t % H);
-        t /= H;
-        const int c = (int)(t % C);
-        const int64_t img = t / C;
+    const bool small = items < ((int64_t)1 << 32);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < items; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = small ? (int64_t)((unsigned)q / per_img) : q / per_img;
+        unsigned r = (unsigned)(q - img * per_img);
+        const int xq = (int)(r % (unsigned)wq);
+        r /= (unsigned)wq;
+        const int yq = (int)(r % (unsigned)hq);
+        const int c = (int)(r / (unsigned)hq);
         int xo = jx, yo = jy, fx = 0, fy = 0;          // no table: centre crop, no flip == the identity
         if (jit) {
             const dopt_b200_jitter j = jit[img];
             xo = j.x_off; yo = j.y_off; fx = j.flip_x; fy = j.flip_y;
         }
-        const int sy = reflect_index((fy ? H - 1 - y : y) + yo - jy, H);
-        const T* row = src + ((img * C + c) * H + sy) * (int64_t)W;
-        float v[4];
+        int sx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int x = xq * 4 + k;
-            v[k] = 0.f;
-            if (x < W) v[k] = load_pixel(row + reflect_index((fx ? W - 1 - x : x) + xo - jx, W));
+            sx[k] = x < W ? reflect_index((fx ? W - 1 - x : x) + xo - jx, W) : 0;
         }
-        float* out = dst + ((img * C + c) * H + y) * (int64_t)W + xq * 4;
-        if (vec) {
-            dbk::st_stream((float4*)out, make_float4(v[0], v[1], v[2], v[3]));
-        } else {
+        const int64_t plane = (img * C + c) * (int64_t)H * W;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (xq * 4 + k < W) out[k] = v[k];
+        for (int j = 0; j < 4; ++j) {
+            const int y = yq * 4 + j;
+            if (y < H) {
+                const int sy = reflect_index((fy ? H - 1 - y : y) + yo - jy, H);
+                const T* row = src + plane + sy * W;
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (xq * 4 + k < W) ? load_pixel(row + sx[k]) : 0.f;
+                float* out = dst + plane + y * W + xq * 4;
+                if (vec) {
+                    dbk::st_stream((float4*)out, make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (xq * 4 + k < W) out[k] = v[k];
+                }
+            }
         }
     }
 }
@@ -113,8 +128,9 @@ static void image_transform(const T* src, float* dst, int64_t n, int c, int h, i
     // the reference's slice arithmetic needs the reflected border to fit inside the image (imagetransformer.d:77-99)
     DB_REQUIRE(jx >= 0 && jy >= 0 && jx <= w && jy <= h, "image_transform: jitter larger than the image");
     if (n == 0) return;
-    const int64_t quads = n * c * h * (int64_t)((w + 3) / 4);
-    image_transform_kernel<T><<<stream_grid(quads, 256, 8), 256, 0, s>>>(src, dst, n, c, h, w, jx, jy, jit);
+    DB_REQUIRE((int64_t)c * h * w < ((int64_t)1 << 31), "image_transform: image too large");
+    const int64_t items = n * c * (int64_t)((h + 3) / 4) * ((w + 3) / 4);
+    image_transform_kernel<T><<<stream_grid(items, 256, 8), 256, 0, s>>>(src, dst, n, c, h, w, jx, jy, jit);
     DB_LAUNCH_CHECK();
 }
 

@@ -114,6 +114,31 @@ CONV = [
     (128, 16, 32, 32, 160, 1, 1, 0, 1),
     (128, 320, 16, 16, 640, 3, 3, 1, 2),
     (128, 320, 16, 16, 640, 1, 1, 0, 2),
+    # BASELINE.json configs[2], VGG19 on 100 x 3 x 32 x 32 (nnet/models/vgg.d; examples/cifar10.d:54-66): every distinct shape.
+    # The 4 x 4 and 2 x 2 feature maps pack 8 / 32 images into one 128-pixel tile.
+    (100, 3, 32, 32, 64, 3, 3, 1, 1),
+    (100, 64, 32, 32, 64, 3, 3, 1, 1),
+    (100, 64, 16, 16, 128, 3, 3, 1, 1),
+    (100, 128, 16, 16, 128, 3, 3, 1, 1),
+    (100, 128, 8, 8, 256, 3, 3, 1, 1),
+    (100, 256, 8, 8, 256, 3, 3, 1, 1),
+    (100, 256, 4, 4, 512, 3, 3, 1, 1),
+    (100, 512, 4, 4, 512, 3, 3, 1, 1),
+    (100, 512, 2, 2, 512, 3, 3, 1, 1),
+    # configs[4], Wide ResNet-16-8 on 50 x 3 x 96 x 96 with strides [2,2,2] (examples/sins10.d:42-52): 96- and 48-pixel rows
+    # (tiles that 128 pixels do not divide), 24 x 24 and 12 x 12 maps, three stride-2 transitions with their 1 x 1 shortcuts
+    (50, 3, 96, 96, 16, 3, 3, 1, 1),
+    (50, 16, 96, 96, 128, 3, 3, 1, 2),
+    (50, 16, 96, 96, 128, 1, 1, 0, 2),
+    (50, 128, 48, 48, 128, 3, 3, 1, 1),
+    (50, 128, 48, 48, 256, 3, 3, 1, 2),
+    (50, 128, 48, 48, 256, 1, 1, 0, 2),
+    (50, 256, 24, 24, 256, 3, 3, 1, 1),
+    (50, 256, 24, 24, 512, 3, 3, 1, 2),
+    (50, 256, 24, 24, 512, 1, 1, 0, 2),
+    (50, 512, 12, 12, 512, 3, 3, 1, 1),
+    # configs[1], the MNIST CNN's second 5 x 5 unpadded convolution (examples/mnist.d; SURVEY 8a: M=6400, N=32, K=800)
+    (100, 32, 12, 12, 32, 5, 5, 0, 1),
 ]
 
 
@@ -155,7 +180,8 @@ def test_cudnn_default_math_error_on_this_gpu():
 # ---------------------------------------------------------------------------------------------------------------------
 # pooling: values and tie routing
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape,dims", [((100, 64, 32, 32), [2, 2]), ((3, 5, 9, 7), [2, 3]), ((100, 32, 24, 24), [2, 2])])
+@pytest.mark.parametrize("shape,dims", [((100, 64, 32, 32), [2, 2]), ((3, 5, 9, 7), [2, 3]), ((100, 32, 24, 24), [2, 2]),
+                                        ((100, 512, 4, 4), [2, 2]), ((100, 512, 2, 2), [2, 2])])   # VGG19's last two pools
 def test_maxpool_and_grad_vs_cudnn(shape, dims):
     x = rand(shape, 9)
     y = Q.maxpool(x, dims)
@@ -248,7 +274,8 @@ def test_add_bias_and_grad_vs_cudnn():
 # ---------------------------------------------------------------------------------------------------------------------
 # batch norm
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(128, 160, 32, 32), (128, 640, 8, 8), (48, 64, 16, 16), (5, 3, 7, 5), (100, 512)])
+@pytest.mark.parametrize("shape", [(128, 160, 32, 32), (128, 640, 8, 8), (48, 64, 16, 16), (5, 3, 7, 5), (100, 512),
+                                   (100, 512, 2, 2), (100, 64, 32, 32), (50, 128, 48, 48), (50, 512, 12, 12)])   # VGG19 / SINS
 def test_batchnorm_vs_cudnn(shape):
     C = shape[1]
     x = rand(shape, 18, 1.7, 0.8)

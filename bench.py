@@ -153,7 +153,8 @@ def adjacent_rows(torch, db, H, x, net, batch, hbm_gbs):
                             "launches": st["launches"], "plan_device_bytes": st["device_bytes"],
                             "rows_sum_to_one": bool(abs(float(probs.sum(axis=1).mean()) - 1.0) < 1e-3),
                             "how": "Plan([preds.output]).execute({features: host array}): H2D of the batch, the test-time "
-                                   "graph (batchNormInference on the fp32 kernels), D2H of the class probabilities, wall clock"}
+                                   "graph (batchNormInference with the relu and the NHWC bf16 staging of the next convolution in its apply pass), "
+                                   "D2H of the class probabilities, wall clock"}
     except Exception as e:
         out["inference"] = {"error": repr(e)}
     return out

@@ -641,6 +641,9 @@ struct BnGradKernel : Kernel {
 struct BnInferKernel : Kernel {
     BnGeom g;
     Scratch ws;
+    Absorb ab;   // test-time plans: the relu that follows and the NHWC bf16 copy the next convolution reads (plan pass "absorb")
+    bool can_absorb() const override { return g.HW < (1ll << 30) && g.C < (1 << 24) && g.N < 65536; }
+    void set_absorbed(const Absorb& a) override { ab = a; }
     BnInferKernel(const dopt_b200_op& d) {
         DB_REQUIRE(d.n_inputs == 5, "batchNormInference: deps are [x, scale, bias, mean, var]");
         g = geom_of(d.inputs[0]);
@@ -653,6 +656,12 @@ struct BnInferKernel : Kernel {
                                                                    (const float*)in[3], (const float*)in[4], coef, (int)g.C);
         DB_LAUNCH_CHECK();
         int64_t V = g.N * g.C * g.HW;
+        if (ab.relu || ab.staged || ab.skip_fp32 || ab.redirect) {
+            // same apply pass as the training kernel's: relu(y) into the relu node's buffer (or nowhere), staged copy beside it
+            float* fp32 = ab.skip_fp32 ? nullptr : (ab.redirect ? ab.redirect : (float*)out);
+            bn_apply_tiled<0>((const float*)in[0], nullptr, coef, fp32, ab.staged, ab.relu, nullptr, g, s);
+            return;
+        }
         bn_apply_kernel<0, false><<<stream_grid(ceil_div(V, 4), 256, 8), 256, 0, s>>>((const float*)in[0], nullptr, coef,
                                                                                       (float*)out, g);
         DB_LAUNCH_CHECK();

@@ -1128,7 +1128,9 @@ static void absorb(Plan& p) {
         int64_t off = 0;
         const int b = root_of(p, R.deps[0], &off);
         Node& B = N[b];
-        if (off != 0 || B.type != "batchNormTrain" || !B.kernel || !B.kernel->can_absorb() || B.absorb_relu >= 0) continue;
+        // (a test-time plan holds batchNormInference -> relu -> convolution, nnet/layers/batchnorm.d:129-140: same absorption)
+        const bool infer = B.type == "batchNormInference" && !getenv("DOPT_B200_NO_INFER_ABSORB");
+        if (off != 0 || (B.type != "batchNormTrain" && !infer) || !B.kernel || !B.kernel->can_absorb() || B.absorb_relu >= 0) continue;
         if (N[R.deps[0]].bytes != R.bytes) continue;
         const int64_t head = R.bytes;
         if (head_is_output(b, head)) continue;
@@ -1151,6 +1153,20 @@ static void absorb(Plan& p) {
         if (si >= 0) {
             B.absorb_stage = si;
             p.stages[si].producer = b;
+        }
+        if (infer && si >= 0) {
+            // no backward pass reads the fp32 relu output here: when the staged convolutions are its only readers it is not written
+            bool fp32_read = head_is_output((int)i, R.bytes);
+            for (auto& u : readers_of_head((int)i, R.bytes))
+                if (std::find(p.stages[si].users.begin(), p.stages[si].users.end(), u) == p.stages[si].users.end()) fp32_read = true;
+            if (!fp32_read) {
+                B.absorb_skip = true;
+                if (R.buf) {
+                    cudaFree(R.buf);
+                    R.buf = nullptr;
+                    p.device_bytes -= R.bytes;
+                }
+            }
         }
     }
     for (size_t si = 0; si < p.stages.size(); ++si) {

@@ -38,7 +38,17 @@ def attach(pool_bytes, device, group=None):
         failure = e
     # Every rank must take the same exchange: a rank that fell back to NCCL alone would wait in ncclAllReduce for peers that
     # sit in the multicast kernel's flag barrier.  One collective vote (it doubles as the barrier behind the zero fill).
-    if not all_agree(failure is None, group, device):
+    try:
+        agreed = all_agree(failure is None, group, device)
+    except Exception as e:   # the vote itself could not run: decide locally, like a single rank would
+        import sys
+        sys.stderr.write("dopt_b200.symm: exchange vote failed (%r)\n" % (e,))
+        agreed = failure is None
+        try:
+            dist.barrier(group)
+        except Exception:
+            pass
+    if not agreed:
         import sys
         sys.stderr.write("dopt_b200.symm: symmetric memory not available on every rank (here: %r); using NCCL\n" % (failure,))
         return None

@@ -215,3 +215,34 @@ def test_wrn_test_time_plan_against_the_oracle(mode, tol):
     np.testing.assert_array_equal(got, again)                      # a test-time plan has no state: idempotent
     assert float(np.abs(got - want).max()) <= tol, float(np.abs(got - want).max())
     assert np.allclose(got.sum(axis=1), 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode,loss_rtol,prob_tol,param_tol", [("fp32", 2e-4, 2e-3, 5e-3), ("bf16", 2e-2, 3e-2, None),
+                                                               ("interior", 2e-2, 3e-2, None)])
+def test_mnist_cnn_adam_at_baseline_size_against_the_oracle(mode, loss_rtol, prob_tol, param_tol):
+    """BASELINE.json configs[1] at its full size -- examples/mnist.d:35-58: conv5x5(32)-relu-pool-conv5x5(32)-relu-pool-dense(10)-
+    softmax on 100 x 1 x 28 x 28, Adam 1e-3 -- where the CPU oracle still finishes a step in about a second: three training steps
+    side by side, losses and class probabilities every step, and in fp32 the parameters at the end."""
+    from oracle import graph_eval as G
+    math, flags = MODES[mode]
+    H.set_math(math)
+    H.set_plan_flags(flags)
+    H.seed(12)
+    x, y = H.float32((100, 1, 28, 28)), H.float32((100, 10))
+    l = H.data_source(x).conv2d(32, (5, 5)).relu().max_pool((2, 2)).conv2d(32, (5, 5)).relu().max_pool((2, 2)).dense(10).softmax()
+    net = H.Network([x], [l])
+    loss = H.cross_entropy(l.train_output, y) + net.param_loss
+    upd = H.Updater(H.ADAM, [loss, l.train_output], network=net, hyper=[H.float32((), [1e-3]), None, None, None])
+    oracle = G.UpdaterOracle(upd)
+    rng = np.random.RandomState(5)
+    data = [(rng.rand(100, 1, 28, 28).astype(F), np.eye(10, dtype=F)[rng.randint(0, 10, 100)]) for _ in range(3)]
+    for s in range(3):
+        args = {x: data[s][0], y: data[s][1]}
+        got, want = upd.step(args), oracle.step(args)
+        assert abs(float(got[0]) - float(want[0])) <= loss_rtol * max(1.0, abs(float(want[0]))), (s, got[0], want[0])
+        assert float(np.abs(got[1] - want[1]).max()) <= prob_tol, (s, float(np.abs(got[1] - want[1]).max()))
+    if param_tol is not None:
+        for p in net.params:
+            gv, wv = p.get(), oracle.value_of(p)
+            scale = max(float(np.abs(wv).max()), 1e-3)
+            assert float(np.abs(gv - wv).max()) <= param_tol * scale, (p.shape, float(np.abs(gv - wv).max()), scale)

@@ -296,6 +296,71 @@ def test_wrn_28_10_headline_graph_inventory():
     assert strides.count((2, 2)) == 4 and strides.count((1, 1)) == 24
 
 
+def test_vgg19_batchnorm_cifar10_graph_inventory():
+    """BASELINE configs[2] -- vgg19(features, [512, 512]).dense(10).softmax() with batchnorm on 100 x 3 x 32 x 32
+    (examples/cifar10.d:54-66) -- pinned against nnet/source/dopt/nnet/models/vgg.d:67-75,104-134 independently of the mirror:
+    the expected inventory is derived from the D source's size list (conv3x3 pad 1 with bias -> batchNorm -> relu per entry,
+    maxPool [2,2] per -1, then dense + relu per top size)."""
+    sizes = [64, 64, -1, 128, 128, -1, 256, 256, 256, 256, -1, 512, 512, 512, 512, -1, 512, 512, 512, 512, -1]
+    want_convs, cin, elems = [], 3, 0
+    for sz in sizes:
+        if sz == -1:
+            continue
+        want_convs.append((sz, cin, 3, 3))
+        elems += sz * cin * 9 + sz + 4 * sz          # filter, bias, batchNorm scale / bias / mean / var
+        cin = sz
+    elems += (512 * 512 + 512) * 2 + 10 * 512 + 10
+    assert len(want_convs) == 16 and elems == 20576842
+    H.seed(1)
+    x, labels = H.float32((100, 3, 32, 32)), H.float32((100, 10))
+    preds = H.vgg19(x, dense_sizes=(512, 512), batchnorm=True).dense(10).softmax()
+    net = H.Network([x], [preds])
+    assert sum(p.volume for p in net.params) == elems
+    assert sorted(tuple(p.shape) for p in net.params if len(p.shape) == 4 and p.shape[0] != 1) == sorted(want_convs)
+    assert sorted(tuple(p.shape) for p in net.params if len(p.shape) == 2) == [(10, 512), (512, 512), (512, 512)]
+    loss = H.cross_entropy(preds.train_output, labels) + net.param_loss
+    upd = H.Updater(H.SGD, [loss, preds.train_output], network=net, hyper=[H.float32((), [0.01]), H.float32((), [0.9])])
+    nodes = H.export(upd.plan_outputs()[0])
+    ts = [nd["type"] for nd in nodes]
+    assert ts.count("convolution") == 16 and ts.count("convolutionFiltersGrad") == 16 and ts.count("convolutionFeaturesGrad") == 15
+    assert ts.count("batchNormTrain") == 16 and ts.count("batchNormGrad") == 16
+    assert ts.count("maxpool") == 5 and ts.count("maxpoolGrad") == 5
+    # (a dense layer adds its bias as a broadcast matmul + add, nnet/layers/dense.d; only the convolutions use addBias)
+    assert ts.count("addBias") == 16 and ts.count("addBiasGrad") == 16 and ts.count("relu") == 16 + 2
+    pools = sorted(tuple(nd["shape"][2:]) for nd in nodes if nd["type"] == "maxpool")
+    assert pools == [(1, 1), (2, 2), (4, 4), (8, 8), (16, 16)]        # 32 x 32 halves five times: the last maps are 2 x 2
+
+
+def test_sins_wrn_16_8_graph_inventory():
+    """BASELINE configs[4] -- wideResNet(features, 16, 8, stride [2,2,2]).dense(10).softmax() on 50 x 3 x 96 x 96
+    (examples/sins10.d:42-52) -- against nnet/source/dopt/nnet/models/wrn.d:56-199: two blocks per group, a 1x1 shortcut where the
+    channel count changes, every group's first block strided, so the maps are 48 x 48, 24 x 24 and 12 x 12."""
+    depth, width, classes = 16, 8, 10
+    n = (depth - 4) // 6
+    want_convs, bn_channels = [(16, 3, 3, 3)], []
+    for cin, u in [(16, 16 * width), (16 * width, 32 * width), (32 * width, 64 * width)]:
+        c = cin
+        for _ in range(n):
+            bn_channels += [c, u]
+            want_convs += [(u, c, 3, 3), (u, u, 3, 3)]
+            if c != u:
+                want_convs.append((u, c, 1, 1))
+            c = u
+    bn_channels.append(64 * width)
+    elems = sum(int(np.prod(sh)) for sh in want_convs) + 4 * sum(bn_channels) + 64 * width * classes + classes
+    assert len(want_convs) == 16 and len(bn_channels) == 13 and elems == 10968570
+    H.seed(1)
+    x = H.float32((50, 3, 96, 96))
+    preds = H.wide_resnet(x, depth, width, stride=(2, 2, 2)).dense(classes).softmax()
+    net = H.Network([x], [preds])
+    assert sum(p.volume for p in net.params) == elems
+    assert sorted(tuple(p.shape) for p in net.params if len(p.shape) == 4 and p.shape[0] != 1) == sorted(want_convs)
+    nodes = H.export([preds.train_output])
+    convs = [nd for nd in nodes if nd["type"] == "convolution"]
+    assert sorted(tuple(nd["attrs"]["stride"]) for nd in convs).count((2, 2)) == 6        # three 3x3 + three 1x1 shortcuts
+    assert sorted(set(tuple(nd["shape"][2:]) for nd in convs)) == [(12, 12), (24, 24), (48, 48), (96, 96)]
+
+
 def test_dropout_layer_graph():
     """nnet/layers/dropout.d:14-29: train output = (uniform > p) * x, test output = x * (1 - p); the mask is not
     differentiable, so the gradient wrt x is parentGrad * mask."""

@@ -325,7 +325,7 @@ def test_vgg19_batchnorm_cifar10_graph_inventory():
     assert ts.count("convolution") == 16 and ts.count("convolutionFiltersGrad") == 16 and ts.count("convolutionFeaturesGrad") == 15
     assert ts.count("batchNormTrain") == 16 and ts.count("batchNormGrad") == 16
     assert ts.count("maxpool") == 5 and ts.count("maxpoolGrad") == 5
-    # (a dense layer adds its bias as a broadcast matmul + add, nnet/layers/dense.d; only the convolutions use addBias)
+    # (a dense layer adds its bias as `y + bias.repeat(N)`, nnet/layers/dense.d:143; only the convolutions use addBias)
     assert ts.count("addBias") == 16 and ts.count("addBiasGrad") == 16 and ts.count("relu") == 16 + 2
     pools = sorted(tuple(nd["shape"][2:]) for nd in nodes if nd["type"] == "maxpool")
     assert pools == [(1, 1), (2, 2), (4, 4), (8, 8), (16, 16)]        # 32 x 32 halves five times: the last maps are 2 x 2

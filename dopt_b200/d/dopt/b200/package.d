@@ -57,6 +57,25 @@ extern(C) nothrow @nogc
     int dopt_b200_plan_execute(dopt_b200_plan_t p, const(int)* varIds, const(void*)* varPtrs, const(int)* varOnHost, int nVars,
                                void** rets, int nRets, void* stream);
     int dopt_b200_plan_destroy(dopt_b200_plan_t p);
+    int dopt_b200_plan_stats(dopt_b200_plan_t p, long* launches, long* deviceBytes, long* loweredNodes);
+    int dopt_b200_plan_profile(dopt_b200_plan_t p, int enable, char* buf, size_t bufLen);   // CUDAPlan.profiler (package.d:265)
+    int dopt_b200_plan_replay_class(dopt_b200_plan_t p, const(char)* opTypes, int reps, double* usecPerRep, long* launchesPerRep,
+                                    void* stream);                                         // measurement aid, no counterpart
+
+    const(char)* dopt_b200_version();
+    int dopt_b200_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t* totalMem);
+    int dopt_b200_has_operation(const(char)* opType);
+    // what DOPT_B200_MATH_DEFAULT resolves to: 1 = strict fp32 kernels (the reference's arithmetic), 2 = bf16 tensor cores (default)
+    void dopt_b200_set_default_math(int math);
+
+    // the dopt.online update rules as direct entry points (optional: the plan fuses the update graphs of sgd.d / adam.d /
+    // amsgrad.d on its own; these serve a host that keeps its own training loop)
+    struct dopt_b200_param { float* w; const(float)* g; float* s0; float* s1; float* s2; long n; }
+    int dopt_b200_sgd_update(const(dopt_b200_param)* params, int nParams, const(float)* lr, const(float)* momentum, int nesterov,
+                             float gradScale, void* stream);
+    int dopt_b200_adam_update(const(dopt_b200_param)* params, int nParams, const(float)* alpha, const(float)* beta1,
+                              const(float)* beta2, const(float)* eps, float* b1, float* b2, int amsgrad, float gradScale,
+                              void* stream);
 
     // on-device input pipeline (replaces the host loops of nnet/data/cifar.d:50-55 and nnet/data/imagetransformer.d:45-138)
     struct dopt_b200_jitter { int x_off, y_off, flip_x, flip_y; }
@@ -85,6 +104,16 @@ extern(C) nothrow @nogc
 enum DOPT_B200_PLAN_FUSE = 1;
 enum DOPT_B200_PLAN_CUDA_GRAPH = 2;
 enum DOPT_B200_PLAN_BF16_INTERIOR = 4;   // activations between tensor-core convolutions stay NHWC bf16 (include/dopt_b200.h)
+
+enum DOPT_B200_MATH_FP32 = 1;
+enum DOPT_B200_MATH_BF16 = 2;
+
+/// Arithmetic of convolution* and large matmul: `setMath(DOPT_B200_MATH_FP32)` gives the reference's strict fp32 results (1e-4 of
+/// cuDNN / cuBLAS), the default is bf16 operands with fp32 accumulation on the tensor cores (include/dopt_b200.h, "NOTE").
+void setMath(int math)
+{
+    dopt_b200_set_default_math(math);
+}
 
 private void check(int rc)
 {

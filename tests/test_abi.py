@@ -34,6 +34,29 @@ def test_header_symbols_are_exported():
         assert getattr(raw, name) is not None, name
 
 
+def test_d_glue_declares_only_what_the_header_declares():
+    """dopt_b200/d/dopt/b200/package.d cannot be compiled here (no D toolchain): at least its extern(C) block must stay in step
+    with the header -- every function it names exists there with the same number of parameters, and every entry point a dopt
+    host needs (kernels, plans, communicator, input pipeline, math mode) is declared in it."""
+    def functions(text):
+        text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)       # comments mention entry points too
+        text = re.sub(r"//[^\n]*", " ", text)
+        out = {}
+        for m in re.finditer(r"\b(dopt_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, re.S):
+            args = m.group(2).strip()
+            out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+    header = functions(open(os.path.join(ROOT, "include", "dopt_b200.h")).read())
+    glue_src = open(os.path.join(ROOT, "dopt_b200", "d", "dopt", "b200", "package.d")).read()
+    glue = functions(glue_src[glue_src.index("extern(C)"):glue_src.index("enum DOPT_B200_PLAN_FUSE")])
+    assert len(glue) >= 30
+    for name, n_args in glue.items():
+        assert name in header, name
+        assert header[name] == n_args, (name, header[name], n_args)
+    missing = set(header) - set(glue) - {"dopt_b200_launch_count", "dopt_b200_tc_profile"}    # bench.py's counters
+    assert not missing, missing
+
+
 def test_every_reference_op_has_a_kernel():
     ops = set(db.list_operations())
     for name in REFERENCE_CUDA_OPS + FALLBACK_OPS_NOW_ON_GPU:

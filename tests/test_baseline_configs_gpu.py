@@ -151,9 +151,9 @@ def _check_config(name, build, kind, hyper, prob_tol=3e-2, bounds=FIRST_BF16):
 # VGG19 is a plain 19-layer stack: nothing like a Wide ResNet's identity paths carries the signal past a layer, so the bf16
 # rounding of every convolution (~1e-2 of the output's rms) compounds, and in the backward pass every relu gate and every
 # max-pool argmax that the forward noise flipped re-routes a gradient element outright.  Measured on a B200 (profiles/r02_summary.md,
-# "BASELINE configs at full size"): loss 3.6669 against 3.6739, class probabilities 0.005 apart on average (0.07 at worst, the
-# arg max agrees on 96 of 100 images); first-step update errors grow smoothly from the classifier (dense 0.09) to the first
-# convolution (0.59) and its batch norm (0.78) -- still clearly the same direction (an unrelated gradient gives 1.41).  Every
+# "End of round"): loss 3.6669 against 3.6739, class probabilities 0.005 apart on average (0.07 at worst, the
+# arg max agrees on 96 of 100 images); first-step update errors grow smoothly from the classifier (dense 0.09) through the last
+# convolution (0.37, right under the 2 x 2 -> 1 x 1 pool) to the first convolution (0.59) and its batch norm (0.78), no jump at any layer -- still clearly the same direction (an unrelated gradient gives 1.41).  Every
 # convolution / batch-norm / pooling shape of this network ALSO passes the op-level comparison with the replayed cuDNN calls
 # (tests/test_cudnn_replay_gpu.py), and a narrow VGG follows the fp32 oracle step by step (tests/test_plan_gpu.py): these
 # bounds guard the assembly at full size -- one wrong layer in a plain stack decorrelates everything above it.
